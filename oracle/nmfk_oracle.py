@@ -1,0 +1,568 @@
+"""CPU oracle: a NumPy restatement of the NMFk.jl factorization hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the product: only
+``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
+legs of ``bench.py`` may import it, and there only as the checker or as the timed CPU
+baseline.  The product path (``nmfk.jl_b200/``) never imports this module and fails loudly
+when its CUDA library is missing.
+
+PARITY PINNING STATUS ("parity unpinned" for per-iteration values):
+  The reference is 100 % Julia and no Julia runtime exists in this image or on the GPU box,
+  so the reference itself cannot be executed, and its own tests hold no numeric fixtures for
+  this path.  What *is* pinned (tests/test_oracle_known_answers.py):
+    * the recorded outputs of the reference on the blind-source-separation notebook
+      (`notebooks/blind_source_separation/blind_source_separation.md:170-264`): X is printed
+      there to 6 digits; the k=2 fit 13.93858 / silhouette 0.994 / AIC -46.21 and kopt = 3
+      are reproduced by this oracle from its own random initialisations;
+    * the feature-extraction notebook decision kopt = 4
+      (`notebooks/feature_extraction/feature_extraction.md:208-292`);
+    * the invariants asserted by `test/test_execute_smoke.jl:6-32`,
+      `test/test_cluster_unit.jl:36-54`, `test/test_normalize.jl:44-55`,
+      `test/test_helpers.jl:60-67`.
+  Per-iteration W/H/fit values are NOT pinned by any reference artefact; they are defined by
+  this restatement (Float64, NumPy/OpenBLAS summation order).
+
+Every function cites the reference file:line it follows (paths relative to /root/reference).
+Third-party semantics that are not vendored in the reference tree are restated from the
+published packages and named where used:
+  * Distances.jl (compat 0.8-0.11, Project.toml:63): ``cosine_dist``, ``pairwise(CosineDist())``
+  * Clustering.jl (compat 0.14/0.15, Project.toml:55): ``silhouettes(assignments, dists)``
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+EPS64 = float(np.finfo(np.float64).eps)  # Julia `eps()` == eps(Float64), used for any T
+
+
+# --------------------------------------------------------------------------------------
+# Helpers: src/NMFkHelpers.jl
+# --------------------------------------------------------------------------------------
+def normnan(X: np.ndarray) -> float:
+    """`normnan` src/NMFkHelpers.jl:226-228 : LinearAlgebra.norm(X[.!isnan.(X)])."""
+    v = np.asarray(X)[~np.isnan(X)]
+    r = np.sqrt(np.sum(v.astype(np.float64) ** 2))
+    return float(np.float32(r)) if v.dtype == np.float32 else float(r)
+
+
+def ssqrnan(X: np.ndarray) -> float:
+    """`ssqrnan` src/NMFkHelpers.jl:222-224 : sum(X[.!isnan.(X)].^2)."""
+    v = np.asarray(X)[~np.isnan(X)]
+    return float(np.sum(v ** 2))
+
+
+def zerostoepsilon(X: np.ndarray) -> np.ndarray:
+    """`zerostoepsilon` src/NMFkHelpers.jl:529-543 : x < eps(T)^2 -> eps(T)^2 (copy)."""
+    Xn = np.array(X, copy=True)
+    e = np.finfo(Xn.dtype).eps ** 2
+    Xn[Xn < e] = e
+    return Xn
+
+
+# --------------------------------------------------------------------------------------
+# Solver: src/NMFkMultiplicative.jl
+# --------------------------------------------------------------------------------------
+class NegativeEntriesError(ValueError):
+    """ErrorException("All matrix entries must be nonnegative!") NMFkMultiplicative.jl:4-7."""
+
+
+def nmf_preprocessing(X: np.ndarray, lam: float = 1e-32):
+    """`NMFpreprocessing!` src/NMFkMultiplicative.jl:3-22.  Mutates X, returns (inan, izero).
+
+    `minimum(X)` propagates NaN in Julia (so does np.min), hence negative entries go
+    undetected when X also holds NaNs - kept as is.
+    """
+    if X.size and np.min(X) < 0:
+        raise NegativeEntriesError("All matrix entries must be nonnegative!")
+    izero = X <= 0
+    X[izero] = lam
+    inan = np.isnan(X)
+    X[inan] = lam
+    return inan, izero
+
+
+def _canon_partition(index: np.ndarray) -> np.ndarray:
+    """Canonical form of the co-clustering matrix `cons` (NMFkMultiplicative.jl:105):
+    cons[i,j] = (index[i]==index[j]) is determined by, for every column, the first column
+    that shares its argmin."""
+    first = {}
+    out = np.empty(len(index), dtype=np.int64)
+    for q, a in enumerate(index):
+        out[q] = first.setdefault(int(a), q)
+    return out
+
+
+def nmf_multiplicative(
+    X: np.ndarray,
+    k: int,
+    *,
+    weight=1,
+    tol: float = 1e-19,
+    tolOF: float = 1e-3,
+    lam: float = 1e-32,
+    maxreattempts: int = 2,
+    maxbaditers: int = 10,
+    maxiter: int = 1000000,
+    stopconv: int = 1000,
+    Wfixed: bool = False,
+    Hfixed: bool = False,
+    Winit: Optional[np.ndarray] = None,
+    Hinit: Optional[np.ndarray] = None,
+    rng: Optional[np.random.Generator] = None,
+    normalizevector: Optional[np.ndarray] = None,
+    trace: Optional[Callable[[int, np.ndarray, np.ndarray, Optional[float]], None]] = None,
+    info: Optional[dict] = None,
+):
+    """`NMFmultiplicative(X::AbstractMatrix, k)` src/NMFkMultiplicative.jl:24-127.
+
+    Mutates X during the run (lambda substitution, NaN imputation) and restores it before
+    returning, exactly like the reference.  `rng` stands in for Julia's global RNG
+    (draw order W then H, :38,:48).  `trace(iter, W, H, obj_or_None)` is called at the end of
+    the body of every iteration (so on the every-10th check iterations W,H carry the clamp of
+    :99-100 and obj is the value of :74; obj is None otherwise) - used for per-iteration parity.
+    Returns (W, H, objvalue) with objvalue the sum of squares of :125.
+    """
+    inan, izero = nmf_preprocessing(X, lam)  # :25
+    n, m = X.shape
+    if normalizevector is not None and len(normalizevector) == n:  # :27-31
+        X /= np.asarray(normalizevector).reshape(n, 1)
+    elif normalizevector is not None and len(normalizevector) != 0:
+        raise ValueError("Length of normalizing vector does not match")
+    if rng is None:
+        rng = np.random.default_rng()
+    if Winit is None or Winit.size == 0:  # :37-45
+        W = rng.random(n * k).reshape((n, k), order="F")
+    else:
+        assert Winit.shape == (n, k)
+        W = Winit
+        if np.isnan(W).any():
+            raise ValueError("Initial values for the W matrix entries include NaNs!")
+    if Hinit is None or Hinit.size == 0:  # :47-55
+        H = rng.random(k * m).reshape((k, m), order="F")
+    else:
+        assert Hinit.shape == (k, m)
+        H = Hinit
+        if np.isnan(H).any():
+            raise ValueError("Initial values for the H matrix entries include NaNs!")
+
+    consold = None  # falses(m, m): never equals a real `cons` (its diagonal is true) when m > 0
+    inc = 0
+    objvalue_best = np.inf
+    iters = 0
+    baditers = 0
+    reattempts = 0
+    stop_reason = "maxiter"
+    any_nan = bool(inan.any())
+    while iters < maxiter and baditers < maxbaditers and reattempts < maxreattempts:  # :64
+        iters += 1
+        if not Hfixed:  # :66-68
+            H = H * (W.T @ (X / (W @ H))) / np.sum(W, axis=0).reshape(k, 1)
+        if not Wfixed:  # :69-71
+            W = W * ((X / (W @ H)) @ H.T) / np.sum(H, axis=1).reshape(1, k)
+        WH = W @ H  # the reference forms W*H again for the imputation, :72
+        if any_nan:
+            X[inan] = WH[inan]
+        objvalue = None
+        if iters % 10 == 0:  # :73
+            objvalue = float(np.sum((((X - W @ H) * weight)[~inan]) ** 2))  # :74
+            if objvalue < tol:  # :75-78
+                stop_reason = "tol"
+                if trace is not None:
+                    trace(iters, W, H, objvalue)
+                break
+            if objvalue < objvalue_best:  # :79-88
+                if (objvalue_best - objvalue) < tolOF:
+                    baditers += 1
+                else:
+                    baditers = 0
+                objvalue_best = objvalue
+            else:
+                baditers += 1
+            if baditers >= maxbaditers:  # :90-98
+                reattempts += 1
+                baditers = 0
+            H = np.maximum(H, EPS64)  # :99
+            W = np.maximum(W, EPS64)  # :100
+            index = np.argmin(H, axis=0)  # :101-103 (first minimum, like Julia argmin)
+            cons = _canon_partition(index)  # :105
+            if consold is not None and np.array_equal(cons, consold):  # :106-111
+                inc += 1
+            else:
+                inc = 0
+            if inc > stopconv:  # :112-115
+                stop_reason = "consistency"
+                if trace is not None:
+                    trace(iters, W, H, objvalue)
+                break
+            consold = cons  # :116
+        if trace is not None:
+            trace(iters, W, H, objvalue)
+    else:
+        if iters >= maxiter:
+            stop_reason = "maxiter"
+        elif reattempts >= maxreattempts:
+            stop_reason = "reattempts"
+        else:
+            stop_reason = "baditers"
+    if normalizevector is not None and len(normalizevector) == n:  # :119-122
+        nv = np.asarray(normalizevector).reshape(n, 1)
+        X *= nv
+        W = W * nv
+    X[izero] = 0  # :123
+    X[inan] = np.nan  # :124
+    objvalue = float(np.sum((((X - W @ H) * weight)[~inan]) ** 2))  # :125
+    if info is not None:
+        info.update(iters=iters, stop_reason=stop_reason, baditers=baditers, reattempts=reattempts)
+    return W, H, objvalue
+
+
+# --------------------------------------------------------------------------------------
+# One restart as reached from execute: src/NMFkExecute.jl:729-807
+# --------------------------------------------------------------------------------------
+def execute_singlerun_compute(
+    X: np.ndarray,
+    nk: int,
+    *,
+    maxiter: int = 10000,
+    tol: float = 1e-19,
+    clusterWmatrix: bool = False,
+    modifymatrices: bool = True,
+    weight=1,
+    info: Optional[dict] = None,
+    **kw,
+):
+    """`execute_singlerun_compute(X::AbstractMatrix, nk; method=:simple, ...)`
+    src/NMFkExecute.jl:729-807 with scale=false, transpose=false, mixture=:null.
+    X is passed by reference (:740) and comes back restored.  Returns (W, H, objvalue) where
+    objvalue = normnan(X - W*H) (:791-792, a NORM) and rows of H sum to one (:800-804)."""
+    W, H, _ = nmf_multiplicative(X, nk, tol=tol, maxiter=maxiter, weight=weight, info=info, **kw)  # :762
+    E = X - W @ H  # :791
+    objvalue = normnan(E)  # :792
+    if modifymatrices:  # :795-805 (mixture == :null)
+        if clusterWmatrix:
+            total = np.sum(W, axis=0, keepdims=True)
+            W = W / total
+            H = H * total.T
+        else:
+            total = np.sum(H, axis=1, keepdims=True)
+            W = W * total.T
+            H = H / total
+    return W, H, objvalue
+
+
+# --------------------------------------------------------------------------------------
+# Third-party semantics (Distances.jl, Clustering.jl), restated
+# --------------------------------------------------------------------------------------
+def cosine_dist(a: np.ndarray, b: np.ndarray) -> float:
+    """Distances.cosine_dist(a,b) = max(1 - a.b / (sqrt(a.a) * sqrt(b.b)), 0)
+    (Distances.jl `CosineDist` eval_reduce/eval_end), call site src/NMFkCluster.jl:470."""
+    ab = float(np.dot(a, b))
+    a2 = float(np.dot(a, a))
+    b2 = float(np.dot(b, b))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        v = np.float64(1.0) - np.float64(ab) / (np.sqrt(np.float64(a2)) * np.sqrt(np.float64(b2)))
+    if math.isnan(v):
+        return float("nan")
+    return float(max(v, 0.0))
+
+
+def pairwise_cosine_rows(V: np.ndarray) -> np.ndarray:
+    """Distances.pairwise(CosineDist(), V; dims=1) (Distances.jl `_pairwise!(r, ::CosineDist, a)`):
+    Gram matrix by BLAS, r[i,j] = max(1 - G[i,j]/(sqrt(G[i,i])*sqrt(G[j,j])), 0), diagonal forced
+    to 0, symmetric.  Call site src/NMFkFinalize.jl:52."""
+    G = V @ V.T
+    nrm = np.sqrt(np.diag(G))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        D = 1.0 - G / (nrm[:, None] * nrm[None, :])
+    D = np.where(np.isnan(D), D, np.maximum(D, 0.0))
+    # lower triangle is computed, upper is its mirror, diagonal is exactly zero
+    iu = np.triu_indices(V.shape[0], 1)
+    D[iu] = D.T[iu]
+    np.fill_diagonal(D, 0.0)
+    return D
+
+
+def silhouettes(assignments: np.ndarray, dists: np.ndarray) -> np.ndarray:
+    """Clustering.silhouettes(assignments, dists) (Clustering.jl 0.14/0.15 `silhouettes.jl`):
+    r[c,j] = sum_{i != j, a_i = c} dists[i,j]; divided by counts[c] - (c == a_j) (0 if that
+    is 0); a = r[a_j,j]; b = min_{c != a_j} r[c,j]; s = a<b ? 1-a/b : a>b ? b/a-1 : 0;
+    s = 0 for singleton clusters.  assignments are 1-based.  Call site NMFkFinalize.jl:55."""
+    a_ = np.asarray(assignments, dtype=np.int64) - 1
+    n = len(a_)
+    k = int(a_.max()) + 1
+    if k < 2:
+        raise ValueError("silhouettes() not defined for the degenerated clustering with a single cluster.")
+    counts = np.bincount(a_, minlength=k)
+    onehot = np.zeros((k, n), dtype=dists.dtype)
+    onehot[a_, np.arange(n)] = 1
+    D = np.array(dists, copy=True)
+    np.fill_diagonal(D, 0.0)  # the i == j term is skipped
+    r = onehot @ D  # r[c, j]
+    for j in range(n):
+        for c in range(k):
+            cnt = counts[c] - (1 if c == a_[j] else 0)
+            r[c, j] = 0.0 if cnt == 0 else r[c, j] / cnt
+    sil = np.zeros(n, dtype=r.dtype)
+    for j in range(n):
+        l = a_[j]
+        a = r[l, j]
+        others = np.delete(r[:, j], l)
+        # typemax start + strict '<' scan == plain minimum (NaN never wins a '<')
+        b = np.inf
+        for v in others:
+            if v < b:
+                b = v
+        if counts[l] == 1:
+            sil[j] = 0
+        else:
+            sil[j] = (1 - a / b) if a < b else ((b / a - 1) if a > b else 0.0)
+    return sil
+
+
+# --------------------------------------------------------------------------------------
+# Solution clustering: src/NMFkCluster.jl:425-517
+# --------------------------------------------------------------------------------------
+def clustersolutions(factors: Sequence[np.ndarray], clusterWmatrix: bool = False):
+    """`clustersolutions(factors, clusterWmatrix=false)` src/NMFkCluster.jl:425-517.
+    Returns (labels k x R, 1-based; centroids)."""
+    if not clusterWmatrix:
+        factors = [np.array(f.T, copy=True) for f in factors]  # :427
+    else:
+        factors = [np.array(f, copy=True) for f in factors]
+    numTrials = len(factors)
+    r, k = factors[0].shape
+    for w in factors:
+        assert w.shape == (r, k)
+    needZeroFix = any(np.min(np.sum(f, axis=0)) == 0 for f in factors)  # :437-444
+    if needZeroFix:  # :445-450
+        factors = [np.vstack([f, np.ones((1, k), dtype=f.dtype)]) for f in factors]
+    cent = factors[0]  # centSeeds and newClusterCenters alias factors[1], :453-455
+    labels = np.zeros((k, numTrials), dtype=np.int64)
+    labels[:, 0] = np.arange(1, k + 1)  # :461
+    D = np.empty((k, k), dtype=factors[0].dtype)
+    for trial in range(1, numTrials):  # :464
+        Wt = factors[trial]
+        for c in range(k):  # :467-472
+            centroid = cent[:, c].copy()
+            for f in range(k):
+                D[f, c] = cosine_dist(Wt[:, f], centroid)
+        D[np.isnan(D)] = 0  # :473
+        while np.min(D) < np.inf:  # :474-485
+            flat = int(np.argmin(D.T))  # column-major first minimum
+            c, f = divmod(flat, k)
+            labels[f, trial] = c + 1
+            D[f, :] += np.inf
+            D[:, c] += np.inf
+            cent[:, c] += Wt[:, f]
+    while labels.min() == 0:  # :487-496
+        flat = int(np.argmin(labels.T))
+        trial, idx = divmod(flat, k)
+        if labels[:, trial].sum() == 0:
+            labels[:, trial] = np.arange(1, k + 1)
+        else:
+            labels[idx, trial] = idx + 1
+    cent = cent / numTrials  # :512
+    return labels, cent.T  # :516
+
+
+# --------------------------------------------------------------------------------------
+# finalize: src/NMFkFinalize.jl:36-79
+# --------------------------------------------------------------------------------------
+def finalize(Wa: Sequence[np.ndarray], Ha: Sequence[np.ndarray], idx: np.ndarray, clusterWmatrix: bool = False):
+    """`finalize(Wa::Vector, Ha::Vector, idx::Matrix, clusterWmatrix=false)`
+    src/NMFkFinalize.jl:36-79.  Returns (W, H, clustersilhouettes, Wvar, Hvar)."""
+    nNMF = len(Wa)
+    nP = Wa[0].shape[0]
+    nk, nC = Ha[0].shape
+    idx_r = idx.reshape(-1, order="F")  # :43
+    if clusterWmatrix:
+        V = zerostoepsilon(np.hstack(Wa)).T  # pairwise over columns == rows of the transpose
+    else:
+        V = zerostoepsilon(np.vstack(Ha))  # :52
+    Dm = pairwise_cosine_rows(V)
+    Dm[np.isnan(Dm)] = 0  # :53-54
+    sil = silhouettes(idx_r, Dm).reshape((nk, nNMF), order="F")  # :55
+    sil[np.isnan(sil)] = 0  # :58
+    dt = Ha[0].dtype
+    clustersil = np.empty((nk, 1), dtype=dt)
+    W = np.empty((nP, nk), dtype=dt)
+    H = np.empty((nk, nC), dtype=dt)
+    Wvar = np.empty((nP, nk), dtype=dt)
+    Hvar = np.empty((nk, nC), dtype=dt)
+    for c in range(1, nk + 1):  # :64-77
+        mask = idx == c
+        clustersil[c - 1, 0] = np.mean(sil.T[mask.T])  # column-major order of findall
+        # idxkk: for every (row a, trial t) with idx[a,t] == c, in column-major order, the row a
+        cm = [(a, t) for t in range(nNMF) for a in range(nk) if idx[a, t] == c]
+        idxkk = [a for a, _ in cm]
+        # map((i, j)->Wa[i][:, j], 1:nNMF, idxkk) zips trial i with the i-th hit's row
+        ws = np.stack([Wa[i][:, j] for i, j in zip(range(nNMF), idxkk)], axis=1)
+        hs = np.stack([Ha[i][j, :] for i, j in zip(range(nNMF), idxkk)], axis=1)
+        H[c - 1, :] = hs.mean(axis=1)
+        W[:, c - 1] = ws.mean(axis=1)
+        Wvar[:, c - 1] = ws.var(axis=1, ddof=1) if ws.shape[1] > 1 else np.nan
+        Hvar[c - 1, :] = hs.var(axis=1, ddof=1) if hs.shape[1] > 1 else np.nan
+    return W, H, clustersil, Wvar, Hvar
+
+
+# --------------------------------------------------------------------------------------
+# k selection and ordering: src/NMFkPostprocess.jl:7-41, 148-158
+# --------------------------------------------------------------------------------------
+def getk(nkrange: Sequence[int], robustness: Sequence[float], cutoff: float = 0.5, strict: bool = True):
+    """`getk` src/NMFkPostprocess.jl:7-41.  `robustness` has one entry per element of nkrange
+    (the caller indexes `robustness[nkrange]`, NMFkExecute.jl:225).  Returns k, 0 or None."""
+    nkrange = list(nkrange)
+    robustness = np.asarray(robustness, dtype=float)
+    if len(nkrange) != len(robustness):  # :8-10
+        robustness = robustness[np.asarray(nkrange) - 1]
+    if np.all(np.isnan(robustness)):  # :11-13
+        return 0
+    if len(nkrange) == 1:  # :14-23
+        if strict:
+            return nkrange[-1] if robustness[-1] > cutoff else None
+        return nkrange[-1]
+    hits = np.flatnonzero(robustness > cutoff)  # :25
+    if len(hits) == 0:
+        if strict:
+            return None
+        rb = np.where(np.isnan(robustness), -np.inf, robustness)
+        return nkrange[int(np.argmax(rb))]
+    return nkrange[int(hits[-1])]
+
+
+def signalorder(W: np.ndarray, H: np.ndarray) -> np.ndarray:
+    """`signalorder` src/NMFkPostprocess.jl:148-158 : sortperm(sum(W[:,i]*H[i,:]); rev=true).
+    Returns 0-based indices."""
+    k = W.shape[1]
+    assert k == H.shape[0]
+    s = np.array([np.sum(np.outer(W[:, i], H[i, :])) for i in range(k)])
+    return np.argsort(-s, kind="stable")
+
+
+# --------------------------------------------------------------------------------------
+# execute_run / execute: src/NMFkExecute.jl:483-711, 178-329
+# --------------------------------------------------------------------------------------
+def execute_run(
+    X: np.ndarray,
+    nk: int,
+    nNMF: int,
+    *,
+    clusterWmatrix: bool = False,
+    weight=1,
+    seed: Optional[int] = None,
+    inits: Optional[Sequence] = None,
+    init_fn: Optional[Callable[[int, int, int, int], tuple]] = None,
+    details: Optional[dict] = None,
+    **kw,
+):
+    """`execute_run(X::AbstractMatrix, nk, nNMF; ...)` src/NMFkExecute.jl:483-711 with the
+    defaults acceptratio=1, acceptfactor=Inf, nanaction=:zeroed, best=true, serial.
+
+    Initialisations: the reference draws from Julia's RNG (seed+i per restart when `seed` is
+    given, :532-537).  Here `inits[i] = (Winit, Hinit)` or `init_fn(i, n, nk, m)` (i is the
+    1-based restart number) supply them explicitly (inject Winit/Hinit).
+    Returns (Wa, Ha, phi, minsilhouette, aic)."""
+    T = X.dtype
+    n, m = X.shape
+    modifymatrices = not ("Wfixed" in kw or "Hfixed" in kw)  # :486-489
+    WBig, HBig, objvalue, iters = [], [], np.empty(nNMF, dtype=T), []
+    for i in range(1, nNMF + 1):  # :534-542
+        kwi = dict(kw)
+        if inits is not None:
+            kwi["Winit"], kwi["Hinit"] = inits[i - 1]
+        elif init_fn is not None:
+            kwi["Winit"], kwi["Hinit"] = init_fn(i, n, nk, m)
+        elif seed is not None:
+            kwi["rng"] = np.random.Generator(np.random.Philox(key=seed + i))
+        inf = {}
+        W, H, of = execute_singlerun_compute(X, nk, modifymatrices=modifymatrices, clusterWmatrix=clusterWmatrix,
+                                             weight=weight, info=inf, **kwi)
+        WBig.append(np.asarray(W, dtype=T))  # stored into Vector{Matrix{T}}, :529-536
+        HBig.append(np.asarray(H, dtype=T))
+        objvalue[i - 1] = of
+        iters.append(inf.get("iters", 0))
+    idxsort = np.argsort(objvalue, kind="stable")  # :545 sortperm
+    bestIdx = int(idxsort[0])
+    Wbest = WBig[bestIdx].copy()
+    Hbest = HBig[bestIdx].copy()
+    for i in idxsort:  # nanaction == :zeroed, :566-580
+        WBig[i][np.isnan(WBig[i])] = 0
+        HBig[i][np.isnan(HBig[i])] = 0
+    minsilhouette = 1
+    labels = None
+    clustersil = None
+    if nk > 1:  # :618-645
+        Ws = [WBig[i] for i in idxsort]
+        Hs = [HBig[i] for i in idxsort]
+        labels, centroids = clustersolutions(Ws if clusterWmatrix else Hs, clusterWmatrix)  # :620-624
+        ci = labels[:, 0]
+        for i, c in enumerate(ci):  # :631-635
+            Wbest[:, i] = WBig[bestIdx][:, c - 1]
+            Hbest[i, :] = HBig[bestIdx][c - 1, :]
+        _, _, clustersil, _, _ = finalize(Ws, Hs, labels, clusterWmatrix)  # :637
+        minsilhouette = T.type(np.min(clustersil))  # :638
+    Wa, Ha = Wbest, Hbest  # best == true, :655-658
+    E = X - Wa @ Ha  # :664
+    E[np.isnan(E)] = 0  # :667
+    phi_final = normnan(E)  # :668
+    numobservations = int(np.sum(~np.isnan(X)))  # :697
+    numparameters = Wa.size + Ha.size  # :698
+    with np.errstate(divide="ignore"):
+        aic = 2 * numparameters + numobservations * math.log(phi_final / numobservations) if phi_final > 0 else -math.inf  # :708
+    if details is not None:
+        details.update(objvalue=objvalue, idxsort=idxsort, labels=labels, clustersil=clustersil, iters=np.asarray(iters),
+                       WBig=WBig, HBig=HBig)
+    return Wa, Ha, T.type(phi_final), minsilhouette, aic
+
+
+def execute_k(X, nk, nNMF=10, *, ordersignals=True, **kw):
+    """`execute(X, nk::Integer, nNMF)` src/NMFkExecute.jl:236-329 without the file cache
+    (load=false, save=false).  Returns (W[:,so], H[so,:], fit, robustness, aic)."""
+    if X.size == 0:
+        raise ValueError("Input array has a zero dimension!")  # :242-244
+    if "Wfixed" in kw or "Hfixed" in kw:  # :305-307
+        ordersignals = False
+    W, H, fit, rob, aic = execute_run(X, nk, nNMF, **kw)  # :309
+    so = signalorder(W, H) if ordersignals else np.arange(W.shape[1])  # :311-318
+    return W[:, so], H[so, :], fit, rob, aic
+
+
+def execute(X, nkrange, nNMF=10, *, cutoff=0.5, per_k_kw: Optional[Callable[[int], dict]] = None, **kw):
+    """`execute(X, nkrange, nNMF; cutoff=0.5, ...)` src/NMFkExecute.jl:178-233 without file IO.
+    Returns (W dict-by-k, H dict-by-k, fitquality[maxk], robustness[maxk], aic[maxk], kopt)."""
+    nkrange = list(nkrange)
+    T = X.dtype
+    maxk = max(nkrange)
+    W, H = {}, {}
+    fitquality = np.zeros(maxk, dtype=T)
+    robustness = np.zeros(maxk, dtype=T)
+    aic = np.zeros(maxk, dtype=T)
+    fitquality[0] = np.inf  # :200
+    robustness[0] = -1  # :201
+    for nk in nkrange:  # :203-205
+        kwk = dict(kw)
+        if per_k_kw is not None:
+            kwk.update(per_k_kw(nk))
+        W[nk], H[nk], fitquality[nk - 1], robustness[nk - 1], aic[nk - 1] = execute_k(X, nk, nNMF, **kwk)
+    idx = np.asarray(nkrange) - 1
+    if np.all(np.isinf(fitquality[idx])):  # :206-208
+        kopt = 0
+    else:
+        for nk in nkrange:  # :211-222
+            fitquality[nk - 1] = normnan(X - W[nk] @ H[nk])
+        kopt = getk(nkrange, robustness[idx], cutoff)  # :225
+    return W, H, fitquality, robustness, aic, kopt
+
+
+# --------------------------------------------------------------------------------------
+# Deterministic initialisations shared by the parity tests and the bench harness
+# (restart i uses Philox(key=seed0+i), draws W (column-major) then H)
+# --------------------------------------------------------------------------------------
+def philox_init(seed0: int, i: int, n: int, k: int, m: int, dtype=np.float64):
+    rng = np.random.Generator(np.random.Philox(key=seed0 + i))
+    W = rng.random(n * k).reshape((n, k), order="F").astype(dtype)
+    H = rng.random(k * m).reshape((k, m), order="F").astype(dtype)
+    return W, H

@@ -1,0 +1,146 @@
+"""Pins the CPU oracle against every known answer the reference holds for this path
+(SURVEY.md §8c).  CPU-only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import nmfk_oracle as o
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def bss_X():
+    return np.loadtxt(os.path.join(HERE, "golden", "bss_notebook_X.csv"), delimiter=",")
+
+
+def test_bss_notebook_recorded_outputs():
+    """notebooks/blind_source_separation/blind_source_separation.md:230-264 (reference's own
+    recorded run on the printed X): k=2 Fit 13.93858 (sum of squares in that NMFk version),
+    silhouette 0.994, AIC -46.21 (with phi = SSQ), kopt = 3, silhouette(4),(5) < 0.5."""
+    X = bss_X()
+    W, H, fit, rob, aic, kopt = o.execute(X, range(2, 6), 10, seed=2021)
+    assert kopt == 3
+    assert fit[1] ** 2 == pytest.approx(13.93858, rel=2e-3)
+    assert rob[1] > 0.95 and rob[2] > 0.5 and rob[3] < 0.5 and rob[4] < 0.5
+    # AIC formula of NMFkExecute.jl:708 evaluated with the notebook's phi (= SSQ there)
+    n, m = X.shape
+    assert 2 * (n * 2 + 2 * m) + n * m * np.log(13.93858 / (n * m)) == pytest.approx(-46.21209, abs=1e-4)
+    # and with this version's phi (= norm) it is what the oracle returns
+    assert aic[1] == pytest.approx(2 * (n * 2 + 2 * m) + n * m * np.log(fit[1] / (n * m)), rel=1e-12)
+    assert fit[2] < 0.1 and fit[3] < 0.1 and fit[4] < 0.1  # rank-3 data: k >= 3 fits
+
+
+def test_readme_example_kopt_is_3():
+    """Readme.md:97-131: a,b,c ~ U(0,1)^15, X = [a+3c, 10a+b, b, 5b+c, a+2b+5c] -> kopt = 3,
+    silhouette(2),(3) > 0.5 > silhouette(4),(5)."""
+    rng = np.random.Generator(np.random.Philox(key=2015))
+    a, b, c = rng.random(15), rng.random(15), rng.random(15)
+    X = np.stack([a + 3 * c, 10 * a + b, b, 5 * b + c, a + 2 * b + 5 * c], axis=1)
+    W, H, fit, rob, aic, kopt = o.execute(X, range(2, 6), 10, seed=100)
+    assert kopt == 3
+    assert rob[1] > 0.5 and rob[2] > 0.5 and rob[3] < 0.5 and rob[4] < 0.5
+    assert fit[0] == np.inf and rob[0] == -1  # NMFkExecute.jl:200-201
+
+
+def test_feature_extraction_kopt_is_4():
+    """notebooks/feature_extraction/feature_extraction.jl:10-24 + .md:208-292: three sines + one
+    random signal mixed by a fixed 4x10 H -> silhouettes high for k<=4, negative after, kopt=4.
+    (s4 comes from Julia's RNG there; drawn from Philox here.)  Range trimmed to 2:6 for time."""
+    t = np.arange(1, 101)
+    s1 = (np.sin(0.05 * t) + 1) / 2
+    s2 = (np.sin(0.3 * t) + 1) / 2
+    s3 = (np.sin(0.5 * t) + 1) / 2
+    s4 = np.random.Generator(np.random.Philox(key=2021)).random(100)
+    W0 = np.stack([s1, s2, s3, s4], axis=1)
+    H0 = np.array([[1, 5, 0, 0, 1, 1, 2, 1, 0, 2], [0, 1, 1, 5, 2, 1, 0, 0, 2, 3], [3, 0, 0, 1, 0, 1, 0, 5, 4, 3],
+                   [1, 1, 4, 1, 5, 0, 1, 1, 5, 3]], dtype=float)
+    X = W0 @ H0
+    W, H, fit, rob, aic, kopt = o.execute(X, range(2, 7), 10, seed=7)
+    assert kopt == 4
+    assert rob[3] > 0.9 and rob[4] < 0.5 and rob[5] < 0.5
+    # recovered H(k=4) rows sum to one (test_execute_smoke.jl:18-19) and match the
+    # row-normalised true H up to a permutation (Hmatrix-4.csv in the notebook directory)
+    He = H[4]
+    assert np.allclose(He.sum(axis=1), 1.0, atol=1e-4)
+    Hn = H0 / H0.sum(axis=1, keepdims=True)
+    for row in Hn:
+        assert min(np.abs(He - row).max(axis=1)) < 5e-2
+
+
+def test_execute_smoke_invariants():
+    """test/test_execute_smoke.jl:6-32."""
+    rng = np.random.default_rng(123)
+    X = np.abs(rng.standard_normal((5, 4)))
+    X0 = X.copy()
+    W, H, obj = o.execute_singlerun_compute(X, 2, maxiter=50, tol=1e-8, rng=np.random.default_rng(1))
+    assert W.shape == (5, 2) and H.shape == (2, 4)
+    assert np.isfinite(obj) and np.isfinite(W).all() and np.isfinite(H).all()
+    assert (W >= 0).all() and (H >= 0).all()
+    assert H[0].sum() == pytest.approx(1.0, abs=1e-4) and H[1].sum() == pytest.approx(1.0, abs=1e-4)
+    assert np.array_equal(X, X0)  # caller's X restored (NMFkMultiplicative.jl:123-124)
+    X = np.abs(np.random.default_rng(321).standard_normal((6, 5)))
+    Wa, Ha, phi, minsil, aic = o.execute_run(X, 1, 2, maxiter=40, tol=1e-8, seed=3)
+    assert Wa.shape == (6, 1) and Ha.shape == (1, 5)
+    assert np.isfinite(phi) and np.isfinite(aic) and minsil == 1
+
+
+def test_clustersolutions_unit():
+    """test/test_cluster_unit.jl:36-54."""
+    f1 = np.array([[1.0, 0], [0, 1], [1, 0], [0, 1]])
+    f2 = np.array([[0.0, 1], [1, 0], [0, 1], [1, 0]])
+    labels, centers = o.clustersolutions([f1, f2], True)
+    assert labels.shape == (2, 2)
+    assert list(labels[:, 0]) == [1, 2]
+    assert sorted(labels[:, 1]) == [1, 2]
+    assert list(labels[:, 1]) == [2, 1]
+    assert centers.shape == (2, 4)
+
+
+def test_helpers_known_answers():
+    """test/test_normalize.jl:44-55 (zerostoepsilon floor eps(Float64)^2) and
+    test/test_helpers.jl:60-67 (NaN-ignoring sums of squares)."""
+    x = np.array([0.0, 1e-40, 1.0, -1.0])
+    y = o.zerostoepsilon(x)
+    e = np.finfo(np.float64).eps ** 2
+    assert y[0] == e and y[1] == e and y[2] == 1.0 and y[3] == e
+    assert x[0] == 0.0  # copy
+    assert o.zerostoepsilon(np.zeros(2, dtype=np.float32))[0] == np.float32(np.finfo(np.float32).eps) ** 2
+    t = np.array([1.0, np.nan, 3.0])
+    assert o.ssqrnan(t - np.array([1.0, 5.0, 2.0])) == 1.0
+    assert o.normnan(np.array([3.0, np.nan, 4.0])) == 5.0
+
+
+def test_getk_and_signalorder():
+    """src/NMFkPostprocess.jl:7-41,148-158."""
+    assert o.getk([2, 3, 4, 5], [0.99, 0.85, -0.57, -0.67]) == 3
+    assert o.getk([2, 3, 4], [0.1, 0.2, 0.3]) is None
+    assert o.getk([2, 3, 4], [0.1, 0.2, 0.3], strict=False) == 4
+    assert o.getk([2, 3], [np.nan, np.nan]) == 0
+    assert o.getk([3], [0.6]) == 3 and o.getk([3], [0.4]) is None
+    assert o.getk([2, 3, 4], [0.9, 0.2, 0.7]) == 4  # findlast, not "first drop"
+    W = np.array([[1.0, 2.0], [1.0, 2.0]])
+    H = np.array([[1.0, 1.0], [3.0, 3.0]])
+    assert list(o.signalorder(W, H)) == [1, 0]
+
+
+def test_negative_entries_raise_and_nan_quirk():
+    """NMFkMultiplicative.jl:4-7; minimum() propagates NaN so NaN + negative passes."""
+    with pytest.raises(o.NegativeEntriesError):
+        o.nmf_preprocessing(np.array([[1.0, -1.0]]))
+    inan, izero = o.nmf_preprocessing(np.array([[np.nan, -1.0, 0.0, 2.0]]))
+    assert list(inan[0]) == [True, False, False, False] and list(izero[0]) == [False, True, True, False]
+
+
+def test_silhouettes_against_sklearn():
+    """Clustering.silhouettes restatement == textbook silhouette on a precomputed metric."""
+    from sklearn.metrics import silhouette_samples
+    rng = np.random.default_rng(0)
+    V = rng.random((30, 6))
+    D = o.pairwise_cosine_rows(V)
+    lab = np.tile(np.arange(1, 4), 10)
+    s = o.silhouettes(lab, D)
+    ref = silhouette_samples(D, lab, metric="precomputed")
+    assert np.allclose(s, ref, atol=1e-12)
+    from scipy.spatial.distance import cdist
+    assert np.allclose(D, cdist(V, V, "cosine"), atol=1e-12)
