@@ -1,0 +1,195 @@
+/*
+ * nmfk_b200.h - C ABI of the B200-native NMFk factorization hot path.
+ *
+ * The reference (SmartTensors/NMFk.jl 1.4.21) is pure Julia and has NO FFI / plugin interface
+ * for this path: its boundary is a set of Julia method signatures.  Each entry point below
+ * therefore replaces a Julia function (file:line relative to /root/reference) and is what a
+ * Julia `ccall` (or Python `ctypes`) binds; INTEGRATION.md shows the reference-side stubs.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no exceptions cross the boundary.
+ *   - every function returns int32 status: 0 ok; <0 argument / domain error (mirrors the
+ *     reference's exceptions, see NMFK_E_*); >0 CUDA error code (cudaError_t).
+ *     nmfk_last_error(ctx) gives the message (ctx may be NULL for creation failures).
+ *   - all matrices are COLUMN-MAJOR, contiguous (Julia `Array` memory): W is n x k, H is k x m,
+ *     stacks are restart-major (W stack = n x k x R, H stack = k x m x R).
+ *   - the caller owns host buffers; the library owns device memory inside nmfk_ctx.
+ *   - one ctx = one CUDA device; calls on one ctx must be serialised by the caller.
+ *   - dtype: NMFK_F32 / NMFK_F64 is the element type T of X and of the factor buffers.
+ *   - there is NO CPU fallback: without a CUDA device nmfk_ctx_create fails.
+ */
+#ifndef NMFK_B200_H
+#define NMFK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMFK_ABI_VERSION 1
+
+enum nmfk_dtype { NMFK_F32 = 0, NMFK_F64 = 1 };
+
+/* status codes (<0): the reference's exceptions for this path */
+enum nmfk_status {
+    NMFK_OK = 0,
+    NMFK_E_INVALID = -1,      /* bad pointer / size / enum */
+    NMFK_E_NEGATIVE = -2,     /* ErrorException("All matrix entries must be nonnegative!") NMFkMultiplicative.jl:4-7 */
+    NMFK_E_NAN_INIT = -3,     /* error("Initial values for the W/H matrix entries include NaNs!") :42-44,52-54 */
+    NMFK_E_SHAPE = -4,        /* AssertionError size(Winit)==(n,k) :40,50 ; normalizevector length :30 */
+    NMFK_E_NO_X = -5,         /* nmfk_set_X has not been called */
+    NMFK_E_UNSUPPORTED = -6,  /* k or shape outside what the engines cover */
+    NMFK_E_EMPTY = -7,        /* error("Input array has a zero dimension!") NMFkExecute.jl:242-244 */
+    NMFK_E_NO_DEVICE = -8     /* no CUDA device / library built without one: fail loudly, never fall back */
+};
+
+/* why a restart stopped (NMFkMultiplicative.jl:64,75,112) */
+enum nmfk_stop_reason {
+    NMFK_STOP_PAUSED = 0,       /* iter_limit reached (trace / resumable runs) */
+    NMFK_STOP_MAXITER = 1,      /* iters >= maxiter */
+    NMFK_STOP_TOL = 2,          /* objvalue < tol */
+    NMFK_STOP_REATTEMPTS = 3,   /* reattempts >= maxreattempts */
+    NMFK_STOP_CONSISTENCY = 4,  /* inc > stopconv */
+    NMFK_STOP_BADITERS = 5      /* baditers >= maxbaditers (unreachable with the reference's reset, kept for the guard) */
+};
+
+enum nmfk_engine { NMFK_ENGINE_AUTO = 0, NMFK_ENGINE_RESIDENT = 1, NMFK_ENGINE_TILED = 2 };
+
+/* Keyword arguments of NMFmultiplicative (NMFkMultiplicative.jl:24) and of
+ * execute_singlerun_compute (NMFkExecute.jl:729), one field per keyword. */
+typedef struct nmfk_params {
+    double tol;             /* tol=1e-19 (as reached from execute, NMFkExecute.jl:729) */
+    double tolOF;           /* tolOF=1e-3 */
+    double eps_clamp;       /* eps() == eps(Float64) = 2.220446049250313e-16, NMFkMultiplicative.jl:99-100 */
+    double weight;          /* scalar weight=1 (vector/matrix weights are not on the B200 path yet) */
+    int32_t maxiter;        /* maxiter=10000 from execute (NMFkExecute.jl:729); 1000000 when called directly */
+    int32_t maxbaditers;    /* 10 */
+    int32_t maxreattempts;  /* 2 */
+    int32_t stopconv;       /* 1000 */
+    int32_t check_every;    /* 10, the mod(iters, 10) of :73 */
+    int32_t Wfixed;         /* Wfixed=false */
+    int32_t Hfixed;         /* Hfixed=false */
+    int32_t normalize;      /* execute_singlerun_compute's modifymatrices && mixture==:null: 1 = rows of H sum to one
+                               (NMFkExecute.jl:800-804); 2 = clusterWmatrix variant (:796-799); 0 = raw W,H */
+    int32_t iter_limit;     /* >0: pause every restart once iters reaches this value (resumable); 0 = none */
+    int32_t engine;         /* nmfk_engine */
+    int32_t reserved[4];
+} nmfk_params;
+
+/* facts about X found by the preprocessing kernel (NMFpreprocessing!, NMFkMultiplicative.jl:3-22) */
+typedef struct nmfk_xinfo {
+    int64_t n, m;
+    int64_t nnan;        /* count(isnan, X) */
+    int64_t nzero;       /* count(X .<= 0) */
+    int32_t zero_row;    /* some row sums to 0 -> the reference warns (:9-11) */
+    int32_t zero_col;    /* some column sums to 0 (:12-14) */
+    double xmin;         /* minimum(X) over non-NaN entries */
+    int32_t dtype;
+    int32_t reserved;
+} nmfk_xinfo;
+
+typedef struct nmfk_ctx nmfk_ctx;     /* one device, one X */
+typedef struct nmfk_batch nmfk_batch; /* R restarts at one k: device-resident W/H stacks + per-restart state */
+
+int32_t nmfk_abi_version(void);
+const char* nmfk_last_error(const nmfk_ctx* ctx);
+void nmfk_default_params(nmfk_params* p); /* the defaults reached from NMFk.execute(...; method=:simple) */
+
+/* ---- context ---------------------------------------------------------------------------- */
+int32_t nmfk_ctx_create(int32_t device, nmfk_ctx** out);
+int32_t nmfk_ctx_destroy(nmfk_ctx* ctx);
+int32_t nmfk_ctx_sync(nmfk_ctx* ctx); /* cudaStreamSynchronize on every stream of the ctx */
+
+/* ---- X: replaces NMFpreprocessing! (NMFkMultiplicative.jl:3-22) ---------------------------
+ * Uploads X (host pointer, or device pointer when on_device != 0), validates it (negative ->
+ * NMFK_E_NEGATIVE unless X also holds NaN, exactly like `minimum(X) < 0`), builds the device
+ * copies the solver streams (X with zeros -> lambda, and its transpose), and leaves the caller's
+ * X untouched - the reference mutates and then restores it (:123-124).
+ * normalizevector (length n, may be NULL) is the keyword of the same name (:27-31). */
+int32_t nmfk_set_X(nmfk_ctx* ctx, const void* X, int64_t n, int64_t m, int32_t dtype, double lambda,
+                   const void* normalizevector, int32_t on_device);
+int32_t nmfk_get_xinfo(const nmfk_ctx* ctx, nmfk_xinfo* out);
+
+/* ---- batches of restarts: replace the restart loop of execute_run (NMFkExecute.jl:510-544) - */
+int32_t nmfk_batch_create(nmfk_ctx* ctx, int32_t k, int32_t R, nmfk_batch** out);
+int32_t nmfk_batch_destroy(nmfk_batch* b);
+/* Winit: n x k x R, Hinit: k x m x R (dtype of X).  NaN -> NMFK_E_NAN_INIT.  Resets the state. */
+int32_t nmfk_batch_set_init(nmfk_batch* b, const void* Winit, const void* Hinit);
+/* U(0,1) initialisation generated on the device: restart r (0-based) uses the stream
+ * numpy.random.Generator(Philox(key=seed0 + r + 1)).random(), W (column-major) then H - the draw
+ * order of NMFkMultiplicative.jl:38,48 and the `seed=kwseed+i` of NMFkExecute.jl:536. */
+int32_t nmfk_batch_init_random(nmfk_batch* b, uint64_t seed0);
+/* Run NMFmultiplicative (+ the post-run objective and normalisation of execute_singlerun_compute,
+ * NMFkExecute.jl:791-804) for every restart of every batch; batches run concurrently. */
+int32_t nmfk_solve(nmfk_ctx* ctx, nmfk_batch* const* batches, int32_t nbatches, const nmfk_params* p);
+/* Copy results to the host; any pointer may be NULL.  obj_ssq: NMFkMultiplicative.jl:125;
+ * obj_norm: NMFkExecute.jl:792. */
+int32_t nmfk_batch_get(nmfk_batch* b, void* W_out, void* H_out, double* obj_ssq, double* obj_norm,
+                       int32_t* iters, int32_t* stop_reason);
+/* Sum of squares sum(((X - W*H)*weight)[!inan]^2) of the current (unnormalised) W,H against the
+ * lambda-substituted X, i.e. the quantity of NMFkMultiplicative.jl:74, for every restart. */
+int32_t nmfk_batch_objective(nmfk_batch* b, double weight, double* obj_ssq);
+
+/* ---- robustness: replaces sortperm + clustersolutions + finalize (NMFkExecute.jl:545-638,
+ *      NMFkCluster.jl:425-517, NMFkFinalize.jl:36-79) on the device-resident H stack ----------
+ * order        R      0-based restart indices sorted by objective (stable), order[0] = best
+ * labels       k x R  1-based cluster of row a of the t-th sorted solution (column-major)
+ * sil          k x R  silhouette of every row (NaN -> 0)
+ * clustersil   k      mean silhouette per cluster; *robustness = min (1 when k == 1)
+ * centroids    k x m  (k x (m+1) when the zero-column fix of NMFkCluster.jl:437-450 fired;
+ *                      *centroid_cols tells which)                                              */
+int32_t nmfk_batch_cluster(nmfk_batch* b, int32_t clusterWmatrix, int32_t* order, int32_t* labels, double* sil,
+                           double* clustersil, double* robustness, void* centroids, int32_t* centroid_cols);
+
+/* ---- one-call forms --------------------------------------------------------------------- */
+/* NMFmultiplicative for R stacked restarts at one k, host buffers in and out
+ * (NMFkMultiplicative.jl:24-127 + NMFkExecute.jl:791-804 when p->normalize != 0). */
+int32_t nmfk_run_batch(nmfk_ctx* ctx, int32_t k, int32_t R, const void* Winit, const void* Hinit,
+                       const nmfk_params* p, void* W_out, void* H_out, double* obj_ssq, double* obj_norm,
+                       int32_t* iters, int32_t* stop_reason);
+/* Fixed iteration count with per-iteration dumps, for parity: W_t is n x k x niter, H_t is
+ * k x m x niter, obj_t[niter] is the :74 objective after every iteration (state machine, checks
+ * and clamps run exactly as in a normal solve). */
+int32_t nmfk_trace(nmfk_ctx* ctx, int32_t k, const void* Winit, const void* Hinit, const nmfk_params* p,
+                   int32_t niter, void* W_t, void* H_t, double* obj_t);
+/* execute_run(X, nk, nNMF) with defaults acceptratio=1, acceptfactor=Inf, nanaction=:zeroed,
+ * best=true (NMFkExecute.jl:483-711): returns the best restart (n x k, k x m), phi = norm of the
+ * residual (:664-668), robustness = min cluster silhouette (:638), aic (:708).
+ * Winit/Hinit may be NULL -> device Philox streams seeded seed0 + i. */
+int32_t nmfk_execute_run(nmfk_ctx* ctx, int32_t k, int32_t R, const void* Winit, const void* Hinit, uint64_t seed0,
+                         const nmfk_params* p, void* W_best, void* H_best, double* phi, double* robustness,
+                         double* aic, int64_t* total_iters);
+/* execute(X, nkrange, nNMF; cutoff) (NMFkExecute.jl:178-233) without the JLD cache: all k of the
+ * range are solved concurrently.  W_out[i] / H_out[i] (may be NULL) receive the signal-ordered
+ * factors of ks[i] (signalorder, NMFkPostprocess.jl:148-158).  *kopt: k, 0 ("no successful
+ * runs"), or -1 (`nothing`).  Winit[i]/Hinit[i] are per-k stacks or NULL (device Philox). */
+int32_t nmfk_execute(nmfk_ctx* ctx, const int32_t* ks, int32_t nks, int32_t R, const void* const* Winit,
+                     const void* const* Hinit, uint64_t seed0, const nmfk_params* p, double cutoff,
+                     void* const* W_out, void* const* H_out, double* fitquality, double* robustness, double* aic,
+                     int32_t* kopt, int64_t* total_iters);
+
+/* getk (NMFkPostprocess.jl:7-41): returns k, 0 (all NaN) or -1 (nothing). */
+int32_t nmfk_getk(const int32_t* ks, const double* robustness, int32_t nks, double cutoff, int32_t strict);
+/* signalorder (NMFkPostprocess.jl:148-158) on host buffers; order is 0-based. */
+int32_t nmfk_signalorder(const void* W, const void* H, int64_t n, int32_t k, int64_t m, int32_t dtype,
+                         int32_t* order);
+
+/* ---- measurement helpers (bench only) --------------------------------------------------- */
+/* kernel launches issued by this ctx since creation (for bench.py's gpu_launches) */
+int64_t nmfk_launch_count(const nmfk_ctx* ctx);
+/* device time (ms, CUDA events on the ctx streams) of the last nmfk_solve */
+double nmfk_last_solve_ms(const nmfk_ctx* ctx);
+/* micro-benchmarks that give the roofline denominators MEASURED_PEAKS.json does not hold:
+ * which: 0 = FP64 DFMA TFLOP/s, 1 = FP64 DMMA (mma.sync m8n8k4) TFLOP/s, 2 = FP32 FFMA TFLOP/s,
+ *        3 = device-to-device copy GB/s (read+write bytes) */
+int32_t nmfk_measure_peak(nmfk_ctx* ctx, int32_t which, double* value);
+
+/* first `count` doubles of numpy.random.Generator(Philox(key=seed)).random(), computed on the HOST with the
+ * same code the device initialiser uses (test hook: bit-compatibility of the init streams without a GPU) */
+int32_t nmfk_philox_host(uint64_t seed, int64_t count, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMFK_B200_H */

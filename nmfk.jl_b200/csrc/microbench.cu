@@ -1,0 +1,129 @@
+// Micro-benchmarks for the roofline denominators MEASURED_PEAKS.json does not hold:
+// FP64 DFMA, FP64 DMMA (mma.sync.m8n8k4.f64), FP32 FFMA throughput and a device copy.
+// bench.py reports the KL kernels against these ("of measured, own micro-benchmark").
+#include "nmfk_internal.h"
+
+namespace nmfk {
+
+namespace {
+
+template <typename T, int CHAINS>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T b) {
+    T acc[CHAINS];
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) acc[c] = (T)(threadIdx.x + c);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int c = 0; c < CHAINS; ++c) acc[c] = fma(acc[c], a, b);
+    }
+    T s = 0;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) s += acc[c];
+    if (s == (T)-1.2345) out[0] = s;  // never true; keeps the chain alive
+}
+
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double a, double b) {
+    double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0}, c2[2] = {0.0, 0.0}, c3[2] = {0.0, 0.0};
+    const double av = a + threadIdx.x, bv = b;
+    for (int i = 0; i < iters; ++i) {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0[0]), "+d"(c0[1])
+                     : "d"(av), "d"(bv));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c1[0]), "+d"(c1[1])
+                     : "d"(av), "d"(bv));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c2[0]), "+d"(c2[1])
+                     : "d"(av), "d"(bv));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c3[0]), "+d"(c3[1])
+                     : "d"(av), "d"(bv));
+    }
+    const double s = c0[0] + c0[1] + c1[0] + c1[1] + c2[0] + c2[1] + c3[0] + c3[1];
+    if (s == -1.2345) out[0] = s;
+}
+
+__global__ void copy_kernel(const double4* __restrict__ src, double4* __restrict__ dst, long long n4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+template <typename F>
+cudaError_t time_best(F launch, int reps, float* best_ms, cudaStream_t s) {
+    cudaEvent_t e0, e1;
+    cudaError_t e;
+    if ((e = cudaEventCreate(&e0)) != cudaSuccess) return e;
+    if ((e = cudaEventCreate(&e1)) != cudaSuccess) return e;
+    *best_ms = 1e30f;
+    for (int r = 0; r < reps + 2; ++r) {
+        cudaEventRecord(e0, s);
+        launch();
+        cudaEventRecord(e1, s);
+        if ((e = cudaEventSynchronize(e1)) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r >= 2 && ms < *best_ms) *best_ms = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t measure_peak(int which, double* value, cudaStream_t s) {
+    cudaError_t e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    float ms = 0.f;
+    if (which == 0 || which == 2) {
+        double* out = nullptr;
+        if ((e = cudaMalloc(&out, 64)) != cudaSuccess) return e;
+        const int blocks = sms * 8, threads = 256, chains = 8;
+        const int iters = which == 0 ? 4096 : 16384;
+        if (which == 0)
+            e = time_best([&] { fma_peak_kernel<double, 8><<<blocks, threads, 0, s>>>(out, iters, 1.0000001, 1e-9); }, 5, &ms, s);
+        else
+            e = time_best([&] { fma_peak_kernel<float, 8><<<blocks, threads, 0, s>>>((float*)out, iters, 1.0000001f, 1e-9f); }, 5,
+                          &ms, s);
+        cudaFree(out);
+        if (e != cudaSuccess) return e;
+        const double flops = 2.0 * (double)blocks * threads * chains * iters;
+        *value = flops / (ms * 1e-3) / 1e12;
+        return cudaSuccess;
+    }
+    if (which == 1) {
+        double* out = nullptr;
+        if ((e = cudaMalloc(&out, 64)) != cudaSuccess) return e;
+        const int blocks = sms * 8, threads = 256, iters = 4096;
+        e = time_best([&] { dmma_peak_kernel<<<blocks, threads, 0, s>>>(out, iters, 1.0, 1e-9); }, 5, &ms, s);
+        cudaFree(out);
+        if (e != cudaSuccess) return e;
+        // per warp per mma: 8*8*4 FMAs = 512 flops; 4 mma per iteration
+        const double flops = 512.0 * 4.0 * iters * (double)blocks * (threads / 32);
+        *value = flops / (ms * 1e-3) / 1e12;
+        return cudaSuccess;
+    }
+    if (which == 3) {
+        const long long bytes = 1ll << 30;
+        double4 *a = nullptr, *b = nullptr;
+        if ((e = cudaMalloc(&a, bytes)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&b, bytes)) != cudaSuccess) {
+            cudaFree(a);
+            return e;
+        }
+        cudaMemsetAsync(a, 1, bytes, s);
+        const long long n4 = bytes / sizeof(double4);
+        e = time_best([&] { copy_kernel<<<sms * 16, 512, 0, s>>>(a, b, n4); }, 5, &ms, s);
+        cudaFree(a);
+        cudaFree(b);
+        if (e != cudaSuccess) return e;
+        *value = 2.0 * (double)bytes / (ms * 1e-3) / 1e9;
+        return cudaSuccess;
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace nmfk

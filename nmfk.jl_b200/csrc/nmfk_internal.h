@@ -1,0 +1,104 @@
+// Internal (host+device) declarations shared by the kernels and the C ABI layer.
+// Nothing here is exported; the public surface is include/nmfk_b200.h.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace nmfk {
+
+// Per-restart solver state, device resident, so that a solve can be paused and resumed
+// (trace mode, host-driven tiled engine).  Scalars of NMFkMultiplicative.jl:56-63.
+struct UnitState {
+    int32_t it;        // iters
+    int32_t bad;       // baditers
+    int32_t re;        // reattempts
+    int32_t inc;       // consecutive unchanged co-clusterings
+    int32_t stop;      // nmfk_stop_reason, 0 while running / paused
+    int32_t has_cons;  // consold holds a real partition (it starts as falses(m,m))
+    int32_t done;      // post-run objective + normalisation applied
+    int32_t pad;
+    double best;       // objvalue_best
+    double obj_chk;    // objective of the last check (NMFkMultiplicative.jl:74)
+    double obj_ssq;    // final sum of squares (:125)
+    double obj_norm;   // normnan(X - W*H) (NMFkExecute.jl:792)
+};
+
+// Arguments of one batched KL solve (R restarts at one k).
+struct SolveArgs {
+    const void* X;    // n x m column-major, zeros -> lambda, NaN kept
+    const void* Xt;   // m x n column-major (the transpose), same substitutions
+    void* W;          // n x k x R
+    void* H;          // k x m x R
+    UnitState* st;    // R
+    int32_t* canon;   // R x m : canonical co-clustering of the previous check
+    void* ximp;       // R x n x m imputed values (only when has_nan), X layout
+    int32_t n, m, k, R;
+    int32_t has_nan;
+    int32_t maxiter, maxbad, maxre, stopconv, check_every, Wfixed, Hfixed, normalize, iter_limit;
+    double lambda, tol, tolOF, eps_clamp, weight;
+};
+
+constexpr int kResidentThreads = 256;
+constexpr int kMaxK = 32;
+
+// template K actually instantiated for a requested k (exact up to 12, then padded)
+inline int resident_template_k(int k) {
+    if (k <= 12) return k;
+    if (k <= 16) return 16;
+    if (k <= 20) return 20;
+    if (k <= 24) return 24;
+    if (k <= 32) return 32;
+    return -1;
+}
+
+// dynamic shared memory the resident kernel needs (bytes); mirrors the carve-up in kl_resident.cuh
+size_t resident_smem_bytes(int n, int m, int Ktemplate, size_t sizeofTC, int nthreads);
+
+// launchers (one translation unit per dtype), return cudaError_t
+cudaError_t launch_kl_resident_f64(const SolveArgs& a, cudaStream_t s);
+cudaError_t launch_kl_resident_f32(const SolveArgs& a, cudaStream_t s);
+// can the resident engine take this shape?  (smem budget of one CTA)
+bool resident_fits(int n, int m, int k, size_t sizeofTC);
+
+// generic residual sums of one (W,H): partials[2*b] = weighted ssq, partials[2*b+1] = plain ssq of CTA b
+int residual_blocks(int n);
+cudaError_t launch_residual(const void* X, int dtype, int n, int m, int k, const void* W, const void* H, double lambda,
+                            int restore, double weight, double* d_partials, cudaStream_t s);
+
+// preprocessing (K1): raw X -> Xp, Xpt + statistics
+struct PreStats {
+    unsigned long long nnan, nzero, nneg;
+    unsigned long long zero_rows, zero_cols;
+};
+cudaError_t launch_preprocess(const void* Xraw, void* Xp, void* Xpt, int64_t n, int64_t m, int dtype, double lambda,
+                              PreStats* d_stats, unsigned char* d_rowflag, unsigned char* d_colflag, double* d_blockmin,
+                              int nblockmin, cudaStream_t s);
+
+// device Philox4x64-10 U(0,1) streams identical to numpy.random.Generator(Philox(key=seed)).random()
+cudaError_t launch_philox_init(void* W, void* H, int64_t n, int k, int64_t m, int R, uint64_t seed0, int dtype,
+                               cudaStream_t s);
+
+// clustering / silhouettes (K10-K12)
+struct ClusterArgs {
+    const void* F;        // factor stack in solver layout (H: k x m x R; W: n x k x R)
+    int32_t len;          // vector length (m for H rows, n for W columns)
+    int32_t k, R;
+    int32_t use_W;        // clusterWmatrix
+    const int32_t* order; // R sorted restart indices (device)
+    int32_t* labels;      // k x R (device), 1-based
+    double* cent;         // k x (len+1) running-sum centroids (device scratch / output)
+    double* sil;          // k x R
+    double* clustersil;   // k
+    int32_t* bias;        // out: 1 if the zero-column fix fired
+    double* V;            // (R*k) x (len+1) gathered + floored vectors, row-major, sorted order
+    double* vnorm;        // R*k
+    double* Dm;           // (R*k) x (R*k) cosine distance matrix
+};
+cudaError_t launch_cluster(const ClusterArgs& a, int dtype, cudaStream_t s);
+cudaError_t launch_zero_nan(void* p, long long len, int dtype, cudaStream_t s);
+
+// micro-benchmarks
+cudaError_t measure_peak(int which, double* value, cudaStream_t s);
+
+}  // namespace nmfk

@@ -1,0 +1,77 @@
+// Generic residual reductions for one (W, H) pair of any size (not on the hot loop):
+//   sum over non-NaN entries of ((X - W*H) * weight)^2   and of (X - W*H)^2
+// used for the :74 objective in trace mode, for phi_final (/root/reference/src/NMFkExecute.jl:664-668)
+// and for the per-k fit re-derivation of execute (:212-222).  Deterministic: one partial per
+// CTA, summed in CTA order on the host.
+#include "nmfk_internal.h"
+
+namespace nmfk {
+
+namespace {
+
+constexpr int kRows = 128;  // rows of X per CTA
+
+template <typename T>
+__global__ void __launch_bounds__(kRows) residual_kernel(const T* __restrict__ X, int n, int m, int k,
+                                                         const T* __restrict__ W, const T* __restrict__ H, T lambda,
+                                                         int restore, double weight, double* __restrict__ partials) {
+    extern __shared__ unsigned char smraw[];
+    T* Ws = reinterpret_cast<T*>(smraw);  // [k][kRows]
+    __shared__ double red[2][kRows / 32];
+    const int i0 = blockIdx.x * kRows, tid = threadIdx.x, i = i0 + tid;
+    for (int a = 0; a < k; ++a) Ws[a * kRows + tid] = (i < n) ? W[(size_t)i + (size_t)a * n] : (T)0;
+    __syncthreads();
+    double sw = 0.0, s1 = 0.0;
+    if (i < n) {
+        for (int j = 0; j < m; ++j) {
+            const T xr = X[(size_t)i + (size_t)j * n];
+            if (xr != xr) continue;
+            T x = xr;
+            if (restore && x == lambda) x = (T)0;
+            const T* h = H + (size_t)j * k;
+            T p = (T)0;
+            for (int a = 0; a < k; ++a) p = fma(Ws[a * kRows + tid], __ldg(h + a), p);
+            const double e = (double)(x - p);
+            s1 = fma(e, e, s1);
+            const double ew = e * weight;
+            sw = fma(ew, ew, sw);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sw += __shfl_xor_sync(0xffffffffu, sw, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if ((tid & 31) == 0) {
+        red[0][tid >> 5] = sw;
+        red[1][tid >> 5] = s1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < kRows / 32; ++w) {
+            a += red[0][w];
+            b += red[1][w];
+        }
+        partials[2 * blockIdx.x] = a;
+        partials[2 * blockIdx.x + 1] = b;
+    }
+}
+
+}  // namespace
+
+int residual_blocks(int n) { return (n + kRows - 1) / kRows; }
+
+cudaError_t launch_residual(const void* X, int dtype, int n, int m, int k, const void* W, const void* H, double lambda,
+                            int restore, double weight, double* d_partials, cudaStream_t s) {
+    const int blocks = residual_blocks(n);
+    const size_t smem = (size_t)k * kRows * (dtype == 1 ? 8 : 4);
+    if (dtype == 1)
+        residual_kernel<double><<<blocks, kRows, smem, s>>>((const double*)X, n, m, k, (const double*)W,
+                                                            (const double*)H, lambda, restore, weight, d_partials);
+    else
+        residual_kernel<float><<<blocks, kRows, smem, s>>>((const float*)X, n, m, k, (const float*)W, (const float*)H,
+                                                           (float)lambda, restore, weight, d_partials);
+    return cudaGetLastError();
+}
+
+}  // namespace nmfk

@@ -1,0 +1,397 @@
+"""Host-side mirror of the reference's Julia interface for the hot path.
+
+Every public function cites the reference method it stands for (paths relative to
+/root/reference/src).  Arrays are NumPy, column-major (Fortran order) like Julia's; nothing
+numeric happens here - all of it is a call into the C ABI (libnmfk_b200.so)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import F32, F64, NMFkError, Params, XInfo, check
+
+_DT = {np.dtype(np.float32): F32, np.dtype(np.float64): F64}
+_NP = {F32: np.float32, F64: np.float64}
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f(a, dtype) -> np.ndarray:
+    return np.asfortranarray(a, dtype=dtype)
+
+
+def default_params(**kw) -> Params:
+    """Keyword defaults as reached from NMFk.execute(...; method=:simple)
+    (NMFkExecute.jl:729 -> NMFkMultiplicative.jl:24)."""
+    p = Params()
+    _lib.load().nmfk_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise TypeError("unknown solver parameter %r" % k)
+        setattr(p, k, v)
+    return p
+
+
+class Context:
+    """One CUDA device + one data matrix X (nmfk_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        check(self._lib.nmfk_ctx_create(device, C.byref(h)))
+        self._h = h
+        self.dtype = None
+        self.n = self.m = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.nmfk_ctx_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_X(self, X: np.ndarray, lam: float = 1e-32):
+        """NMFpreprocessing! (NMFkMultiplicative.jl:3-22).  The caller's X is never modified."""
+        X = np.asarray(X)
+        if X.ndim != 2:
+            raise ValueError("X must be a matrix (N>2 arrays are delegated to tensorfactorization in the reference)")
+        if X.dtype not in _DT:
+            X = X.astype(np.float64)
+        Xf = np.asfortranarray(X)
+        self.dtype = _DT[Xf.dtype]
+        self.np_dtype = Xf.dtype.type
+        self.n, self.m = Xf.shape
+        check(self._lib.nmfk_set_X(self._h, _ptr(Xf), self.n, self.m, self.dtype, lam, None, 0), self._h)
+        return self.xinfo()
+
+    def xinfo(self) -> XInfo:
+        xi = XInfo()
+        check(self._lib.nmfk_get_xinfo(self._h, C.byref(xi)), self._h)
+        return xi
+
+    def batch(self, k: int, R: int) -> "Batch":
+        return Batch(self, k, R)
+
+    def solve(self, batches: Sequence["Batch"], params: Optional[Params] = None):
+        """The restart loop of execute_run for all batches at once (NMFkExecute.jl:510-544)."""
+        p = params or default_params()
+        arr = (C.c_void_p * len(batches))(*[b._h for b in batches])
+        check(self._lib.nmfk_solve(self._h, arr, len(batches), C.byref(p)), self._h)
+
+    @property
+    def launches(self) -> int:
+        return int(self._lib.nmfk_launch_count(self._h))
+
+    @property
+    def last_solve_ms(self) -> float:
+        return float(self._lib.nmfk_last_solve_ms(self._h))
+
+    def measure_peak(self, which: int) -> float:
+        v = C.c_double()
+        check(self._lib.nmfk_measure_peak(self._h, which, C.byref(v)), self._h)
+        return v.value
+
+
+class Batch:
+    """R restarts at one k with device-resident factor stacks (nmfk_batch)."""
+
+    def __init__(self, ctx: Context, k: int, R: int):
+        self.ctx, self.k, self.R = ctx, int(k), int(R)
+        h = C.c_void_p()
+        check(ctx._lib.nmfk_batch_create(ctx._h, self.k, self.R, C.byref(h)), ctx._h)
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self.ctx._lib.nmfk_batch_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_init(self, Winit: np.ndarray, Hinit: np.ndarray):
+        """Winit: (R, n, k) or list of n x k; Hinit: (R, k, m).  Sizes are asserted like
+        NMFkMultiplicative.jl:40,50."""
+        c = self.ctx
+        W = np.stack([_f(w, c.np_dtype) for w in Winit]) if not isinstance(Winit, np.ndarray) else Winit
+        H = np.stack([_f(h, c.np_dtype) for h in Hinit]) if not isinstance(Hinit, np.ndarray) else Hinit
+        assert W.shape == (self.R, c.n, self.k), "size(Winit) == (n, k)"
+        assert H.shape == (self.R, self.k, c.m), "size(Hinit) == (k, m)"
+        # restart-major stack of column-major matrices
+        Wb = np.ascontiguousarray(np.transpose(W, (0, 2, 1)), dtype=c.np_dtype)
+        Hb = np.ascontiguousarray(np.transpose(H, (0, 2, 1)), dtype=c.np_dtype)
+        check(c._lib.nmfk_batch_set_init(self._h, _ptr(Wb), _ptr(Hb)), c._h)
+
+    def init_random(self, seed0: int):
+        check(self.ctx._lib.nmfk_batch_init_random(self._h, int(seed0)), self.ctx._h)
+
+    def get(self, factors: bool = True):
+        """-> dict(W (R,n,k), H (R,k,m), obj_ssq, obj_norm, iters, stop_reason)."""
+        c = self.ctx
+        R, k = self.R, self.k
+        out = {}
+        Wb = np.empty((R, k, c.n), dtype=c.np_dtype) if factors else None
+        Hb = np.empty((R, c.m, k), dtype=c.np_dtype) if factors else None
+        ssq = np.empty(R)
+        nrm = np.empty(R)
+        it = np.empty(R, dtype=np.int32)
+        sr = np.empty(R, dtype=np.int32)
+        check(c._lib.nmfk_batch_get(self._h, _ptr(Wb), _ptr(Hb), ssq.ctypes.data_as(_lib._pdbl),
+                                    nrm.ctypes.data_as(_lib._pdbl), it.ctypes.data_as(_lib._pi32),
+                                    sr.ctypes.data_as(_lib._pi32)), c._h)
+        if factors:
+            out["W"] = np.transpose(Wb, (0, 2, 1))  # views: (R, n, k) with column-major matrices
+            out["H"] = np.transpose(Hb, (0, 2, 1))
+        out.update(obj_ssq=ssq, obj_norm=nrm, iters=it, stop_reason=sr)
+        return out
+
+    def objective(self, weight: float = 1.0) -> np.ndarray:
+        o = np.empty(self.R)
+        check(self.ctx._lib.nmfk_batch_objective(self._h, weight, o.ctypes.data_as(_lib._pdbl)), self.ctx._h)
+        return o
+
+    def cluster(self, clusterWmatrix: bool = False):
+        """sortperm + clustersolutions + finalize silhouettes (NMFkExecute.jl:545-638,
+        NMFkCluster.jl:425-517, NMFkFinalize.jl:36-79).
+        -> dict(order (R,), labels (k,R) 1-based, sil (k,R), clustersil (k,), robustness, centroids)."""
+        c = self.ctx
+        R, k = self.R, self.k
+        order = np.empty(R, dtype=np.int32)
+        labels = np.empty((R, k), dtype=np.int32)
+        sil = np.empty((R, k))
+        csil = np.empty(k)
+        rob = C.c_double()
+        ln = c.n if clusterWmatrix else c.m
+        cent = np.zeros((ln + 1, k), dtype=c.np_dtype)
+        cols = C.c_int32()
+        check(c._lib.nmfk_batch_cluster(self._h, int(clusterWmatrix), order.ctypes.data_as(_lib._pi32),
+                                        labels.ctypes.data_as(_lib._pi32), sil.ctypes.data_as(_lib._pdbl),
+                                        csil.ctypes.data_as(_lib._pdbl), C.byref(rob), _ptr(cent), C.byref(cols)), c._h)
+        return dict(order=order, labels=labels.T, sil=sil.T, clustersil=csil, robustness=rob.value,
+                    centroids=cent[:cols.value].T if cols.value else None)
+
+
+# ------------------------------------------------------------------------------------------
+# reference-shaped functions
+# ------------------------------------------------------------------------------------------
+def _params_from_kw(kw: dict, **defaults) -> Params:
+    """Map the reference's keyword names onto nmfk_params; unknown keywords are tolerated like the
+    `kw...` sink of NMFkMultiplicative.jl:24."""
+    names = {"tol": "tol", "tolOF": "tolOF", "maxiter": "maxiter", "maxbaditers": "maxbaditers",
+             "maxreattempts": "maxreattempts", "stopconv": "stopconv", "Wfixed": "Wfixed", "Hfixed": "Hfixed",
+             "weight": "weight", "engine": "engine", "iter_limit": "iter_limit", "normalize": "normalize"}
+    vals = dict(defaults)
+    for k in list(kw):
+        if k in names:
+            vals[names[k]] = kw.pop(k)
+    if "weight" in vals and not np.isscalar(vals["weight"]):
+        raise NMFkError(-6, "vector/matrix weights are not on the B200 path yet")
+    for b in ("Wfixed", "Hfixed"):
+        if b in vals:
+            vals[b] = int(bool(vals[b]))
+    return default_params(**vals)
+
+
+def NMFmultiplicative(X, k: int, *, Winit=None, Hinit=None, seed: int = -1, lam: float = 1e-32, ctx: Context = None,
+                      **kw):
+    """`NMFk.NMFmultiplicative(X, k; ...)` NMFkMultiplicative.jl:24-127 -> (W, H, objvalue) with
+    objvalue the sum of squares of :125.  maxiter defaults to 1000000 as in the direct call."""
+    own = ctx is None
+    ctx = ctx or Context()
+    try:
+        if own or X is not None:
+            ctx.set_X(X, lam)
+        p = _params_from_kw(kw, maxiter=kw.pop("maxiter", 1000000), normalize=0)
+        b = ctx.batch(k, 1)
+        if Winit is not None and Hinit is not None:
+            b.set_init(np.asarray(Winit)[None], np.asarray(Hinit)[None])
+        elif Winit is None and Hinit is None:
+            b.init_random(seed - 1 if seed >= 0 else int(np.random.randint(0, 2 ** 31)))
+        else:
+            raise NMFkError(-6, "give both Winit and Hinit or neither")
+        ctx.solve([b], p)
+        r = b.get()
+        b.close()
+        return np.asfortranarray(r["W"][0]), np.asfortranarray(r["H"][0]), float(r["obj_ssq"][0])
+    finally:
+        if own:
+            ctx.close()
+
+
+def execute_singlerun(X, nk: int, *, Winit=None, Hinit=None, seed: int = -1, clusterWmatrix: bool = False,
+                      ctx: Context = None, **kw):
+    """`execute_singlerun_compute(X, nk; method=:simple, ...)` NMFkExecute.jl:729-807 ->
+    (W, H, objvalue): objvalue = normnan(X - W*H), rows of H sum to one."""
+    own = ctx is None
+    ctx = ctx or Context()
+    try:
+        ctx.set_X(X, kw.pop("lam", 1e-32))
+        modify = not ("Wfixed" in kw or "Hfixed" in kw)
+        p = _params_from_kw(kw, normalize=(2 if clusterWmatrix else 1) if modify else 0)
+        b = ctx.batch(nk, 1)
+        if Winit is not None and Hinit is not None:
+            b.set_init(np.asarray(Winit)[None], np.asarray(Hinit)[None])
+        else:
+            b.init_random(seed - 1 if seed >= 0 else int(np.random.randint(0, 2 ** 31)))
+        ctx.solve([b], p)
+        r = b.get()
+        b.close()
+        return np.asfortranarray(r["W"][0]), np.asfortranarray(r["H"][0]), ctx.np_dtype(r["obj_norm"][0])
+    finally:
+        if own:
+            ctx.close()
+
+
+def execute_run(X, nk: int, nNMF: int, *, clusterWmatrix: bool = False, seed: Optional[int] = None, inits=None,
+                ctx: Context = None, details: Optional[dict] = None, **kw):
+    """`execute_run(X, nk, nNMF; ...)` NMFkExecute.jl:483-711 (defaults acceptratio=1,
+    acceptfactor=Inf, nanaction=:zeroed, best=true) -> (Wa, Ha, phi, minsilhouette, aic).
+    `seed`: restart i draws from Philox(key=seed+i) (the `seed=kwseed+i` of :536);
+    `inits=(Winit (R,n,k), Hinit (R,k,m))` injects explicit initialisations."""
+    own = ctx is None
+    ctx = ctx or Context()
+    try:
+        ctx.set_X(X, kw.pop("lam", 1e-32))
+        modify = not ("Wfixed" in kw or "Hfixed" in kw)
+        p = _params_from_kw(kw, normalize=(2 if clusterWmatrix else 1) if modify else 0)
+        n, m, dt = ctx.n, ctx.m, ctx.np_dtype
+        Wb = np.empty((nk, n), dtype=dt)
+        Hb = np.empty((m, nk), dtype=dt)
+        phi, rob, aic = C.c_double(), C.c_double(), C.c_double()
+        tot = C.c_int64()
+        Wi = Hi = None
+        if inits is not None:
+            Wi = np.ascontiguousarray(np.transpose(np.asarray(inits[0], dtype=dt), (0, 2, 1)))
+            Hi = np.ascontiguousarray(np.transpose(np.asarray(inits[1], dtype=dt), (0, 2, 1)))
+            assert Wi.shape == (nNMF, nk, n) and Hi.shape == (nNMF, m, nk)
+        seed0 = int(seed) if seed is not None else int(np.random.randint(0, 2 ** 31))
+        check(ctx._lib.nmfk_execute_run(ctx._h, nk, nNMF, _ptr(Wi), _ptr(Hi), seed0, C.byref(p), _ptr(Wb), _ptr(Hb),
+                                        C.byref(phi), C.byref(rob), C.byref(aic), C.byref(tot)), ctx._h)
+        if details is not None:
+            details.update(total_iters=tot.value, solve_ms=ctx.last_solve_ms)
+        return Wb.T, Hb.T, dt(phi.value), (1 if nk == 1 else dt(rob.value)), aic.value
+    finally:
+        if own:
+            ctx.close()
+
+
+def execute(X, nkrange, nNMF: int = 10, *, cutoff: float = 0.5, seed: Optional[int] = None, inits=None,
+            ctx: Context = None, details: Optional[dict] = None, **kw):
+    """`NMFk.execute(X, nkrange, nNMF; cutoff=0.5, method=:simple, ...)` NMFkExecute.jl:178-233 without
+    the JLD cache -> (W, H, fitquality, robustness, aic, kopt).  W, H are dicts keyed by k (the
+    reference's Vector indexed by k); fitquality/robustness/aic have length maximum(nkrange) with
+    fitquality[1]=Inf, robustness[1]=-1 (:200-201); kopt is k, 0 or None (`nothing`).
+    All k of the range are solved concurrently on the device."""
+    if isinstance(nkrange, (int, np.integer)):
+        raise TypeError("use execute_k / execute_run for a single k")
+    ks = [int(k) for k in nkrange]
+    own = ctx is None
+    ctx = ctx or Context()
+    try:
+        ctx.set_X(X, kw.pop("lam", 1e-32))
+        modify = not ("Wfixed" in kw or "Hfixed" in kw)
+        p = _params_from_kw(kw, normalize=(2 if kw.pop("clusterWmatrix", False) else 1) if modify else 0)
+        n, m, dt = ctx.n, ctx.m, ctx.np_dtype
+        nks = len(ks)
+        Wo = [np.empty((k, n), dtype=dt) for k in ks]
+        Ho = [np.empty((m, k), dtype=dt) for k in ks]
+        Wop = (C.c_void_p * nks)(*[w.ctypes.data for w in Wo])
+        Hop = (C.c_void_p * nks)(*[h.ctypes.data for h in Ho])
+        Wi_keep, Hi_keep = [], []
+        Wip = Hip = None
+        if inits is not None:  # inits[k] = (Winit (R,n,k), Hinit (R,k,m))
+            for k in ks:
+                Wi_keep.append(np.ascontiguousarray(np.transpose(np.asarray(inits[k][0], dtype=dt), (0, 2, 1))))
+                Hi_keep.append(np.ascontiguousarray(np.transpose(np.asarray(inits[k][1], dtype=dt), (0, 2, 1))))
+            Wip = (C.c_void_p * nks)(*[w.ctypes.data for w in Wi_keep])
+            Hip = (C.c_void_p * nks)(*[h.ctypes.data for h in Hi_keep])
+        fit = np.empty(nks)
+        rob = np.empty(nks)
+        aic = np.empty(nks)
+        kopt = C.c_int32()
+        tot = C.c_int64()
+        karr = np.asarray(ks, dtype=np.int32)
+        seed0 = int(seed) if seed is not None else int(np.random.randint(0, 2 ** 31))
+        check(ctx._lib.nmfk_execute(ctx._h, karr.ctypes.data_as(_lib._pi32), nks, nNMF, Wip, Hip, seed0, C.byref(p),
+                                    cutoff, Wop, Hop, fit.ctypes.data_as(_lib._pdbl), rob.ctypes.data_as(_lib._pdbl),
+                                    aic.ctypes.data_as(_lib._pdbl), C.byref(kopt), C.byref(tot)), ctx._h)
+        maxk = max(ks)
+        fitquality = np.zeros(maxk, dtype=dt)
+        robustness = np.zeros(maxk, dtype=dt)
+        aicv = np.zeros(maxk, dtype=dt)
+        fitquality[0] = np.inf  # :200
+        robustness[0] = -1  # :201
+        W, H = {}, {}
+        for i, k in enumerate(ks):
+            W[k], H[k] = Wo[i].T, Ho[i].T
+            fitquality[k - 1], robustness[k - 1], aicv[k - 1] = fit[i], (1 if k == 1 else rob[i]), aic[i]
+        if details is not None:
+            details.update(total_iters=tot.value, solve_ms=ctx.last_solve_ms, launches=ctx.launches)
+        ko = kopt.value
+        return W, H, fitquality, robustness, aicv, (None if ko < 0 else ko)
+    finally:
+        if own:
+            ctx.close()
+
+
+def getk(nkrange, robustness, cutoff: float = 0.5, strict: bool = True):
+    """`getk` NMFkPostprocess.jl:7-41 -> k, 0, or None."""
+    ks = np.asarray(list(nkrange), dtype=np.int32)
+    rb = np.asarray(robustness, dtype=np.float64)
+    if len(ks) != len(rb):
+        rb = rb[ks - 1]  # :8-10
+    rb = np.ascontiguousarray(rb)
+    r = _lib.load().nmfk_getk(ks.ctypes.data_as(_lib._pi32), rb.ctypes.data_as(_lib._pdbl), len(ks), cutoff, int(strict))
+    return None if r < 0 else int(r)
+
+
+def signalorder(W, H) -> np.ndarray:
+    """`signalorder` NMFkPostprocess.jl:148-158 -> 0-based order (descending contribution)."""
+    W = np.asarray(W)
+    dt = np.float32 if W.dtype == np.float32 else np.float64
+    Wf, Hf = _f(W, dt), _f(H, dt)
+    n, k = Wf.shape
+    assert Hf.shape[0] == k
+    o = np.empty(k, dtype=np.int32)
+    check(_lib.load().nmfk_signalorder(_ptr(Wf), _ptr(Hf), n, k, Hf.shape[1], _DT[np.dtype(dt)],
+                                       o.ctypes.data_as(_lib._pi32)))
+    return o
+
+
+def trace(X, k: int, Winit, Hinit, niter: int, *, ctx: Context = None, **kw):
+    """Per-iteration dump for parity tests (nmfk_trace): -> (W_t (niter,n,k), H_t (niter,k,m), obj_t)."""
+    own = ctx is None
+    ctx = ctx or Context()
+    try:
+        ctx.set_X(X, kw.pop("lam", 1e-32))
+        p = _params_from_kw(kw, normalize=0, maxiter=kw.pop("maxiter", 1000000))
+        n, m, dt = ctx.n, ctx.m, ctx.np_dtype
+        Wi, Hi = _f(Winit, dt), _f(Hinit, dt)
+        assert Wi.shape == (n, k) and Hi.shape == (k, m)
+        Wt = np.empty((niter, k, n), dtype=dt)
+        Ht = np.empty((niter, m, k), dtype=dt)
+        ob = np.empty(niter)
+        check(ctx._lib.nmfk_trace(ctx._h, k, _ptr(Wi), _ptr(Hi), C.byref(p), niter, _ptr(Wt), _ptr(Ht),
+                                  ob.ctypes.data_as(_lib._pdbl)), ctx._h)
+        return np.transpose(Wt, (0, 2, 1)), np.transpose(Ht, (0, 2, 1)), ob
+    finally:
+        if own:
+            ctx.close()

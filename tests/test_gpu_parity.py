@@ -1,0 +1,242 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical
+seeded initialisations.  Tolerances (BASELINE.json north_star): per-iteration W, H and fit
+within 1e-9 relative for Float64 and 1e-4 for Float32 over a fixed iteration count;
+cluster assignments, robustness ranking and kopt identical."""
+import numpy as np
+import pytest
+
+import nmfk_b200 as nb
+from nmfk_b200 import synth
+from oracle import nmfk_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+RTOL64 = 1e-9
+RTOL32 = 1e-4
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def oracle_trace(X, k, W0, H0, niter, **kw):
+    Ws, Hs, objs = [], [], []
+
+    def cb(it, W, H, obj):
+        Ws.append(W.copy())
+        Hs.append(H.copy())
+
+    Xc = np.array(X, dtype=np.float64, order="F", copy=True)
+    o.nmf_multiplicative(Xc, k, Winit=W0.astype(np.float64), Hinit=H0.astype(np.float64), maxiter=niter, trace=cb, **kw)
+    # the :74 objective of every iteration's W,H against the lambda-substituted X
+    Xl = np.array(X, dtype=np.float64, copy=True)
+    inan = np.isnan(Xl)
+    Xl[Xl <= 0] = 1e-32
+    for W, H in zip(Ws, Hs):
+        E = (Xl - W @ H)[~inan]
+        objs.append(float(np.sum(E ** 2)))
+    return np.stack(Ws), np.stack(Hs), np.asarray(objs)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = nb.Context()
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("n,m,k,niter", [(15, 5, 2, 60), (15, 5, 3, 60), (15, 5, 5, 45), (50, 20, 4, 40), (37, 300, 7, 25),
+                                         (1000, 200, 10, 25), (300, 64, 13, 22), (100, 40, 32, 22), (64, 9, 1, 30)])
+def test_trace_parity_f64(ctx, n, m, k, niter):
+    X = synth.readme_bss() if (n, m) == (15, 5) else synth.mixture(n, m, 3, seed=7)
+    W0, H0 = synth.philox_inits(11, 1, n, k, m)
+    Wt, Ht, ob = nb.trace(X, k, W0[0], H0[0], niter, ctx=ctx)
+    Wr, Hr, obr = oracle_trace(X, k, W0[0], H0[0], niter)
+    assert len(Wr) == niter, "oracle stopped early; pick another case"
+    for t in range(niter):
+        assert relerr(Wt[t], Wr[t]) < RTOL64, ("W", t)
+        assert relerr(Ht[t], Hr[t]) < RTOL64, ("H", t)
+    assert np.allclose(ob, obr, rtol=1e-7, atol=1e-18 + 1e-9 * obr.max())
+
+
+@pytest.mark.parametrize("n,m,k,niter", [(15, 5, 3, 40), (200, 50, 6, 30), (1000, 200, 10, 20), (128, 96, 16, 20)])
+def test_trace_parity_f32(ctx, n, m, k, niter):
+    X = synth.mixture(n, m, 4, seed=5, dtype=np.float32)
+    W0, H0 = synth.philox_inits(3, 1, n, k, m, dtype=np.float32)
+    Wt, Ht, ob = nb.trace(X, k, W0[0], H0[0], niter, ctx=ctx)
+    Wr, Hr, obr = oracle_trace(X, k, W0[0], H0[0], niter)  # the reference computes in Float64
+    for t in range(niter):
+        assert relerr(Wt[t], Wr[t]) < RTOL32, ("W", t)
+        assert relerr(Ht[t], Hr[t]) < RTOL32, ("H", t)
+
+
+def test_full_stop_rule_matches_oracle(ctx):
+    """Reference stop rule (tolOF/baditers/reattempts state machine): same iteration counts,
+    stop reasons, objective and normalised factors for every restart."""
+    X = synth.readme_bss()
+    for k in (2, 3, 4):
+        R = 6
+        W0, H0 = synth.philox_inits(100, R, 15, k, 5)
+        ctx.set_X(X)
+        b = ctx.batch(k, R)
+        b.set_init(W0, H0)
+        ctx.solve([b])
+        g = b.get()
+        for r in range(R):
+            inf = {}
+            Xc = X.copy()
+            W, H, of = o.execute_singlerun_compute(Xc, k, Winit=W0[r].copy(), Hinit=H0[r].copy(), info=inf)
+            assert np.array_equal(Xc, X)
+            assert g["iters"][r] == inf["iters"], (k, r)
+            assert g["stop_reason"][r] == {"maxiter": 1, "tol": 2, "reattempts": 3, "consistency": 4}[inf["stop_reason"]]
+            assert g["obj_norm"][r] == pytest.approx(of, rel=1e-6, abs=1e-12)
+            assert relerr(g["W"][r], W) < 1e-7 and relerr(g["H"][r], H) < 1e-7
+            assert np.allclose(g["H"][r].sum(axis=1), 1.0, atol=1e-12)  # test_execute_smoke.jl:18-19
+        b.close()
+
+
+def test_execute_matches_oracle_decisions(ctx):
+    """execute(X, 2:5, 10): kopt, cluster labels, robustness, fit, aic vs the oracle from the same
+    Philox streams (device-generated here, NumPy-generated there)."""
+    X = synth.readme_bss()
+    det = {}
+    W, H, fit, rob, aic, kopt = nb.execute(X, range(2, 6), 10, seed=100, ctx=ctx, details=det)
+    Wo, Ho, fito, robo, aico, kopto = o.execute(X.copy(), range(2, 6), 10, seed=100)
+    assert kopt == kopto == 3
+    assert fit[0] == np.inf and rob[0] == -1
+    for k in range(2, 6):
+        assert rob[k - 1] == pytest.approx(robo[k - 1], abs=1e-6), k
+        assert fit[k - 1] == pytest.approx(fito[k - 1], rel=1e-5, abs=1e-10), k
+        assert aic[k - 1] == pytest.approx(aico[k - 1], rel=1e-5), k
+        assert relerr(W[k], Wo[k]) < 1e-6 and relerr(H[k], Ho[k]) < 1e-6
+    assert list(np.argsort(-rob[1:5], kind="stable")) == list(np.argsort(-robo[1:5], kind="stable"))
+    assert det["total_iters"] > 0
+
+
+def test_cluster_labels_bit_identical(ctx):
+    """clustersolutions + silhouettes on the solver's H stacks: labels identical to the oracle,
+    silhouettes to 1e-9."""
+    X = synth.mixture(60, 24, 3, seed=9)
+    for k in (2, 3, 5):
+        R = 12
+        ctx.set_X(X)
+        b = ctx.batch(k, R)
+        b.init_random(500)
+        ctx.solve([b], nb.default_params(maxiter=200))
+        g = b.get()
+        cl = b.cluster()
+        order = np.argsort(g["obj_norm"], kind="stable")
+        assert list(cl["order"]) == list(order)
+        Hs = [np.array(g["H"][i], dtype=np.float64) for i in order]
+        Ws = [np.array(g["W"][i], dtype=np.float64) for i in order]
+        labels, cent = o.clustersolutions(Hs, False)
+        assert np.array_equal(cl["labels"], labels)
+        _, _, csil, _, _ = o.finalize(Ws, Hs, labels, False)
+        assert np.allclose(cl["clustersil"], csil[:, 0], atol=1e-9)
+        assert cl["robustness"] == pytest.approx(float(csil.min()), abs=1e-9)
+        assert np.allclose(cl["centroids"], cent, rtol=1e-10)
+        b.close()
+
+
+def test_cluster_unit_case_from_reference(ctx):
+    """test/test_cluster_unit.jl:36-54 through the device path (clusterWmatrix=true)."""
+    f1 = np.array([[1.0, 0], [0, 1], [1, 0], [0, 1]])
+    f2 = np.array([[0.0, 1], [1, 0], [0, 1], [1, 0]])
+    ctx.set_X(np.ones((4, 3)))
+    b = ctx.batch(2, 2)
+    H = np.ones((2, 2, 3))
+    b.set_init(np.stack([f1, f2]), H)
+    ctx.solve([b], nb.default_params(maxiter=0, normalize=0))  # no iterations: just evaluate + keep factors
+    g = b.get()
+    assert np.array_equal(g["W"][0], f1) and np.array_equal(g["W"][1], f2)
+    cl = b.cluster(clusterWmatrix=True)
+    assert cl["labels"].shape == (2, 2)
+    assert list(cl["labels"][:, 0]) == [1, 2] and list(cl["labels"][:, 1]) == [2, 1]
+    assert cl["centroids"].shape == (2, 4)
+    b.close()
+
+
+def test_device_philox_init_equals_numpy(ctx):
+    X = synth.mixture(33, 17, 2, seed=1)
+    ctx.set_X(X)
+    b = ctx.batch(3, 4)
+    b.init_random(41)
+    ctx.solve([b], nb.default_params(maxiter=0, normalize=0))
+    g = b.get()
+    W0, H0 = synth.philox_inits(41, 4, 33, 3, 17)
+    assert np.array_equal(g["W"], W0) and np.array_equal(g["H"], H0)
+    b.close()
+
+
+def test_zeros_nan_and_errors(ctx):
+    rng = np.random.default_rng(3)
+    X = synth.mixture(40, 12, 3, seed=2)
+    X[rng.random(X.shape) < 0.1] = 0.0
+    xi = ctx.set_X(X)
+    assert xi.nzero == int((X <= 0).sum()) and xi.nnan == 0
+    W0, H0 = synth.philox_inits(5, 1, 40, 3, 12)
+    Wt, Ht, ob = nb.trace(X, 3, W0[0], H0[0], 30, ctx=ctx)
+    Wr, Hr, obr = oracle_trace(X, 3, W0[0], H0[0], 30)
+    assert relerr(Wt[-1], Wr[-1]) < RTOL64 and relerr(Ht[-1], Hr[-1]) < RTOL64
+    # NaN entries: EM-style imputation X[inan] = (W*H)[inan] (NMFkMultiplicative.jl:72; runtests.jl:270-273)
+    Xn = synth.mixture(40, 12, 3, seed=2)
+    Xn[rng.random(Xn.shape) < 0.2] = np.nan
+    xi = ctx.set_X(Xn)
+    assert xi.nnan == int(np.isnan(Xn).sum())
+    Wt, Ht, ob = nb.trace(Xn, 3, W0[0], H0[0], 35, ctx=ctx)
+    Wr, Hr, obr = oracle_trace(Xn, 3, W0[0], H0[0], 35)
+    for t in (0, 1, 9, 10, 34):
+        assert relerr(Wt[t], Wr[t]) < RTOL64 and relerr(Ht[t], Hr[t]) < RTOL64, t
+    # negative entries throw (NMFkMultiplicative.jl:4-7) ...
+    Xneg = X.copy()
+    Xneg[3, 4] = -1.0
+    with pytest.raises(nb.NegativeEntriesError):
+        ctx.set_X(Xneg)
+    # ... unless a NaN hides them from minimum()
+    Xneg[0, 0] = np.nan
+    ctx.set_X(Xneg)
+    # NaN initial values are an error (:42-44)
+    ctx.set_X(X)
+    b = ctx.batch(3, 1)
+    Wbad = W0.copy()
+    Wbad[0, 2, 1] = np.nan
+    with pytest.raises(nb.NMFkError) as ei:
+        b.set_init(Wbad, H0)
+    assert ei.value.status == -3
+    b.close()
+
+
+def test_fixed_factors(ctx):
+    """Wfixed / Hfixed (NMFkMultiplicative.jl:66,69): the fixed factor never changes."""
+    X = synth.mixture(30, 10, 2, seed=4)
+    W0, H0 = synth.philox_inits(8, 1, 30, 2, 10)
+    for kw in ({"Wfixed": True}, {"Hfixed": True}):
+        Wt, Ht, ob = nb.trace(X, 2, W0[0], H0[0], 25, ctx=ctx, **kw)
+        Wr, Hr, obr = oracle_trace(X, 2, W0[0], H0[0], 25, **kw)
+        assert relerr(Wt[-1], Wr[-1]) < RTOL64 and relerr(Ht[-1], Hr[-1]) < RTOL64
+
+
+def test_c2_shape_sweep_properties(ctx):
+    """BASELINE config C2 shape at reduced restart count: all k concurrently, reference stop rule.
+    Size-independent properties: rows of H sum to one, W,H >= 0, objective == ||X - WH||,
+    rank-5 data => fit collapses at k >= 5, robustness high at the true rank."""
+    X = synth.mixture(1000, 200, 5, seed=2015)
+    ctx.set_X(X)
+    ks = list(range(2, 11))
+    bs = [ctx.batch(k, 8) for k in ks]
+    for b in bs:
+        b.init_random(2015)
+    ctx.solve(bs)
+    for k, b in zip(ks, bs):
+        g = b.get()
+        assert (g["W"] >= 0).all() and (g["H"] >= 0).all()
+        assert np.allclose(g["H"].sum(axis=2), 1.0, atol=1e-10)
+        r = int(np.argmin(g["obj_norm"]))
+        assert np.linalg.norm(X - g["W"][r] @ g["H"][r]) == pytest.approx(g["obj_norm"][r], rel=1e-8)
+        assert (g["iters"] % 10 == 0).all() and (g["iters"] <= 10000).all()
+        assert set(g["stop_reason"]) <= {1, 2, 3, 4}
+        if k >= 5:
+            assert g["obj_norm"].min() < 1.0
+        b.close()
