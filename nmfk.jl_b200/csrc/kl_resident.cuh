@@ -100,16 +100,90 @@ __device__ __forceinline__ void factor_sums(const TC* __restrict__ V, int nred, 
     }
 }
 
-// Sweep of one thread over reduction indices [t0,t1) for own index o:
-//   acc[a] += sum_t V[t][a] * (D[o,t] / (u . V[t,:]))
-// UNR consecutive t are processed together (independent dot-product chains and divisions give the
-// FP64 pipe ILP); X values for the next group are prefetched while the current group computes.
+// x / p on the hot loop.  The compiler's IEEE division carries a slow-path CALL that splits the
+// loop body into basic blocks and serialises the unrolled steps; here the quotient is
+// x * (1/p) with 1/p from MUFU.RCP64H + two Newton steps (relative error ~2^-52, well inside the
+// 1e-9 parity budget), straight-line.  `unsafe` flags operands outside the range where that is
+// valid (zero, subnormal, huge, Inf, NaN): the caller redoes those with the IEEE division so that
+// degenerate restarts produce the same Inf/NaN pattern as the reference's `X ./ (W*H)`.
+__device__ __forceinline__ double fast_div(double x, double p, bool& unsafe) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
+    double e = fma(-p, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-p, r, 1.0);
+    r = fma(r, e, r);
+    const unsigned ex = ((unsigned)__double2hiint(p) >> 20) & 0x7ffu;
+    unsafe = (ex < 2u) | (ex > 0x7fbu) | (__double2hiint(p) < 0);
+    return x * r;
+}
+__device__ __forceinline__ float fast_div(float x, float p, bool& unsafe) {
+    unsafe = !(p > 1e-37f && p < 1e37f);
+    return __fdividef(x, p);
+}
+
+// dot product u.v with two interleaved partial sums (halves the dependent-FMA chain)
+template <typename TC, int K, int KP>
+__device__ __forceinline__ TC dot2(const TC (&u)[KP], const TC (&v)[KP]) {
+    TC p0 = (TC)0, p1 = (TC)0;
+#pragma unroll
+    for (int a = 0; a + 1 < K; a += 2) {
+        p0 = fma(u[a], v[a], p0);
+        p1 = fma(u[a + 1], v[a + 1], p1);
+    }
+    if (K & 1) p0 = fma(u[K - 1], v[K - 1], p0);
+    return p0 + p1;
+}
+
+// One straight-line group of UNR reduction steps: UNR independent dot products, UNR independent
+// divisions, then K independent accumulator chains (acc[a] += V[t][a] * x_t / (u . V[t,:])).
 // V rows are re-read from shared memory for the accumulation phase instead of being kept live
 // (registers are the scarce resource: u and acc already hold 2K values).
-template <typename TX, typename TC, int K, int KP, bool TRANSPOSED, int UNR>
+template <typename TC, int K, int KP, int UNR>
+__device__ __forceinline__ void kl_group(const TC (&x)[UNR], const TC* const (&vrow)[UNR], const bool (&live)[UNR],
+                                         const TC (&u)[KP], TC (&acc)[KP]) {
+    TC p[UNR], qv[UNR];
+    bool bad = false;
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) {
+        TC v[KP];
+        load_row<TC, KP>(vrow[q], v);
+        p[q] = dot2<TC, K, KP>(u, v);
+    }
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) {
+        bool uq;
+        qv[q] = fast_div(x[q], p[q], uq);
+        bad |= uq;
+    }
+    if (bad) {  // rare: operands outside the fast path's range -> IEEE semantics
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) qv[q] = div_cold<TC>(x[q], p[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < UNR; ++q)
+        if (!live[q]) qv[q] = (TC)0;
+    if (K > 4) asm volatile("" ::: "memory");  // do not keep the UNR V rows live: re-read them
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) {
+        TC v[KP];
+        load_row<TC, KP>(vrow[q], v);
+#pragma unroll
+        for (int a = 0; a < K; ++a) acc[a] = fma(v[a], qv[q], acc[a]);
+    }
+}
+
+// Sweep of one thread over reduction indices [t0,t1) for own index o:
+//   acc[a] += sum_t V[t][a] * (D[o,t] / (u . V[t,:]))
+// UNR consecutive t form one straight-line group: UNR independent dot products, UNR independent
+// divisions, then K independent accumulator chains - enough ILP to keep the FP64 pipe busy with
+// 4 warps per scheduler.  X values of the next group are prefetched while the current one
+// computes.  V rows are re-read from shared memory for the accumulation phase instead of being
+// kept live (registers are the scarce resource: u and acc already hold 2K values).
+template <typename TX, typename TC, int K, int KP, bool TRANSPOSED, bool HASNAN, int UNR>
 __device__ __forceinline__ void sweep(const TX* __restrict__ dcol, int nown, int o, int t0, int t1, const TC (&u)[KP],
-                                      TC (&acc)[KP], const TC* __restrict__ V, bool has_nan, bool first_iter,
-                                      TC lambda, const TC* __restrict__ ximp, int ldimp) {
+                                      TC (&acc)[KP], const TC* __restrict__ V, bool first_iter, TC lambda,
+                                      const TC* __restrict__ ximp, int ldimp) {
     TX xn[UNR];
 #pragma unroll
     for (int q = 0; q < UNR; ++q) xn[q] = (t0 + q < t1) ? __ldg(dcol + (size_t)(t0 + q) * nown) : (TX)1;
@@ -118,51 +192,41 @@ __device__ __forceinline__ void sweep(const TX* __restrict__ dcol, int nown, int
 #pragma unroll
         for (int q = 0; q < UNR; ++q) {
             x[q] = (TC)xn[q];
-            if (has_nan && (xn[q] != xn[q]))
-                x[q] = first_iter ? lambda
-                                  : ximp[TRANSPOSED ? ((size_t)(t + q) + (size_t)o * ldimp)
-                                                    : ((size_t)o + (size_t)(t + q) * ldimp)];
+            if (HASNAN) {
+                if (xn[q] != xn[q])
+                    x[q] = first_iter ? lambda
+                                      : ximp[TRANSPOSED ? ((size_t)(t + q) + (size_t)o * ldimp)
+                                                        : ((size_t)o + (size_t)(t + q) * ldimp)];
+            }
         }
 #pragma unroll
         for (int q = 0; q < UNR; ++q) {
             const int tn = t + UNR + q;
             xn[q] = (tn < t1) ? __ldg(dcol + (size_t)tn * nown) : (TX)1;
         }
-        TC qv[UNR];
+        const TC* vrow[UNR];
+        bool live[UNR];
 #pragma unroll
         for (int q = 0; q < UNR; ++q) {
-            const int tt = (t + q < t1) ? (t + q) : t;  // tail: recompute a valid row, contribution zeroed below
-            TC v[KP];
-            load_row<TC, KP>(V + (size_t)tt * KP, v);
-            TC p = (TC)0;
-#pragma unroll
-            for (int a = 0; a < K; ++a) p = fma(u[a], v[a], p);
-            qv[q] = (t + q < t1) ? (x[q] / p) : (TC)0;
+            live[q] = (t + q < t1);
+            vrow[q] = V + (size_t)(live[q] ? (t + q) : t) * KP;  // tail: a valid row, contribution zeroed
         }
-        if (K > 4) asm volatile("" ::: "memory");  // do not keep the UNR V rows live: re-read them
-#pragma unroll
-        for (int q = 0; q < UNR; ++q) {
-            const int tt = (t + q < t1) ? (t + q) : t;
-            TC v[KP];
-            load_row<TC, KP>(V + (size_t)tt * KP, v);
-#pragma unroll
-            for (int a = 0; a < K; ++a) acc[a] = fma(v[a], qv[q], acc[a]);
-        }
+        kl_group<TC, K, KP, UNR>(x, vrow, live, u, acc);
     }
 }
 
 // One half-update.  D is column-major with leading dimension = nown (own index contiguous).
 // TRANSPOSED tells how to address the imputation buffer (always stored in X layout, ld = n).
-template <typename TX, typename TC, int K, int KP, bool TRANSPOSED>
-__device__ __forceinline__ void half_update(const TX* __restrict__ D, int nown, int nred, TC* __restrict__ U,
-                                            const TC* __restrict__ V, const TC* __restrict__ den, TC* __restrict__ scr,
-                                            bool has_nan, bool first_iter, TC lambda, const TC* __restrict__ ximp,
-                                            int ldimp) {
+template <typename TX, typename TC, int K, int KP, bool TRANSPOSED, bool HASNAN>
+__device__ __forceinline__ void half_update(const TX* __restrict__ D, int nown, int nred, int kact,
+                                            TC* __restrict__ U, const TC* __restrict__ V, const TC* __restrict__ den,
+                                            TC* __restrict__ scr, bool first_iter, TC lambda,
+                                            const TC* __restrict__ ximp, int ldimp) {
     const int tid = threadIdx.x, NT = blockDim.x;
     int S = NT / nown;
     if (S > nred) S = nred;
     if (S < 1) S = 1;
-    constexpr int UNR = 2;
+    constexpr int UNR = (K <= 12 ? 2 : 2);
     if (S == 1) {
         // every thread sweeps the whole reduction range for own rows tid, tid+NT, ...
         for (int o = tid; o < nown; o += NT) {
@@ -170,12 +234,13 @@ __device__ __forceinline__ void half_update(const TX* __restrict__ D, int nown, 
             load_row<TC, KP>(U + (size_t)o * KP, u);
 #pragma unroll
             for (int a = 0; a < KP; ++a) acc[a] = (TC)0;
-            sweep<TX, TC, K, KP, TRANSPOSED, UNR>(D + o, nown, o, 0, nred, u, acc, V, has_nan, first_iter, lambda, ximp,
-                                                  ldimp);
+            sweep<TX, TC, K, KP, TRANSPOSED, HASNAN, UNR>(D + o, nown, o, 0, nred, u, acc, V, first_iter, lambda, ximp,
+                                                          ldimp);
             // (U .* acc) ./ den : Julia's left-to-right broadcast of `H .* (...) ./ sum`
             TC* urow = U + (size_t)o * KP;
 #pragma unroll
-            for (int a = 0; a < K; ++a) urow[a] = div_cold<TC>(u[a] * acc[a], den[a]);
+            for (int a = 0; a < K; ++a)
+                if (a < kact) urow[a] = div_cold<TC>(u[a] * acc[a], den[a]);
         }
         __syncthreads();
         return;
@@ -189,8 +254,8 @@ __device__ __forceinline__ void half_update(const TX* __restrict__ D, int nown, 
     if (active) {
         load_row<TC, KP>(U + (size_t)o * KP, u);
         const int t0 = (int)(((long long)nred * s) / S), t1 = (int)(((long long)nred * (s + 1)) / S);
-        sweep<TX, TC, K, KP, TRANSPOSED, UNR>(D + o, nown, o, t0, t1, u, acc, V, has_nan, first_iter, lambda, ximp,
-                                              ldimp);
+        sweep<TX, TC, K, KP, TRANSPOSED, HASNAN, UNR>(D + o, nown, o, t0, t1, u, acc, V, first_iter, lambda, ximp,
+                                                      ldimp);
         if (s > 0) {
             TC* dst = scr + ((size_t)(s - 1) * nown + o) * KP;
 #pragma unroll
@@ -206,7 +271,8 @@ __device__ __forceinline__ void half_update(const TX* __restrict__ D, int nown, 
         }
         TC* urow = U + (size_t)o * KP;
 #pragma unroll
-        for (int a = 0; a < K; ++a) urow[a] = div_cold<TC>(u[a] * acc[a], den[a]);
+        for (int a = 0; a < K; ++a)
+            if (a < kact) urow[a] = div_cold<TC>(u[a] * acc[a], den[a]);
     }
     __syncthreads();
 }
@@ -278,7 +344,17 @@ struct ResidentSmem {
         r.off_den = o;
         o = al(o + (size_t)KP * szTC);
         r.off_scr = o;
-        o = al(o + (size_t)nthreads * KP * szTC);
+        // cross-slice partials: only when a pass has fewer own indices than threads (S > 1)
+        size_t scr = 0;
+        {
+            int S = nthreads / m;  // H-update: own = m, reduction = n
+            if (S > n) S = n;
+            if (S > 1) scr = (size_t)(S - 1) * m * KP;
+            S = nthreads / n;  // W-update: own = n, reduction = m
+            if (S > m) S = m;
+            if (S > 1 && (size_t)(S - 1) * n * KP > scr) scr = (size_t)(S - 1) * n * KP;
+        }
+        o = al(o + scr * szTC);
         r.off_red = o;
         o = al(o + 40 * sizeof(double));
         r.off_idx = o;
@@ -290,7 +366,7 @@ struct ResidentSmem {
     }
 };
 
-template <typename TX, typename TC, int K>
+template <typename TX, typename TC, int K, bool HASNAN>
 __global__ void __launch_bounds__(kResidentThreads, (K <= 12 ? 2 : 1)) kl_resident_kernel(const SolveArgs a) {
     constexpr int VEC = VecOf<TC>::N;
     constexpr int KP = (K + VEC - 1) / VEC * VEC;
@@ -315,8 +391,8 @@ __global__ void __launch_bounds__(kResidentThreads, (K <= 12 ? 2 : 1)) kl_reside
     TC* Wg = static_cast<TC*>(a.W) + (size_t)r * n * k;
     TC* Hg = static_cast<TC*>(a.H) + (size_t)r * k * m;
     int* canon_old = a.canon + (size_t)r * m;
-    TC* ximp = a.has_nan ? static_cast<TC*>(a.ximp) + (size_t)r * n * m : nullptr;
-    const bool has_nan = a.has_nan != 0;
+    TC* ximp = HASNAN ? static_cast<TC*>(a.ximp) + (size_t)r * n * m : nullptr;
+    constexpr bool has_nan = HASNAN;
     const TC lambda = (TC)a.lambda;
 
     // ---- load factors (column-major global -> row-of-k shared), zero the padding ----
@@ -361,12 +437,12 @@ __global__ void __launch_bounds__(kResidentThreads, (K <= 12 ? 2 : 1)) kl_reside
         if (!a.Hfixed) {  // :66-68
             factor_sums<TC, K, KP>(Ws, n, den);
             __syncthreads();
-            half_update<TX, TC, K, KP, true>(Xt, m, n, Hs, Ws, den, scr, has_nan, first_iter, lambda, ximp, n);
+            half_update<TX, TC, K, KP, true, HASNAN>(Xt, m, n, k, Hs, Ws, den, scr, first_iter, lambda, ximp, n);
         }
         if (!a.Wfixed) {  // :69-71
             factor_sums<TC, K, KP>(Hs, m, den);
             __syncthreads();
-            half_update<TX, TC, K, KP, false>(X, n, m, Ws, Hs, den, scr, has_nan, first_iter, lambda, ximp, n);
+            half_update<TX, TC, K, KP, false, HASNAN>(X, n, m, k, Ws, Hs, den, scr, first_iter, lambda, ximp, n);
         }
         if (has_nan) impute_pass<TX, TC, K, KP>(X, n, m, Ws, Hs, ximp);  // :72
         if (it % a.check_every == 0) {                                    // :73
@@ -510,10 +586,18 @@ cudaError_t launch_resident_k(const SolveArgs& a, cudaStream_t s) {
     constexpr int VEC = VecOf<TC>::N;
     constexpr int KP = (K + VEC - 1) / VEC * VEC;
     const size_t smem = ResidentSmem::make(a.n, a.m, KP, sizeof(TC), kResidentThreads).total;
-    cudaError_t e = cudaFuncSetAttribute(kl_resident_kernel<TX, TC, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) return e;
-    kl_resident_kernel<TX, TC, K><<<a.R, kResidentThreads, smem, s>>>(a);
+    cudaError_t e;
+    if (a.has_nan) {
+        e = cudaFuncSetAttribute(kl_resident_kernel<TX, TC, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem);
+        if (e != cudaSuccess) return e;
+        kl_resident_kernel<TX, TC, K, true><<<a.R, kResidentThreads, smem, s>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(kl_resident_kernel<TX, TC, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem);
+        if (e != cudaSuccess) return e;
+        kl_resident_kernel<TX, TC, K, false><<<a.R, kResidentThreads, smem, s>>>(a);
+    }
     return cudaGetLastError();
 }
 

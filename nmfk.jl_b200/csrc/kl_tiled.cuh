@@ -1,0 +1,726 @@
+// Tiled KL engine: the same multiplicative updates as kl_resident.cuh for problems whose factors
+// do NOT fit in one SM's shared memory (BASELINE configs C3, C4, C5).
+//
+// Replaces the loop body of NMFk.NMFmultiplicative (/root/reference/src/NMFkMultiplicative.jl:64-118)
+// with one kernel launch per half-update for ALL restarts of a batch:
+//   grid = slices x own-blocks x R, restart index fastest, so the CTAs that are resident at the
+//   same time work on the SAME block of X for different restarts: X is fetched from HBM once and
+//   re-read from the 126 MB L2 by the other restarts.
+//   A CTA owns 256 consecutive "own" indices (rows of W, or columns of H) of one restart and walks
+//   the reduction index in chunks of TCH: the X tile (TCH x 256) and the other factor's rows
+//   (TCH x k) are staged into shared memory by a 3-stage cp.async pipeline (every thread fetches
+//   exactly the X elements it will consume, fully coalesced), the two thin products and the
+//   element-wise division happen in registers.
+//   If the own dimension alone cannot fill the GPU the reduction range is split in slices whose
+//   partial sums are combined in slice order by a second kernel (deterministic; it is also the
+//   hook for row-sharding X across GPUs: all-reduce the partials between the two kernels).
+// The stop-state machine (tolOF / baditers / reattempts / co-clustering consistency, :73-116) runs
+// in a per-restart check kernel every `check_every` iterations; finished restarts are skipped by
+// every later launch.
+#pragma once
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <vector>
+
+#include "kl_resident.cuh"  // load_row, warp_sum, block_sum, div_cold, VecOf
+
+namespace nmfk {
+
+constexpr int kTiledThreads = 256;
+constexpr int kTiledStages = 3;
+
+template <typename TX>
+struct TiledCfg {
+    static constexpr int TCH = sizeof(TX) == 8 ? 16 : 32;  // reduction indices per pipeline stage
+};
+
+struct TiledPassArgs {
+    const void* D;      // data in "own-contiguous" layout: element (o,t) at D[o + t*nown]
+    void* U;            // own factor stack
+    const void* V;      // broadcast factor stack
+    const void* den;    // R x 32 : sum_t V[t,a]
+    void* partial;      // slices x R x nown x K partial numerators (S > 1) or nullptr
+    const UnitState* st;
+    const void* ximp;   // R x n x m (X layout) or nullptr
+    long long u_rstride, v_rstride;  // elements between restarts
+    long long su_o, su_a, sv_t, sv_a;
+    int nown, nred, k, R, S, nblocks;
+    int transposed;     // 1: D is X^T (H-update) -> imputation index = t + o*ldimp
+    int ldimp;
+    int has_nan, first_iter;
+    double lambda;
+};
+
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem));
+}
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T* smem, const T* gmem) {
+    if constexpr (sizeof(T) == 8)
+        cp_async_8(smem, gmem);
+    else
+        cp_async_4(smem, gmem);
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+template <typename TX, typename TC, int K, bool HASNAN>
+__global__ void __launch_bounds__(kTiledThreads, (K <= 12 ? 2 : 1)) tiled_pass_kernel(const TiledPassArgs a) {
+    constexpr int VEC = VecOf<TC>::N;
+    constexpr int KP = (K + VEC - 1) / VEC * VEC;
+    constexpr int TCH = TiledCfg<TX>::TCH;
+    constexpr int NT = kTiledThreads;
+    constexpr int ST = kTiledStages;
+    extern __shared__ __align__(16) unsigned char smem[];
+    TC* Vs = reinterpret_cast<TC*>(smem);                                      // [ST][TCH][KP]
+    TX* Ds = reinterpret_cast<TX*>(smem + (size_t)ST * TCH * KP * sizeof(TC));  // [ST][TCH][NT]
+
+    const int tid = threadIdx.x;
+    const int r = blockIdx.x % a.R;
+    const int rest = blockIdx.x / a.R;
+    const int ob = rest % a.nblocks;
+    const int slice = rest / a.nblocks;
+    if (a.st[r].stop != 0) return;  // finished restarts are frozen
+    const int k = a.k;
+    const int o = ob * NT + tid;
+    const bool valid = o < a.nown;
+    const int t_begin = (int)(((long long)a.nred * slice) / a.S);
+    const int t_end = (int)(((long long)a.nred * (slice + 1)) / a.S);
+    const int nchunks = (t_end - t_begin + TCH - 1) / TCH;
+
+    const TX* D = static_cast<const TX*>(a.D);
+    TC* U = static_cast<TC*>(a.U) + (long long)r * a.u_rstride;
+    const TC* V = static_cast<const TC*>(a.V) + (long long)r * a.v_rstride;
+    const TC* ximp = HASNAN ? static_cast<const TC*>(a.ximp) + (long long)r * a.nown * a.nred : nullptr;
+    const TC lambda = (TC)a.lambda;
+
+    // padding columns of the broadcast rows stay zero for the whole kernel
+    for (int e = tid; e < ST * TCH * KP; e += NT) Vs[e] = (TC)0;
+    __syncthreads();
+
+    auto issue = [&](int chunk) {
+        const int stage = chunk % ST;
+        const int t0 = t_begin + chunk * TCH;
+        const int cnt = min(TCH, t_end - t0);
+        TC* vs = Vs + (size_t)stage * TCH * KP;
+        TX* ds = Ds + (size_t)stage * TCH * NT;
+        // the other factor's rows t0..t0+cnt: coalesced along whichever index is contiguous
+        if (a.sv_t == 1) {
+            for (int e = tid; e < cnt * k; e += NT) {
+                const int tl = e % cnt, c = e / cnt;
+                cp_async_elem<TC>(vs + tl * KP + c, V + (long long)(t0 + tl) + (long long)c * a.sv_a);
+            }
+        } else {
+            for (int e = tid; e < cnt * k; e += NT) {
+                const int c = e % k, tl = e / k;
+                cp_async_elem<TC>(vs + tl * KP + c, V + (long long)(t0 + tl) * a.sv_t + c);
+            }
+        }
+        // the X elements this thread will consume
+        if (valid) {
+            const TX* src = D + (long long)o + (long long)t0 * a.nown;
+#pragma unroll 4
+            for (int tl = 0; tl < cnt; ++tl) cp_async_elem<TX>(ds + tl * NT + tid, src + (long long)tl * a.nown);
+        }
+    };
+
+    TC u[KP], acc[KP];
+#pragma unroll
+    for (int c = 0; c < KP; ++c) {
+        u[c] = (TC)0;
+        acc[c] = (TC)0;
+    }
+    if (valid) {
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+            if (c < k) u[c] = U[(long long)o * a.su_o + (long long)c * a.su_a];
+    }
+
+#pragma unroll
+    for (int c = 0; c < ST - 1; ++c) {
+        if (c < nchunks) issue(c);
+        cp_async_commit();
+    }
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+        cp_async_wait<ST - 2>();
+        __syncthreads();  // chunk's data visible to all; everyone is done with the stage refilled below
+        if (chunk + ST - 1 < nchunks) issue(chunk + ST - 1);
+        cp_async_commit();
+        const int stage = chunk % ST;
+        const int t0 = t_begin + chunk * TCH;
+        const int cnt = min(TCH, t_end - t0);
+        const TC* vs = Vs + (size_t)stage * TCH * KP;
+        const TX* ds = Ds + (size_t)stage * TCH * NT + tid;
+        if (valid) {
+            constexpr int UNR = 2;
+            for (int tl = 0; tl < cnt; tl += UNR) {
+                TC x[UNR];
+                const TC* vrow[UNR];
+                bool live[UNR];
+#pragma unroll
+                for (int q = 0; q < UNR; ++q) {
+                    live[q] = (tl + q < cnt);
+                    const int tq = live[q] ? (tl + q) : tl;
+                    const TX xr = ds[tq * NT];
+                    x[q] = (TC)xr;
+                    if (HASNAN) {
+                        if (xr != xr)
+                            x[q] = a.first_iter ? lambda
+                                                : ximp[a.transposed ? ((long long)(t0 + tq) + (long long)o * a.ldimp)
+                                                                    : ((long long)o + (long long)(t0 + tq) * a.ldimp)];
+                    }
+                    vrow[q] = vs + tq * KP;
+                }
+                kl_group<TC, K, KP, UNR>(x, vrow, live, u, acc);
+            }
+        }
+    }
+    cp_async_wait<0>();
+    if (!valid) return;
+    if (a.S == 1) {
+        const TC* den = static_cast<const TC*>(a.den) + (long long)r * 32;
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+            if (c < k) U[(long long)o * a.su_o + (long long)c * a.su_a] = div_cold<TC>(u[c] * acc[c], den[c]);
+    } else {
+        TC* dst = static_cast<TC*>(a.partial) + (((long long)slice * a.R + r) * a.nown + o) * K;
+#pragma unroll
+        for (int c = 0; c < K; ++c) dst[c] = acc[c];
+    }
+}
+
+// S > 1: U[o,a] <- (U[o,a] * sum_slices partial) / den, slices added in order
+template <typename TC, int K>
+__global__ void tiled_combine_kernel(const TiledPassArgs a) {
+    const int r = blockIdx.y;
+    if (a.st[r].stop != 0) return;
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= a.nown) return;
+    TC* U = static_cast<TC*>(a.U) + (long long)r * a.u_rstride;
+    const TC* den = static_cast<const TC*>(a.den) + (long long)r * 32;
+    TC acc[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) acc[c] = (TC)0;
+    for (int s = 0; s < a.S; ++s) {
+        const TC* src = static_cast<const TC*>(a.partial) + (((long long)s * a.R + r) * a.nown + o) * K;
+#pragma unroll
+        for (int c = 0; c < K; ++c) acc[c] += src[c];
+    }
+#pragma unroll
+    for (int c = 0; c < K; ++c)
+        if (c < a.k) {
+            const long long idx = (long long)o * a.su_o + (long long)c * a.su_a;
+            U[idx] = div_cold<TC>(U[idx] * acc[c], den[c]);
+        }
+}
+
+// den[r][a] = sum_t V_r[t,a] : grid (k, R), fixed-order block reduction
+template <typename TC>
+__global__ void __launch_bounds__(256) tiled_sums_kernel(const void* Vv, long long v_rstride, long long sv_t,
+                                                         long long sv_a, int nred, const UnitState* st, void* denv) {
+    __shared__ double red[40];
+    const int c = blockIdx.x, r = blockIdx.y;
+    if (st[r].stop != 0) return;
+    const TC* V = static_cast<const TC*>(Vv) + (long long)r * v_rstride + (long long)c * sv_a;
+    double s = 0.0;
+    for (int t = threadIdx.x; t < nred; t += blockDim.x) s += (double)V[(long long)t * sv_t];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) static_cast<TC*>(denv)[(long long)r * 32 + c] = (TC)s;
+}
+
+// sum over non-NaN entries of ((x - W_r H_r) w)^2 and (x - W_r H_r)^2 for 128 rows x all columns;
+// partials[(r*nblk + b)*2 + {0,1}].  only_running: skip finished restarts (the :74 check);
+// restore: substituted zeros count as 0 (final objective).
+template <typename TX, typename TC>
+__global__ void __launch_bounds__(128) tiled_objective_kernel(const TX* __restrict__ X, int n, int m, int k,
+                                                              const TC* __restrict__ Wst, const TC* __restrict__ Hst,
+                                                              const UnitState* st, TC lambda, int restore,
+                                                              int only_running, double weight,
+                                                              double* __restrict__ partials) {
+    extern __shared__ unsigned char smraw[];
+    TC* Ws = reinterpret_cast<TC*>(smraw);  // [k][128]
+    __shared__ double red[2][4];
+    const int r = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
+    const bool stopped = st[r].stop != 0;
+    if (only_running ? stopped : (st[r].done != 0 || !stopped)) return;
+    const TC* W = Wst + (long long)r * n * k;
+    const TC* H = Hst + (long long)r * k * m;
+    const int i = b * 128 + tid;
+    for (int c = 0; c < k; ++c) Ws[c * 128 + tid] = (i < n) ? W[(long long)i + (long long)c * n] : (TC)0;
+    __syncthreads();
+    double sw = 0.0, s1 = 0.0;
+    if (i < n) {
+        for (int j = 0; j < m; ++j) {
+            const TX xr = X[(long long)i + (long long)j * n];
+            if (xr != xr) continue;
+            TC x = (TC)xr;
+            if (restore && x == lambda) x = (TC)0;
+            const TC* h = H + (long long)j * k;
+            TC p = (TC)0;
+            for (int c = 0; c < k; ++c) p = fma(Ws[c * 128 + tid], __ldg(h + c), p);
+            const double e = (double)(x - p);
+            s1 = fma(e, e, s1);
+            const double ew = e * weight;
+            sw = fma(ew, ew, sw);
+        }
+    }
+    sw = warp_sum(sw);
+    s1 = warp_sum(s1);
+    if ((tid & 31) == 0) {
+        red[0][tid >> 5] = sw;
+        red[1][tid >> 5] = s1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int w = 0; w < 4; ++w) {
+            a0 += red[0][w];
+            a1 += red[1][w];
+        }
+        partials[((long long)r * gridDim.x + b) * 2] = a0;
+        partials[((long long)r * gridDim.x + b) * 2 + 1] = a1;
+    }
+}
+
+// X[inan] = (W*H)[inan] (:72) for every running restart
+template <typename TX, typename TC>
+__global__ void __launch_bounds__(128) tiled_impute_kernel(const TX* __restrict__ X, int n, int m, int k,
+                                                           const TC* __restrict__ Wst, const TC* __restrict__ Hst,
+                                                           const UnitState* st, TC* __restrict__ ximp) {
+    const int r = blockIdx.y;
+    if (st[r].stop != 0) return;
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    const TC* W = Wst + (long long)r * n * k;
+    const TC* H = Hst + (long long)r * k * m;
+    TC* xi = ximp + (long long)r * n * m;
+    for (int j = 0; j < m; ++j) {
+        const TX xr = X[(long long)i + (long long)j * n];
+        if (xr == xr) continue;
+        TC p = (TC)0;
+        for (int c = 0; c < k; ++c) p = fma(W[(long long)i + (long long)c * n], H[(long long)j * k + c], p);
+        xi[(long long)i + (long long)j * n] = p;
+    }
+}
+
+struct TiledCheckArgs {
+    void* W;
+    void* H;
+    UnitState* st;
+    int32_t* canon;
+    const double* partials;  // R x nblk x 2
+    int n, m, k, nblk;
+    int it;                  // iteration just completed
+    int maxbad, stopconv;
+    double tol, tolOF, eps_clamp;
+    int* active_count;
+};
+
+// the every-10th-iteration block of NMFmultiplicative (:73-116) for one restart per CTA
+template <typename TC>
+__global__ void __launch_bounds__(256) tiled_check_kernel(const TiledCheckArgs a) {
+    extern __shared__ int smi[];
+    int* idx = smi;           // m
+    int* first = smi + a.m;   // k
+    __shared__ double s_obj;
+    __shared__ int s_stop;
+    const int r = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+    UnitState* st = a.st + r;
+    if (st->stop != 0) return;
+    const int n = a.n, m = a.m, k = a.k;
+    TC* W = static_cast<TC*>(a.W) + (long long)r * n * k;
+    TC* H = static_cast<TC*>(a.H) + (long long)r * k * m;
+    int32_t* canon_old = a.canon + (long long)r * m;
+    if (tid == 0) {
+        double obj = 0.0;
+        for (int b = 0; b < a.nblk; ++b) obj += a.partials[((long long)r * a.nblk + b) * 2];
+        s_obj = obj;
+        int stop = 0;
+        int bad = st->bad, re = st->re;
+        double best = st->best;
+        st->obj_chk = obj;
+        if (obj < a.tol) {
+            stop = 2;  // :75-78 (before the clamp)
+        } else {
+            if (obj < best) {
+                if ((best - obj) < a.tolOF)
+                    ++bad;
+                else
+                    bad = 0;
+                best = obj;
+            } else {
+                ++bad;
+            }
+            if (bad >= a.maxbad) {
+                ++re;
+                bad = 0;
+            }
+            st->bad = bad;
+            st->re = re;
+            st->best = best;
+        }
+        s_stop = stop;
+    }
+    __syncthreads();
+    if (s_stop == 2) {
+        if (tid == 0) {
+            st->stop = 2;
+            st->it = a.it;
+        }
+        return;
+    }
+    const TC epsc = (TC)a.eps_clamp;
+    for (long long e = tid; e < (long long)n * k; e += NT) {
+        const TC v = W[e];
+        W[e] = (v != v) ? v : (v < epsc ? epsc : v);
+    }
+    for (long long e = tid; e < (long long)k * m; e += NT) {
+        const TC v = H[e];
+        H[e] = (v != v) ? v : (v < epsc ? epsc : v);
+    }
+    for (int c = tid; c < k; c += NT) first[c] = INT_MAX;
+    __syncthreads();
+    for (int j = tid; j < m; j += NT) {
+        const TC* h = H + (long long)j * k;
+        TC bv = h[0];
+        int bi = 0;
+        for (int c = 1; c < k; ++c) {
+            const TC v = h[c];
+            const bool take = (bv != bv) ? false : ((v != v) ? true : (v < bv));
+            if (take) {
+                bv = v;
+                bi = c;
+            }
+        }
+        idx[j] = bi;
+        atomicMin(&first[bi], j);
+    }
+    __syncthreads();
+    const int has_cons = st->has_cons;
+    int same = 1;
+    for (int j = tid; j < m; j += NT) {
+        const int c = first[idx[j]];
+        if (!has_cons || canon_old[j] != c) same = 0;
+        idx[j] = c;
+    }
+    same = __syncthreads_and(same);
+    int inc = st->inc;
+    __syncthreads();
+    inc = same ? inc + 1 : 0;
+    const bool stopc = inc > a.stopconv;
+    if (!stopc)
+        for (int j = tid; j < m; j += NT) canon_old[j] = idx[j];
+    if (tid == 0) {
+        st->inc = inc;
+        st->it = a.it;
+        if (stopc)
+            st->stop = 4;
+        else
+            st->has_cons = 1;
+    }
+}
+
+// post-run: objective sums -> state, then normalisation (NMFkExecute.jl:791-804); one CTA per restart
+template <typename TC>
+__global__ void __launch_bounds__(256) tiled_finish_kernel(void* Wv, void* Hv, UnitState* stv, const double* partials,
+                                                           int n, int m, int k, int nblk, int normalize) {
+    __shared__ double red[40];
+    __shared__ double tot[32];
+    const int r = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+    UnitState* st = stv + r;
+    if (st->stop == 0 || st->done != 0) return;
+    TC* W = static_cast<TC*>(Wv) + (long long)r * n * k;
+    TC* H = static_cast<TC*>(Hv) + (long long)r * k * m;
+    if (tid == 0) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int b = 0; b < nblk; ++b) {
+            a0 += partials[((long long)r * nblk + b) * 2];
+            a1 += partials[((long long)r * nblk + b) * 2 + 1];
+        }
+        st->obj_ssq = a0;
+        st->obj_norm = sqrt(a1);
+    }
+    if (normalize == 1) {  // total = sum(H; dims=2); W .*= total'; H ./= total
+        for (int c = 0; c < k; ++c) {
+            double s = 0.0;
+            for (int j = tid; j < m; j += NT) s += (double)H[(long long)j * k + c];
+            s = block_sum(s, red);
+            if (tid == 0) tot[c] = (double)(TC)s;
+        }
+        __syncthreads();
+        for (long long e = tid; e < (long long)n * k; e += NT) W[e] = W[e] * (TC)tot[e / n];
+        for (long long e = tid; e < (long long)k * m; e += NT) H[e] = div_cold<TC>(H[e], (TC)tot[e % k]);
+    } else if (normalize == 2) {  // total = sum(W; dims=1); W ./= total; H .*= total'
+        for (int c = 0; c < k; ++c) {
+            double s = 0.0;
+            for (int i = tid; i < n; i += NT) s += (double)W[(long long)i + (long long)c * n];
+            s = block_sum(s, red);
+            if (tid == 0) tot[c] = (double)(TC)s;
+        }
+        __syncthreads();
+        for (long long e = tid; e < (long long)n * k; e += NT) W[e] = div_cold<TC>(W[e], (TC)tot[e / n]);
+        for (long long e = tid; e < (long long)k * m; e += NT) H[e] = H[e] * (TC)tot[e % k];
+    }
+    __syncthreads();
+    if (tid == 0) st->done = 1;
+}
+
+// loop guard of :64 evaluated on the device between iterations: marks restarts that must not start
+// another iteration and counts the ones still running
+static __global__ void tiled_guard_kernel(UnitState* st, int R, int it, int maxiter, int maxbad, int maxre, int iter_limit,
+                                   int* active_count) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    UnitState* s = st + r;
+    if (s->stop != 0) return;
+    s->it = it;
+    if (it >= maxiter)
+        s->stop = 1;
+    else if (s->bad >= maxbad)
+        s->stop = 5;
+    else if (s->re >= maxre)
+        s->stop = 3;
+    else if (!(iter_limit > 0 && it >= iter_limit))
+        atomicAdd(active_count, 1);
+}
+
+template <typename TX, typename TC, int K>
+cudaError_t launch_tiled_pass_k(const TiledPassArgs& a, cudaStream_t s) {
+    constexpr int VEC = VecOf<TC>::N;
+    constexpr int KP = (K + VEC - 1) / VEC * VEC;
+    constexpr int TCH = TiledCfg<TX>::TCH;
+    const size_t smem = (size_t)kTiledStages * TCH * (KP * sizeof(TC) + kTiledThreads * sizeof(TX));
+    const long long grid = (long long)a.S * a.nblocks * a.R;
+    if (grid > 2147483647ll) return cudaErrorInvalidValue;
+    cudaError_t e;
+    if (a.has_nan) {
+        e = cudaFuncSetAttribute(tiled_pass_kernel<TX, TC, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        tiled_pass_kernel<TX, TC, K, true><<<(unsigned)grid, kTiledThreads, smem, s>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(tiled_pass_kernel<TX, TC, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        tiled_pass_kernel<TX, TC, K, false><<<(unsigned)grid, kTiledThreads, smem, s>>>(a);
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (a.S > 1) {
+        dim3 g((a.nown + 255) / 256, a.R);
+        tiled_combine_kernel<TC, K><<<g, 256, 0, s>>>(a);
+        e = cudaGetLastError();
+    }
+    return e;
+}
+
+}  // namespace nmfk
+
+// ------------------------------------------------------------------------------------------
+// host driver (one instantiation per dtype)
+// ------------------------------------------------------------------------------------------
+namespace nmfk {
+
+template <typename TX, typename TC>
+cudaError_t dispatch_tiled_pass(const TiledPassArgs& a, cudaStream_t s) {
+    const int kt = resident_template_k(a.k);
+    NMFK_DISPATCH_K(launch_tiled_pass_k, TX, TC, kt, a, s)
+}
+
+#define NMFK_TRY(call)                      \
+    do {                                    \
+        cudaError_t e__ = (call);           \
+        if (e__ != cudaSuccess) {           \
+            err = e__;                      \
+            goto done;                      \
+        }                                   \
+    } while (0)
+
+template <typename TX, typename TC>
+cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches) {
+    const int n = a.n, m = a.m, k = a.k, R = a.R;
+    const int kt = resident_template_k(k);
+    if (kt < 0) return cudaErrorInvalidValue;
+    cudaError_t err = cudaSuccess;
+    int sms = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int nblkH = (m + kTiledThreads - 1) / kTiledThreads;  // H-update: own = columns
+    const int nblkW = (n + kTiledThreads - 1) / kTiledThreads;  // W-update: own = rows
+    constexpr int TCH = TiledCfg<TX>::TCH;
+    auto slices = [&](int nblk, int nred) {
+        const long long target = 4ll * sms;
+        long long S = (target + (long long)nblk * R - 1) / ((long long)nblk * R);
+        const long long smax = std::max(1, nred / (TCH * 8));
+        if (S > smax) S = smax;
+        if (S < 1) S = 1;
+        return (int)S;
+    };
+    const int SH = slices(nblkH, n), SW = slices(nblkW, m);
+    const int nblkObj = (n + 127) / 128;
+
+    TC* den = nullptr;
+    TC* partial = nullptr;
+    double* objp = nullptr;
+    int* d_active = nullptr;
+    int* h_active = nullptr;
+    std::vector<UnitState> hst((size_t)R);
+    int it = 0;
+    bool any_running = false;
+    const size_t psz = std::max((size_t)(SH > 1 ? (size_t)SH * R * m * kt : 0), (size_t)(SW > 1 ? (size_t)SW * R * n * kt : 0));
+
+    NMFK_TRY(cudaMalloc(&den, (size_t)R * 32 * sizeof(TC)));
+    if (psz) NMFK_TRY(cudaMalloc(&partial, psz * sizeof(TC)));
+    NMFK_TRY(cudaMalloc(&objp, (size_t)R * nblkObj * 2 * sizeof(double)));
+    NMFK_TRY(cudaMalloc(&d_active, sizeof(int)));
+    NMFK_TRY(cudaMallocHost(&h_active, sizeof(int)));
+    NMFK_TRY(cudaMemcpyAsync(hst.data(), a.st, (size_t)R * sizeof(UnitState), cudaMemcpyDeviceToHost, s));
+    NMFK_TRY(cudaStreamSynchronize(s));
+    for (auto& u : hst)
+        if (u.stop == 0 && !u.done) {
+            any_running = true;
+            it = std::max(it, (int)u.it);
+        }
+    if (any_running) {
+        // restarts of one batch advance in lockstep
+        TiledPassArgs ph{}, pw{};
+        ph.D = a.Xt;
+        ph.U = a.H;
+        ph.V = a.W;
+        ph.den = den;
+        ph.partial = SH > 1 ? partial : nullptr;
+        ph.st = a.st;
+        ph.ximp = a.ximp;
+        ph.u_rstride = (long long)k * m;
+        ph.v_rstride = (long long)n * k;
+        ph.su_o = k;
+        ph.su_a = 1;
+        ph.sv_t = 1;
+        ph.sv_a = n;
+        ph.nown = m;
+        ph.nred = n;
+        ph.k = k;
+        ph.R = R;
+        ph.S = SH;
+        ph.nblocks = nblkH;
+        ph.transposed = 1;
+        ph.ldimp = n;
+        ph.has_nan = a.has_nan;
+        ph.lambda = a.lambda;
+        pw = ph;
+        pw.D = a.X;
+        pw.U = a.W;
+        pw.V = a.H;
+        pw.partial = SW > 1 ? partial : nullptr;
+        pw.u_rstride = (long long)n * k;
+        pw.v_rstride = (long long)k * m;
+        pw.su_o = 1;
+        pw.su_a = n;
+        pw.sv_t = k;
+        pw.sv_a = 1;
+        pw.nown = n;
+        pw.nred = m;
+        pw.S = SW;
+        pw.nblocks = nblkW;
+        pw.transposed = 0;
+
+        if (a.has_nan && it > 0) {  // resume: rebuild X[inan] = (W*H)[inan]
+            dim3 g((n + 127) / 128, R);
+            tiled_impute_kernel<TX, TC><<<g, 128, 0, s>>>((const TX*)a.X, n, m, k, (const TC*)a.W, (const TC*)a.H, a.st,
+                                                          (TC*)a.ximp);
+            NMFK_TRY(cudaGetLastError());
+            ++*launches;
+        }
+        bool need_guard = true;
+        while (true) {
+            if (need_guard) {
+                NMFK_TRY(cudaMemsetAsync(d_active, 0, sizeof(int), s));
+                tiled_guard_kernel<<<(R + 127) / 128, 128, 0, s>>>(a.st, R, it, a.maxiter, a.maxbad, a.maxre, a.iter_limit,
+                                                                   d_active);
+                NMFK_TRY(cudaGetLastError());
+                ++*launches;
+                NMFK_TRY(cudaMemcpyAsync(h_active, d_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+                NMFK_TRY(cudaStreamSynchronize(s));
+                if (*h_active == 0) break;
+                need_guard = false;
+            }
+            ++it;
+            ph.first_iter = pw.first_iter = (it == 1);
+            if (!a.Hfixed) {
+                tiled_sums_kernel<TC><<<dim3(k, R), 256, 0, s>>>(a.W, (long long)n * k, 1, n, n, a.st, den);
+                NMFK_TRY(cudaGetLastError());
+                NMFK_TRY((dispatch_tiled_pass<TX, TC>(ph, s)));
+                *launches += 2 + (SH > 1);
+            }
+            if (!a.Wfixed) {
+                tiled_sums_kernel<TC><<<dim3(k, R), 256, 0, s>>>(a.H, (long long)k * m, k, 1, m, a.st, den);
+                NMFK_TRY(cudaGetLastError());
+                NMFK_TRY((dispatch_tiled_pass<TX, TC>(pw, s)));
+                *launches += 2 + (SW > 1);
+            }
+            if (a.has_nan) {
+                dim3 g((n + 127) / 128, R);
+                tiled_impute_kernel<TX, TC><<<g, 128, 0, s>>>((const TX*)a.X, n, m, k, (const TC*)a.W, (const TC*)a.H,
+                                                              a.st, (TC*)a.ximp);
+                NMFK_TRY(cudaGetLastError());
+                ++*launches;
+            }
+            if (it % a.check_every == 0) {
+                dim3 g(nblkObj, R);
+                tiled_objective_kernel<TX, TC><<<g, 128, (size_t)k * 128 * sizeof(TC), s>>>(
+                    (const TX*)a.X, n, m, k, (const TC*)a.W, (const TC*)a.H, a.st, (TC)a.lambda, 0, 1, a.weight, objp);
+                NMFK_TRY(cudaGetLastError());
+                TiledCheckArgs c{};
+                c.W = a.W;
+                c.H = a.H;
+                c.st = a.st;
+                c.canon = a.canon;
+                c.partials = objp;
+                c.n = n;
+                c.m = m;
+                c.k = k;
+                c.nblk = nblkObj;
+                c.it = it;
+                c.maxbad = a.maxbad;
+                c.stopconv = a.stopconv;
+                c.tol = a.tol;
+                c.tolOF = a.tolOF;
+                c.eps_clamp = a.eps_clamp;
+                tiled_check_kernel<TC><<<R, 256, (size_t)(m + k) * sizeof(int), s>>>(c);
+                NMFK_TRY(cudaGetLastError());
+                *launches += 2;
+                need_guard = true;
+            }
+            if (it >= a.maxiter || (a.iter_limit > 0 && it >= a.iter_limit)) need_guard = true;
+        }
+    }
+    {
+        // post-run objective on the restored X + normalisation for restarts that stopped in this call
+        dim3 g(nblkObj, R);
+        tiled_objective_kernel<TX, TC><<<g, 128, (size_t)k * 128 * sizeof(TC), s>>>(
+            (const TX*)a.X, n, m, k, (const TC*)a.W, (const TC*)a.H, a.st, (TC)a.lambda, 1, 0, a.weight, objp);
+        NMFK_TRY(cudaGetLastError());
+        tiled_finish_kernel<TC><<<R, 256, 0, s>>>(a.W, a.H, a.st, objp, n, m, k, nblkObj, a.normalize);
+        NMFK_TRY(cudaGetLastError());
+        *launches += 2;
+        NMFK_TRY(cudaStreamSynchronize(s));
+    }
+done:
+    if (den) cudaFree(den);
+    if (partial) cudaFree(partial);
+    if (objp) cudaFree(objp);
+    if (d_active) cudaFree(d_active);
+    if (h_active) cudaFreeHost(h_active);
+    return err;
+}
+
+}  // namespace nmfk

@@ -43,6 +43,30 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, 
     if (s == -1.2345) out[0] = s;
 }
 
+// dependent-issue latency (cycles per instruction) of DFMA (which=0), FFMA (1), MUFU.RCP64H+DFMA pair (2)
+__global__ void latency_kernel(double* out, int iters, int which, double a, double b) {
+    double x = a + threadIdx.x;
+    float xf = (float)a + threadIdx.x;
+    const long long t0 = clock64();
+    if (which == 0) {
+        for (int i = 0; i < iters; ++i) x = fma(x, a, b);
+    } else if (which == 1) {
+        const float af = (float)a, bf = (float)b;
+        for (int i = 0; i < iters; ++i) xf = fmaf(xf, af, bf);
+    } else {
+        for (int i = 0; i < iters; ++i) {
+            double r;
+            asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+            x = fma(r, a, b);
+        }
+    }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) {
+        out[0] = (double)(t1 - t0) / iters;
+        out[1] = x + xf;
+    }
+}
+
 __global__ void copy_kernel(const double4* __restrict__ src, double4* __restrict__ dst, long long n4) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
         dst[i] = src[i];
@@ -121,6 +145,19 @@ cudaError_t measure_peak(int which, double* value, cudaStream_t s) {
         cudaFree(b);
         if (e != cudaSuccess) return e;
         *value = 2.0 * (double)bytes / (ms * 1e-3) / 1e9;
+        return cudaSuccess;
+    }
+    if (which >= 4 && which <= 6) {  // latencies in SM cycles: 4 DFMA, 5 FFMA, 6 RCP64H+DFMA
+        double* out = nullptr;
+        if ((e = cudaMalloc(&out, 64)) != cudaSuccess) return e;
+        latency_kernel<<<1, 32, 0, s>>>(out, 8192, which - 4, 1.0000001, 1e-9);
+        latency_kernel<<<1, 32, 0, s>>>(out, 8192, which - 4, 1.0000001, 1e-9);
+        double h[2] = {0, 0};
+        e = cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        cudaFree(out);
+        if (e != cudaSuccess) return e;
+        *value = h[0];
         return cudaSuccess;
     }
     return cudaErrorInvalidValue;

@@ -240,3 +240,65 @@ def test_c2_shape_sweep_properties(ctx):
         if k >= 5:
             assert g["obj_norm"].min() < 1.0
         b.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# tiled engine (factors streamed; BASELINE configs C3-C5), forced on small shapes via engine=2
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,m,k,niter,dt", [(1000, 200, 10, 22, np.float64), (300, 64, 13, 22, np.float64),
+                                            (5000, 40, 4, 21, np.float64), (40, 3000, 3, 21, np.float64),
+                                            (700, 300, 32, 12, np.float64), (777, 333, 7, 21, np.float32),
+                                            (15, 5, 3, 40, np.float64)])
+def test_tiled_trace_parity(ctx, n, m, k, niter, dt):
+    X = synth.mixture(n, m, 3, seed=17, dtype=dt)
+    W0, H0 = synth.philox_inits(23, 1, n, k, m, dtype=dt)
+    Wt, Ht, ob = nb.trace(X, k, W0[0], H0[0], niter, ctx=ctx, engine=2)
+    Wr, Hr, obr = oracle_trace(X, k, W0[0], H0[0], niter)
+    tol = RTOL64 if dt == np.float64 else RTOL32
+    for t in range(niter):
+        assert relerr(Wt[t], Wr[t]) < tol, ("W", t)
+        assert relerr(Ht[t], Hr[t]) < tol, ("H", t)
+    if dt == np.float64:
+        assert np.allclose(ob, obr, rtol=1e-7, atol=1e-18 + 1e-9 * obr.max())
+
+
+def test_tiled_nan_and_fixed(ctx):
+    rng = np.random.default_rng(5)
+    Xn = synth.mixture(300, 70, 3, seed=2)
+    Xn[rng.random(Xn.shape) < 0.15] = np.nan
+    Xn[rng.random(Xn.shape) < 0.05] = 0.0
+    W0, H0 = synth.philox_inits(5, 1, 300, 3, 70)
+    Wt, Ht, ob = nb.trace(Xn, 3, W0[0], H0[0], 25, ctx=ctx, engine=2)
+    Wr, Hr, obr = oracle_trace(Xn, 3, W0[0], H0[0], 25)
+    for t in (0, 1, 9, 10, 24):
+        assert relerr(Wt[t], Wr[t]) < RTOL64 and relerr(Ht[t], Hr[t]) < RTOL64, t
+    X = synth.mixture(300, 70, 3, seed=2)
+    for kw in ({"Wfixed": True}, {"Hfixed": True}):
+        Wt, Ht, ob = nb.trace(X, 3, W0[0], H0[0], 15, ctx=ctx, engine=2, **kw)
+        Wr, Hr, obr = oracle_trace(X, 3, W0[0], H0[0], 15, **kw)
+        assert relerr(Wt[-1], Wr[-1]) < RTOL64 and relerr(Ht[-1], Hr[-1]) < RTOL64
+
+
+def test_tiled_full_stop_rule_matches_resident_and_oracle(ctx):
+    """Same restarts through both engines with the reference stop rule: identical iteration
+    counts and stop reasons, factors equal to rounding; and equal to the oracle."""
+    X = synth.readme_bss()
+    k, R = 3, 6
+    W0, H0 = synth.philox_inits(100, R, 15, k, 5)
+    ctx.set_X(X)
+    res = {}
+    for eng in (1, 2):
+        b = ctx.batch(k, R)
+        b.set_init(W0, H0)
+        ctx.solve([b], nb.default_params(engine=eng))
+        res[eng] = b.get()
+        b.close()
+    assert np.array_equal(res[1]["iters"], res[2]["iters"])
+    assert np.array_equal(res[1]["stop_reason"], res[2]["stop_reason"])
+    assert relerr(res[2]["W"], res[1]["W"]) < 1e-8 and relerr(res[2]["H"], res[1]["H"]) < 1e-8
+    assert np.allclose(res[2]["obj_norm"], res[1]["obj_norm"], rtol=1e-6, atol=1e-12)
+    for r in range(R):
+        inf = {}
+        W, H, of = o.execute_singlerun_compute(X.copy(), k, Winit=W0[r].copy(), Hinit=H0[r].copy(), info=inf)
+        assert res[2]["iters"][r] == inf["iters"]
+        assert relerr(res[2]["W"][r], W) < 1e-7 and relerr(res[2]["H"][r], H) < 1e-7

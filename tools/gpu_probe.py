@@ -22,7 +22,8 @@ except Exception as e:  # pragma: no cover
 
 ctx = nb.Context(0)
 peaks = {}
-for name, which in (("fp64_dfma_tflops", 0), ("fp64_dmma_tflops", 1), ("fp32_ffma_tflops", 2), ("copy_gbs", 3)):
+for name, which in (("fp64_dfma_tflops", 0), ("fp64_dmma_tflops", 1), ("fp32_ffma_tflops", 2), ("copy_gbs", 3),
+                    ("lat_dfma_cyc", 4), ("lat_ffma_cyc", 5), ("lat_rcp64h_dfma_cyc", 6)):
     peaks[name] = [ctx.measure_peak(which) for _ in range(2)]
 out["peaks"] = peaks
 
@@ -60,6 +61,10 @@ res.append(dict(tag="C2 full stop rule k=2:10 R=100", **run(range(2, 11), 100)))
 res.append(dict(tag="C2 full stop rule k=2:10 R=100 (repeat)", **run(range(2, 11), 100)))
 out["runs"] = res
 
+# tiled engine on the same shape (engine=2) and on a mid-size shape it is meant for
+res.append(dict(tag="TILED fixed100 k=10 R=100", **run([10], 100, maxiter=100, engine=2)))
+res.append(dict(tag="TILED fixed100 k=4 R=100", **run([4], 100, maxiter=100, engine=2)))
+out["runs"] = res
 # end-to-end execute (solve + clustering + selection) through the public API
 t0 = time.perf_counter()
 det = {}
@@ -73,5 +78,15 @@ res32 = []
 for k in (4, 10):
     res32.append(dict(tag="f32 fixed100 k=%d R=296" % k, **run([k], 296, maxiter=100)))
 out["runs_f32"] = res32
+# mid-size shapes for the tiled engine: f32 4000x4000 k=16 R=16 and f64 20000x1000 k=16 R=16
+Xm = synth.mixture(4000, 4000, 16, seed=3, dtype=np.float32)
+ctx.set_X(Xm)
+n, m = Xm.shape
+out["runs_tiled"] = [dict(tag="TILED f32 4000x4000 k=16 R=16 20it", **run([16], 16, maxiter=20))]
+Xm = synth.mixture(20000, 1000, 8, seed=3)
+ctx.set_X(Xm)
+n, m = Xm.shape
+out["runs_tiled"].append(dict(tag="TILED f64 20000x1000 k=16 R=16 20it", **run([16], 16, maxiter=20)))
+out["runs_tiled"].append(dict(tag="TILED f64 20000x1000 k=32 R=32 20it", **run([32], 32, maxiter=20)))
 ctx.close()
 print(json.dumps(out, indent=1))
