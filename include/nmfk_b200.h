@@ -131,6 +131,20 @@ int32_t nmfk_batch_get(nmfk_batch* b, void* W_out, void* H_out, double* obj_ssq,
  * lambda-substituted X, i.e. the quantity of NMFkMultiplicative.jl:74, for every restart. */
 int32_t nmfk_batch_objective(nmfk_batch* b, double weight, double* obj_ssq);
 
+/* ---- multi-GPU plumbing (restart sharding, NMFkExecute.jl:511-526 `pmap` over restarts) ------------
+ * One process per GPU: every rank solves its own restarts; the H stacks and objectives are then
+ * all-gathered (NCCL via torch.distributed on the device pointers below) and the rank that owns a
+ * k imports them into an H-only batch to run nmfk_batch_cluster over all R_total solutions. */
+int32_t nmfk_batch_create_hstack(nmfk_ctx* ctx, int32_t k, int32_t R, nmfk_batch** out); /* no W stack */
+/* device pointers of the factor stacks (W may come back NULL for an H-only batch) */
+int32_t nmfk_batch_device_ptrs(nmfk_batch* b, void** W, void** H);
+/* load finished solutions: H (k x m x R) and optionally W from host or device memory, plus the
+ * objective (NMFkExecute.jl:792) and iteration count of every restart; marks them done */
+int32_t nmfk_batch_import(nmfk_batch* b, const void* W, const void* H, const double* obj_norm,
+                          const int32_t* iters, int32_t on_device);
+/* phi = normnan(X - W*H) with NaN residuals dropped (NMFkExecute.jl:664-668) for host factors */
+int32_t nmfk_fit(nmfk_ctx* ctx, int32_t k, const void* W, const void* H, double* phi);
+
 /* ---- robustness: replaces sortperm + clustersolutions + finalize (NMFkExecute.jl:545-638,
  *      NMFkCluster.jl:425-517, NMFkFinalize.jl:36-79) on the device-resident H stack ----------
  * order        R      0-based restart indices sorted by objective (stable), order[0] = best

@@ -49,6 +49,7 @@ struct nmfk_batch {
 };
 
 static thread_local std::string g_err;
+static int32_t residual(nmfk_ctx* c, int k, const void* W, const void* H, int restore, double weight, double out[2]);
 
 static size_t esize(int dtype) { return dtype == NMFK_F64 ? 8 : 4; }
 
@@ -236,6 +237,60 @@ int32_t nmfk_batch_create(nmfk_ctx* c, int32_t k, int32_t R, nmfk_batch** out) {
     return NMFK_OK;
 }
 
+int32_t nmfk_batch_create_hstack(nmfk_ctx* c, int32_t k, int32_t R, nmfk_batch** out) {
+    if (!c || !out) return fail(c, NMFK_E_INVALID, "nmfk_batch_create_hstack: NULL argument");
+    *out = nullptr;
+    if (!c->has_X) return fail(c, NMFK_E_NO_X, "nmfk_set_X has not been called");
+    if (k < 1 || R < 1) return fail(c, NMFK_E_INVALID, "nmfk_batch_create_hstack: k and R must be >= 1");
+    CU(c, cudaSetDevice(c->device));
+    nmfk_batch* b = new nmfk_batch();
+    b->ctx = c;
+    b->k = k;
+    b->R = R;
+    cudaError_t e = cudaMalloc(&b->H, (size_t)k * c->m * R * esize(c->dtype));
+    if (e == cudaSuccess) e = cudaMalloc(&b->st, (size_t)R * sizeof(UnitState));
+    if (e != cudaSuccess) {
+        nmfk_batch_destroy(b);
+        CU(c, e);
+    }
+    *out = b;
+    return NMFK_OK;
+}
+
+int32_t nmfk_batch_device_ptrs(nmfk_batch* b, void** W, void** H) {
+    if (!b) return fail(nullptr, NMFK_E_INVALID, "nmfk_batch_device_ptrs: NULL batch");
+    if (W) *W = b->W;
+    if (H) *H = b->H;
+    return NMFK_OK;
+}
+
+int32_t nmfk_batch_import(nmfk_batch* b, const void* W, const void* H, const double* obj_norm, const int32_t* iters,
+                          int32_t on_device) {
+    if (!b || !H || !obj_norm) return fail(b ? b->ctx : nullptr, NMFK_E_INVALID, "nmfk_batch_import: NULL argument");
+    nmfk_ctx* c = b->ctx;
+    CU(c, cudaSetDevice(c->device));
+    const size_t es = esize(c->dtype);
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (W) {
+        if (!b->W) return fail(c, NMFK_E_INVALID, "nmfk_batch_import: this batch has no W stack");
+        CU(c, cudaMemcpyAsync(b->W, W, (size_t)c->n * b->k * b->R * es, kind, c->stream));
+    }
+    CU(c, cudaMemcpyAsync(b->H, H, (size_t)b->k * c->m * b->R * es, kind, c->stream));
+    std::vector<UnitState> st((size_t)b->R);
+    for (int r = 0; r < b->R; ++r) {
+        std::memset(&st[r], 0, sizeof(UnitState));
+        st[r].it = iters ? iters[r] : 0;
+        st[r].stop = NMFK_STOP_MAXITER;
+        st[r].done = 1;
+        st[r].best = st[r].obj_chk = st[r].obj_ssq = std::numeric_limits<double>::quiet_NaN();
+        st[r].obj_norm = obj_norm[r];
+    }
+    CU(c, cudaMemcpyAsync(b->st, st.data(), st.size() * sizeof(UnitState), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    b->inited = true;
+    return NMFK_OK;
+}
+
 int32_t nmfk_batch_destroy(nmfk_batch* b) {
     if (!b) return NMFK_OK;
     if (b->ctx) cudaSetDevice(b->ctx->device);
@@ -353,6 +408,7 @@ int32_t nmfk_solve(nmfk_ctx* c, nmfk_batch* const* batches, int32_t nb, const nm
     for (int i = 0; i < nb; ++i) {
         if (!batches[i] || batches[i]->ctx != c) return fail(c, NMFK_E_INVALID, "nmfk_solve: batch of another ctx");
         if (!batches[i]->inited) return fail(c, NMFK_E_INVALID, "nmfk_solve: batch has no initialisation");
+        if (!batches[i]->W || !batches[i]->canon) return fail(c, NMFK_E_INVALID, "nmfk_solve: H-only batch");
     }
     while ((int)c->pool.size() < nb) {
         cudaStream_t s;
@@ -496,8 +552,9 @@ int32_t nmfk_batch_cluster(nmfk_batch* b, int32_t clusterWmatrix, int32_t* order
     const size_t es = esize(c->dtype);
     const int len = clusterWmatrix ? (int)c->n : (int)c->m;
     const int N = R * k, ld = len + 1;
+    if (clusterWmatrix && !b->W) return fail(c, NMFK_E_INVALID, "nmfk_batch_cluster: clusterWmatrix on an H-only batch");
     // nanaction = :zeroed (:566-580)
-    CU(c, launch_zero_nan(b->W, (long long)c->n * k * R, c->dtype, c->stream));
+    if (b->W) CU(c, launch_zero_nan(b->W, (long long)c->n * k * R, c->dtype, c->stream));
     CU(c, launch_zero_nan(b->H, (long long)k * c->m * R, c->dtype, c->stream));
     c->launches += 2;
     ClusterArgs a{};
@@ -567,6 +624,29 @@ int32_t nmfk_batch_cluster(nmfk_batch* b, int32_t clusterWmatrix, int32_t* order
                     ((float*)centroids_out)[(size_t)cc + (size_t)j * k] = (float)v;
             }
     }
+    return NMFK_OK;
+}
+
+int32_t nmfk_fit(nmfk_ctx* c, int32_t k, const void* W, const void* H, double* phi) {
+    if (!c || !W || !H || !phi || k < 1) return fail(c, NMFK_E_INVALID, "nmfk_fit: bad arguments");
+    if (!c->has_X) return fail(c, NMFK_E_NO_X, "nmfk_set_X has not been called");
+    CU(c, cudaSetDevice(c->device));
+    const size_t es = esize(c->dtype);
+    const size_t wb = (size_t)c->n * k * es, hb = (size_t)k * c->m * es;
+    void *dW = nullptr, *dH = nullptr;
+    CU(c, cudaMalloc(&dW, wb));
+    cudaError_t e = cudaMalloc(&dH, hb);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dW, W, wb, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dH, H, hb, cudaMemcpyHostToDevice, c->stream);
+    double o[2] = {0, 0};
+    int32_t rc = NMFK_OK;
+    if (e == cudaSuccess) rc = residual(c, k, dW, dH, 1, 1.0, o);
+    cudaFree(dW);
+    if (dH) cudaFree(dH);
+    CU(c, e);
+    if (rc) return rc;
+    *phi = std::sqrt(o[1]);
+    if (c->dtype == NMFK_F32) *phi = (double)(float)*phi;
     return NMFK_OK;
 }
 

@@ -58,6 +58,27 @@ __device__ __forceinline__ void load_row(const TC* __restrict__ p, TC (&v)[KP]) 
     }
 }
 
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem));
+}
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T* smem, const T* gmem) {
+    if constexpr (sizeof(T) == 8)
+        cp_async_8(smem, gmem);
+    else
+        cp_async_4(smem, gmem);
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
 // IEEE division kept out of line where it is not on the hot loop (the inlined sequence is ~25
 // instructions plus a slow path; the factor-update epilogues would otherwise unroll K copies of it)
 template <typename TC>
@@ -180,39 +201,54 @@ __device__ __forceinline__ void kl_group(const TC (&x)[UNR], const TC* const (&v
 // 4 warps per scheduler.  X values of the next group are prefetched while the current one
 // computes.  V rows are re-read from shared memory for the accumulation phase instead of being
 // kept live (registers are the scarce resource: u and acc already hold 2K values).
+constexpr int kRingGroups = 8;  // cp.async groups in flight per thread (each group = UNR steps)
+
 template <typename TX, typename TC, int K, int KP, bool TRANSPOSED, bool HASNAN, int UNR>
 __device__ __forceinline__ void sweep(const TX* __restrict__ dcol, int nown, int o, int t0, int t1, const TC (&u)[KP],
                                       TC (&acc)[KP], const TC* __restrict__ V, bool first_iter, TC lambda,
-                                      const TC* __restrict__ ximp, int ldimp) {
-    TX xn[UNR];
+                                      const TC* __restrict__ ximp, int ldimp, TX* __restrict__ ring, int NT) {
+    // ring[(slot*UNR + q)*NT] is private to this thread (the pointer already includes threadIdx.x):
+    // X is L2-resident but ~600 cycles away, so every thread keeps (G-1)*UNR of its own X values in
+    // flight with cp.async instead of holding them in registers.
+    constexpr int G = kRingGroups;
+    const int ngroups = (t1 - t0 + UNR - 1) / UNR;
+    auto issue = [&](int g) {
 #pragma unroll
-    for (int q = 0; q < UNR; ++q) xn[q] = (t0 + q < t1) ? __ldg(dcol + (size_t)(t0 + q) * nown) : (TX)1;
-    for (int t = t0; t < t1; t += UNR) {
+        for (int q = 0; q < UNR; ++q) {
+            const int t = t0 + g * UNR + q;
+            if (t < t1) cp_async_elem<TX>(ring + ((g & (G - 1)) * UNR + q) * NT, dcol + (size_t)t * nown);
+        }
+    };
+#pragma unroll
+    for (int g = 0; g < G - 1; ++g) {
+        if (g < ngroups) issue(g);
+        cp_async_commit();
+    }
+    for (int g = 0; g < ngroups; ++g) {
+        cp_async_wait<G - 2>();  // group g has landed
+        const int t = t0 + g * UNR;
         TC x[UNR];
-#pragma unroll
-        for (int q = 0; q < UNR; ++q) {
-            x[q] = (TC)xn[q];
-            if (HASNAN) {
-                if (xn[q] != xn[q])
-                    x[q] = first_iter ? lambda
-                                      : ximp[TRANSPOSED ? ((size_t)(t + q) + (size_t)o * ldimp)
-                                                        : ((size_t)o + (size_t)(t + q) * ldimp)];
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < UNR; ++q) {
-            const int tn = t + UNR + q;
-            xn[q] = (tn < t1) ? __ldg(dcol + (size_t)tn * nown) : (TX)1;
-        }
         const TC* vrow[UNR];
         bool live[UNR];
 #pragma unroll
         for (int q = 0; q < UNR; ++q) {
             live[q] = (t + q < t1);
+            const TX xr = live[q] ? ring[((g & (G - 1)) * UNR + q) * NT] : (TX)1;
+            x[q] = (TC)xr;
+            if (HASNAN) {
+                if (xr != xr)
+                    x[q] = first_iter ? lambda
+                                      : ximp[TRANSPOSED ? ((size_t)(t + q) + (size_t)o * ldimp)
+                                                        : ((size_t)o + (size_t)(t + q) * ldimp)];
+            }
             vrow[q] = V + (size_t)(live[q] ? (t + q) : t) * KP;  // tail: a valid row, contribution zeroed
         }
+        // refill the slot consumed in the PREVIOUS iteration (its values are already in registers)
+        if (g + G - 1 < ngroups) issue(g + G - 1);
+        cp_async_commit();
         kl_group<TC, K, KP, UNR>(x, vrow, live, u, acc);
     }
+    cp_async_wait<0>();
 }
 
 // One half-update.  D is column-major with leading dimension = nown (own index contiguous).
@@ -221,12 +257,12 @@ template <typename TX, typename TC, int K, int KP, bool TRANSPOSED, bool HASNAN>
 __device__ __forceinline__ void half_update(const TX* __restrict__ D, int nown, int nred, int kact,
                                             TC* __restrict__ U, const TC* __restrict__ V, const TC* __restrict__ den,
                                             TC* __restrict__ scr, bool first_iter, TC lambda,
-                                            const TC* __restrict__ ximp, int ldimp) {
+                                            const TC* __restrict__ ximp, int ldimp, TX* __restrict__ ring) {
     const int tid = threadIdx.x, NT = blockDim.x;
     int S = NT / nown;
     if (S > nred) S = nred;
     if (S < 1) S = 1;
-    constexpr int UNR = (K <= 12 ? 2 : 2);
+    constexpr int UNR = 2;
     if (S == 1) {
         // every thread sweeps the whole reduction range for own rows tid, tid+NT, ...
         for (int o = tid; o < nown; o += NT) {
@@ -235,7 +271,7 @@ __device__ __forceinline__ void half_update(const TX* __restrict__ D, int nown, 
 #pragma unroll
             for (int a = 0; a < KP; ++a) acc[a] = (TC)0;
             sweep<TX, TC, K, KP, TRANSPOSED, HASNAN, UNR>(D + o, nown, o, 0, nred, u, acc, V, first_iter, lambda, ximp,
-                                                          ldimp);
+                                                          ldimp, ring + tid, NT);
             // (U .* acc) ./ den : Julia's left-to-right broadcast of `H .* (...) ./ sum`
             TC* urow = U + (size_t)o * KP;
 #pragma unroll
@@ -255,7 +291,7 @@ __device__ __forceinline__ void half_update(const TX* __restrict__ D, int nown, 
         load_row<TC, KP>(U + (size_t)o * KP, u);
         const int t0 = (int)(((long long)nred * s) / S), t1 = (int)(((long long)nred * (s + 1)) / S);
         sweep<TX, TC, K, KP, TRANSPOSED, HASNAN, UNR>(D + o, nown, o, t0, t1, u, acc, V, first_iter, lambda, ximp,
-                                                      ldimp);
+                                                      ldimp, ring + tid, NT);
         if (s > 0) {
             TC* dst = scr + ((size_t)(s - 1) * nown + o) * KP;
 #pragma unroll
@@ -332,8 +368,8 @@ __device__ __forceinline__ void impute_pass(const TX* __restrict__ X, int n, int
 
 struct ResidentSmem {
     // byte offsets of the carve-up; computed identically on host (resident_smem_bytes) and device
-    size_t off_W, off_H, off_den, off_scr, off_red, off_idx, off_first, total;
-    __host__ __device__ static ResidentSmem make(int n, int m, int KP, size_t szTC, int nthreads) {
+    size_t off_W, off_H, off_den, off_scr, off_red, off_idx, off_first, off_ring, total;
+    __host__ __device__ static ResidentSmem make(int n, int m, int KP, size_t szTC, size_t szTX, int nthreads) {
         ResidentSmem r;
         auto al = [](size_t x) { return (x + 15) & ~size_t(15); };
         size_t o = 0;
@@ -361,13 +397,15 @@ struct ResidentSmem {
         o = al(o + (size_t)m * sizeof(int));
         r.off_first = o;
         o = al(o + (size_t)(KP + 4) * sizeof(int));
+        r.off_ring = o;
+        o = al(o + (size_t)kRingGroups * 2 * nthreads * szTX);  // UNR = 2 steps per group
         r.total = o;
         return r;
     }
 };
 
 template <typename TX, typename TC, int K, bool HASNAN>
-__global__ void __launch_bounds__(kResidentThreads, (K <= 12 ? 2 : 1)) kl_resident_kernel(const SolveArgs a) {
+__global__ void __launch_bounds__(resident_threads(K), 1) kl_resident_kernel(const SolveArgs a) {
     constexpr int VEC = VecOf<TC>::N;
     constexpr int KP = (K + VEC - 1) / VEC * VEC;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -377,7 +415,7 @@ __global__ void __launch_bounds__(kResidentThreads, (K <= 12 ? 2 : 1)) kl_reside
     UnitState* stg = a.st + r;
     if (stg->done) return;  // finished in an earlier (resumed) solve
 
-    const ResidentSmem L = ResidentSmem::make(n, m, KP, sizeof(TC), NT);
+    const ResidentSmem L = ResidentSmem::make(n, m, KP, sizeof(TC), sizeof(TX), NT);
     TC* Ws = reinterpret_cast<TC*>(smem + L.off_W);
     TC* Hs = reinterpret_cast<TC*>(smem + L.off_H);
     TC* den = reinterpret_cast<TC*>(smem + L.off_den);
@@ -385,6 +423,7 @@ __global__ void __launch_bounds__(kResidentThreads, (K <= 12 ? 2 : 1)) kl_reside
     double* red = reinterpret_cast<double*>(smem + L.off_red);
     int* idx = reinterpret_cast<int*>(smem + L.off_idx);
     int* first = reinterpret_cast<int*>(smem + L.off_first);
+    TX* ring = reinterpret_cast<TX*>(smem + L.off_ring);
 
     const TX* X = static_cast<const TX*>(a.X);
     const TX* Xt = static_cast<const TX*>(a.Xt);
@@ -437,12 +476,12 @@ __global__ void __launch_bounds__(kResidentThreads, (K <= 12 ? 2 : 1)) kl_reside
         if (!a.Hfixed) {  // :66-68
             factor_sums<TC, K, KP>(Ws, n, den);
             __syncthreads();
-            half_update<TX, TC, K, KP, true, HASNAN>(Xt, m, n, k, Hs, Ws, den, scr, first_iter, lambda, ximp, n);
+            half_update<TX, TC, K, KP, true, HASNAN>(Xt, m, n, k, Hs, Ws, den, scr, first_iter, lambda, ximp, n, ring);
         }
         if (!a.Wfixed) {  // :69-71
             factor_sums<TC, K, KP>(Hs, m, den);
             __syncthreads();
-            half_update<TX, TC, K, KP, false, HASNAN>(X, n, m, k, Ws, Hs, den, scr, first_iter, lambda, ximp, n);
+            half_update<TX, TC, K, KP, false, HASNAN>(X, n, m, k, Ws, Hs, den, scr, first_iter, lambda, ximp, n, ring);
         }
         if (has_nan) impute_pass<TX, TC, K, KP>(X, n, m, Ws, Hs, ximp);  // :72
         if (it % a.check_every == 0) {                                    // :73
@@ -585,18 +624,19 @@ template <typename TX, typename TC, int K>
 cudaError_t launch_resident_k(const SolveArgs& a, cudaStream_t s) {
     constexpr int VEC = VecOf<TC>::N;
     constexpr int KP = (K + VEC - 1) / VEC * VEC;
-    const size_t smem = ResidentSmem::make(a.n, a.m, KP, sizeof(TC), kResidentThreads).total;
+    constexpr int NT = resident_threads(K);
+    const size_t smem = ResidentSmem::make(a.n, a.m, KP, sizeof(TC), sizeof(TX), NT).total;
     cudaError_t e;
     if (a.has_nan) {
         e = cudaFuncSetAttribute(kl_resident_kernel<TX, TC, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem);
         if (e != cudaSuccess) return e;
-        kl_resident_kernel<TX, TC, K, true><<<a.R, kResidentThreads, smem, s>>>(a);
+        kl_resident_kernel<TX, TC, K, true><<<a.R, NT, smem, s>>>(a);
     } else {
         e = cudaFuncSetAttribute(kl_resident_kernel<TX, TC, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem);
         if (e != cudaSuccess) return e;
-        kl_resident_kernel<TX, TC, K, false><<<a.R, kResidentThreads, smem, s>>>(a);
+        kl_resident_kernel<TX, TC, K, false><<<a.R, NT, smem, s>>>(a);
     }
     return cudaGetLastError();
 }

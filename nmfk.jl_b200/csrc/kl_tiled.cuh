@@ -52,27 +52,6 @@ struct TiledPassArgs {
     double lambda;
 };
 
-__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem));
-}
-template <typename T>
-__device__ __forceinline__ void cp_async_elem(T* smem, const T* gmem) {
-    if constexpr (sizeof(T) == 8)
-        cp_async_8(smem, gmem);
-    else
-        cp_async_4(smem, gmem);
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N));
-}
-
 template <typename TX, typename TC, int K, bool HASNAN>
 __global__ void __launch_bounds__(kTiledThreads, (K <= 12 ? 2 : 1)) tiled_pass_kernel(const TiledPassArgs a) {
     constexpr int VEC = VecOf<TC>::N;

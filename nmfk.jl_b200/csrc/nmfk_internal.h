@@ -39,7 +39,8 @@ struct SolveArgs {
     double lambda, tol, tolOF, eps_clamp, weight;
 };
 
-constexpr int kResidentThreads = 256;
+// threads per restart-CTA of the resident engine: 512 (<=128 registers) while u/acc fit, 256 beyond
+__host__ __device__ constexpr int resident_threads(int Ktemplate) { return Ktemplate <= 12 ? 512 : 256; }
 constexpr int kMaxK = 32;
 
 // template K actually instantiated for a requested k (exact up to 12, then padded)
@@ -53,7 +54,7 @@ inline int resident_template_k(int k) {
 }
 
 // dynamic shared memory the resident kernel needs (bytes); mirrors the carve-up in kl_resident.cuh
-size_t resident_smem_bytes(int n, int m, int Ktemplate, size_t sizeofTC, int nthreads);
+size_t resident_smem_bytes(int n, int m, int Ktemplate, size_t sizeofTC);
 
 // launchers (one translation unit per dtype), return cudaError_t
 cudaError_t launch_kl_resident_f64(const SolveArgs& a, cudaStream_t s);

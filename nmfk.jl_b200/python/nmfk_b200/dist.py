@@ -1,0 +1,220 @@
+"""Restart-sharded execute across the GPUs of one box: one process per GPU, torch.distributed
+(NCCL) for the plumbing.
+
+The reference farms restarts out with `Distributed.pmap` (NMFkExecute.jl:511-526) and gathers the
+(W, H, objvalue) tuples by value.  Here every rank solves its own restarts for every k (X is
+replicated: it is small next to the factor stacks), then only what the robustness analysis needs
+crosses NVLink: the H stacks (k x m per restart), objectives and iteration counts are
+all-gathered, the clustering + silhouettes of the R_total = world * R_local solutions of a given k
+run on the rank that owns that k (k index mod world), and the best restart's W (n x k) is
+broadcast from the rank that solved it.  There is no collective inside the iteration loop.
+
+The helpers that do not touch the device (`owner_of`, `global_index`, `gather_solutions`,
+`merge_sweep`) are covered by world_size-2 gloo tests on CPU (tests/test_dist_cpu.py)."""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import api
+from ._lib import check
+
+
+def owner_of(k_index: int, world: int) -> int:
+    """Rank that clusters the solutions of the k_index-th entry of the sweep."""
+    return k_index % world
+
+
+def global_index(rank: int, r_local: int, R_local: int) -> int:
+    """Position of restart r_local of `rank` in the gathered (rank-major) stack."""
+    return rank * R_local + r_local
+
+
+def split_global(g: int, R_local: int):
+    return divmod(g, R_local)  # (rank, r_local)
+
+
+def gather_solutions(H_local, obj_local, iters_local, group=None):
+    """all_gather of one k's solutions.  H_local: tensor (R_local, m, k) (stack layout, any device),
+    obj_local: (R_local,) float64, iters_local: (R_local,) int32.  Returns rank-major concatenations."""
+    import torch
+    import torch.distributed as td
+
+    world = td.get_world_size(group)
+    Hs = [torch.empty_like(H_local) for _ in range(world)]
+    td.all_gather(Hs, H_local.contiguous(), group=group)
+    meta_local = torch.stack([obj_local.to(torch.float64), iters_local.to(torch.float64)], dim=0).contiguous()
+    metas = [torch.empty_like(meta_local) for _ in range(world)]
+    td.all_gather(metas, meta_local, group=group)
+    H = torch.cat(Hs, dim=0)
+    obj = torch.cat([mt[0] for mt in metas])
+    iters = torch.cat([mt[1] for mt in metas]).to(torch.int32)
+    return H, obj, iters
+
+
+def aic(n: int, m: int, k: int, nnan: int, phi: float) -> float:
+    """aic = 2*numparameters + numobservations*log(phi/numobservations) (NMFkExecute.jl:697-708)."""
+    nobs = n * m - nnan
+    return 2.0 * (n * k + k * m) + nobs * math.log(phi / nobs) if phi > 0 else -math.inf
+
+
+def merge_sweep(ks: Sequence[int], per_k: Dict[int, dict], cutoff: float = 0.5):
+    """Assemble execute's return values (NMFkExecute.jl:196-232) from per-k results."""
+    maxk = max(ks)
+    fit = np.zeros(maxk)
+    rob = np.zeros(maxk)
+    aicv = np.zeros(maxk)
+    fit[0] = np.inf
+    rob[0] = -1
+    for k in ks:
+        fit[k - 1], rob[k - 1], aicv[k - 1] = per_k[k]["fit"], per_k[k]["robustness"], per_k[k]["aic"]
+    idx = np.asarray(list(ks)) - 1
+    kopt = 0 if np.all(np.isinf(fit[idx])) else api.getk(list(ks), rob[idx], cutoff)
+    return fit, rob, aicv, kopt
+
+
+class _DevPtr:
+    """Zero-copy view of library-owned device memory for torch (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def _h_stack_tensor(batch, ctx):
+    import ctypes as C
+    import torch
+
+    W, H = C.c_void_p(), C.c_void_p()
+    check(ctx._lib.nmfk_batch_device_ptrs(batch._h, C.byref(W), C.byref(H)), ctx._h)
+    ts = "<f8" if ctx.np_dtype == np.float64 else "<f4"
+    return torch.as_tensor(_DevPtr(H.value, (batch.R, ctx.m, batch.k), ts), device="cuda"), W.value
+
+
+def execute_sharded(ctx, X, ks: Sequence[int], R_local: int, *, inits=None, seed0: Optional[int] = None,
+                    stack_layout: bool = False, rank: int = 0, world: int = 1, cutoff: float = 0.5, params=None):
+    """execute(X, ks, nNMF = world * R_local) with the restarts sharded over `world` ranks.
+
+    inits[k] = (Winit, Hinit) for THIS rank's restarts ((R,n,k)/(R,k,m), or with stack_layout=True
+    already (R,k,n)/(R,m,k) C-contiguous == column-major stacks); otherwise device Philox streams
+    seeded seed0 + rank*R_local + i.  Returns a dict; on world == 1 this is exactly nmfk_execute."""
+    ks = [int(k) for k in ks]
+    if world == 1:
+        import ctypes as C
+        from . import _lib
+        ctx.set_X(X)
+        p = params or api.default_params()
+        n, m, dt = ctx.n, ctx.m, ctx.np_dtype
+        nks = len(ks)
+        Wo = [np.empty((k, n), dtype=dt) for k in ks]
+        Ho = [np.empty((m, k), dtype=dt) for k in ks]
+        Wop = (C.c_void_p * nks)(*[w.ctypes.data for w in Wo])
+        Hop = (C.c_void_p * nks)(*[h.ctypes.data for h in Ho])
+        Wip = Hip = None
+        keep = []
+        if inits is not None:
+            for k in ks:
+                Wi, Hi = inits[k]
+                if not stack_layout:
+                    Wi = np.ascontiguousarray(np.transpose(np.asarray(Wi, dtype=dt), (0, 2, 1)))
+                    Hi = np.ascontiguousarray(np.transpose(np.asarray(Hi, dtype=dt), (0, 2, 1)))
+                keep.append((Wi, Hi))
+            Wip = (C.c_void_p * nks)(*[w.ctypes.data for w, _ in keep])
+            Hip = (C.c_void_p * nks)(*[h.ctypes.data for _, h in keep])
+        fit, rob, aicv = np.empty(nks), np.empty(nks), np.empty(nks)
+        kopt, tot = C.c_int32(), C.c_int64()
+        karr = np.asarray(ks, dtype=np.int32)
+        check(ctx._lib.nmfk_execute(ctx._h, karr.ctypes.data_as(_lib._pi32), nks, R_local, Wip, Hip,
+                                    int(seed0 or 0), C.byref(p), cutoff, Wop, Hop, fit.ctypes.data_as(_lib._pdbl),
+                                    rob.ctypes.data_as(_lib._pdbl), aicv.ctypes.data_as(_lib._pdbl), C.byref(kopt),
+                                    C.byref(tot)), ctx._h)
+        d2h = sum(w.nbytes + h.nbytes for w, h in zip(Wo, Ho)) + 3 * 8 * nks + 12
+        return dict(W={k: w.T for k, w in zip(ks, Wo)}, H={k: h.T for k, h in zip(ks, Ho)}, fit=fit, robustness=rob,
+                    aic=aicv, kopt=(None if kopt.value < 0 else kopt.value), total_iters_local=int(tot.value),
+                    d2h_bytes=d2h)
+
+    import ctypes as C
+    import torch
+    import torch.distributed as td
+
+    xi = ctx.set_X(X)
+    p = params or api.default_params()
+    n, m, dt = ctx.n, ctx.m, ctx.np_dtype
+    batches = []
+    for k in ks:
+        b = ctx.batch(k, R_local)
+        if inits is not None:
+            Wi, Hi = inits[k]
+            if stack_layout:
+                check(ctx._lib.nmfk_batch_set_init(b._h, Wi.ctypes.data_as(C.c_void_p), Hi.ctypes.data_as(C.c_void_p)),
+                      ctx._h)
+            else:
+                b.set_init(Wi, Hi)
+        else:
+            b.init_random(int(seed0 or 0) + rank * R_local)
+        batches.append(b)
+    ctx.solve(batches, p)
+    per_k, d2h, tot_local = {}, 0, 0
+    R_total = world * R_local
+    for i, (k, b) in enumerate(zip(ks, batches)):
+        st = b.get(factors=False)
+        tot_local += int(st["iters"].sum())
+        Hdev, Wptr = _h_stack_tensor(b, ctx)
+        obj = torch.from_numpy(st["obj_norm"]).cuda()
+        its = torch.from_numpy(st["iters"]).cuda()
+        Hall, oall, iall = gather_solutions(Hdev, obj, its)  # NCCL over NVLink
+        own = owner_of(i, world)
+        best = torch.zeros(2, dtype=torch.int64, device="cuda")
+        res = None
+        if rank == own:
+            hb = C.c_void_p()
+            check(ctx._lib.nmfk_batch_create_hstack(ctx._h, k, R_total, C.byref(hb)), ctx._h)
+            oh = oall.cpu().numpy()
+            ih = iall.cpu().numpy().astype(np.int32)
+            Hc = Hall.contiguous()
+            check(ctx._lib.nmfk_batch_import(hb, None, C.c_void_p(Hc.data_ptr()), oh.ctypes.data_as(C.POINTER(C.c_double)),
+                                             ih.ctypes.data_as(C.POINTER(C.c_int32)), 1), ctx._h)
+            hbatch = api.Batch.__new__(api.Batch)
+            hbatch.ctx, hbatch.k, hbatch.R, hbatch._h = ctx, k, R_total, hb
+            cl = hbatch.cluster()
+            g = int(cl["order"][0])
+            br, bl = split_global(g, R_local)
+            best[0], best[1] = br, bl
+            Hbest = Hall[g].cpu().numpy()  # (m, k)
+            res = dict(robustness=(1.0 if k == 1 else cl["robustness"]), labels1=cl["labels"][:, 0].copy(), Hbest=Hbest)
+            hbatch.close()
+        td.broadcast(best, src=own)
+        br, bl = int(best[0]), int(best[1])
+        # the best restart's W travels from the rank that solved it to the owner of k
+        Wbest = torch.empty((k, n), dtype=torch.float64 if dt == np.float64 else torch.float32, device="cuda")
+        if rank == br:
+            ts = "<f8" if dt == np.float64 else "<f4"
+            Wstack = torch.as_tensor(_DevPtr(Wptr, (R_local, k, n), ts), device="cuda")
+            Wbest.copy_(Wstack[bl])
+        td.broadcast(Wbest, src=br)
+        if rank == own:
+            Wb = Wbest.cpu().numpy()  # (k, n) == n x k column-major
+            Hb = res["Hbest"]
+            if k > 1:  # Wbest[:, i] = W[:, labels[i,1]]  (NMFkExecute.jl:631-635)
+                ci = res["labels1"] - 1
+                Wb = np.ascontiguousarray(Wb[ci, :])
+                Hb = np.ascontiguousarray(Hb[:, ci])
+            phi = C.c_double()
+            check(ctx._lib.nmfk_fit(ctx._h, k, Wb.ctypes.data_as(C.c_void_p), Hb.ctypes.data_as(C.c_void_p),
+                                    C.byref(phi)), ctx._h)
+            so = api.signalorder(Wb.T, Hb.T)
+            per_k[k] = dict(fit=phi.value, robustness=res["robustness"], aic=aic(n, m, k, xi.nnan, phi.value),
+                            W=Wb.T[:, so], H=Hb.T[so, :])
+            d2h += Wb.nbytes + Hb.nbytes + 24
+        b.close()
+    # small per-k scalars to every rank for the selection of kopt
+    gathered = [None] * world
+    td.all_gather_object(gathered, {k: {q: v[q] for q in ("fit", "robustness", "aic")} for k, v in per_k.items()})
+    allk = {}
+    for g in gathered:
+        allk.update(g)
+    fit, rob, aicv, kopt = merge_sweep(ks, allk, cutoff)
+    return dict(W={k: v["W"] for k, v in per_k.items()}, H={k: v["H"] for k, v in per_k.items()}, fit=fit,
+                robustness=rob, aic=aicv, kopt=kopt, total_iters_local=tot_local, d2h_bytes=d2h)
