@@ -54,7 +54,10 @@ enum nmfk_stop_reason {
     NMFK_STOP_BADITERS = 5      /* baditers >= maxbaditers (unreachable with the reference's reset, kept for the guard) */
 };
 
-enum nmfk_engine { NMFK_ENGINE_AUTO = 0, NMFK_ENGINE_RESIDENT = 1, NMFK_ENGINE_TILED = 2 };
+/* AUTO: resident when the factors fit in one SM's shared memory, else tiled.  RESIDENT uses the
+ * tensor-pipe (DMMA m8n8k4) formulation for Float64 and the scalar-FMA one for Float32;
+ * RESIDENT_SCALAR forces the scalar-FMA formulation (kept for A/B measurements and parity). */
+enum nmfk_engine { NMFK_ENGINE_AUTO = 0, NMFK_ENGINE_RESIDENT = 1, NMFK_ENGINE_TILED = 2, NMFK_ENGINE_RESIDENT_SCALAR = 3 };
 
 /* Keyword arguments of NMFmultiplicative (NMFkMultiplicative.jl:24) and of
  * execute_singlerun_compute (NMFkExecute.jl:729), one field per keyword. */

@@ -378,6 +378,7 @@ static void fill_args(const nmfk_batch* b, const nmfk_params* p, SolveArgs& a) {
     a.k = b->k;
     a.R = b->R;
     a.has_nan = c->info.nnan > 0;
+    a.SH = a.SW = 1;
     a.maxiter = p->maxiter;
     a.maxbad = p->maxbaditers;
     a.maxre = p->maxreattempts;
@@ -430,12 +431,18 @@ int32_t nmfk_solve(nmfk_ctx* c, nmfk_batch* const* batches, int32_t nb, const nm
         fill_args(b, p, a);
         cudaStream_t s = c->pool[q];
         CU(c, cudaStreamWaitEvent(s, c->ev0, 0));
-        bool resident = resident_fits(a.n, a.m, a.k, es);
+        const bool want_scalar = (p->engine == NMFK_ENGINE_RESIDENT_SCALAR) || c->dtype != NMFK_F64;
+        const bool fits_dmma = !want_scalar && resident_dmma_fits(a.n, a.m, a.k);
+        const bool fits_scalar = resident_fits(a.n, a.m, a.k, es);
+        bool resident = fits_dmma || fits_scalar;
         if (p->engine == NMFK_ENGINE_TILED) resident = false;
-        if (p->engine == NMFK_ENGINE_RESIDENT && !resident)
+        if ((p->engine == NMFK_ENGINE_RESIDENT || p->engine == NMFK_ENGINE_RESIDENT_SCALAR) && !resident)
             return fail(c, NMFK_E_UNSUPPORTED, "resident engine: factors do not fit in shared memory (or k > 32)");
         if (resident) {
-            CU(c, c->dtype == NMFK_F64 ? launch_kl_resident_f64(a, s) : launch_kl_resident_f32(a, s));
+            if (fits_dmma)
+                CU(c, launch_kl_resident_dmma(a, s));
+            else
+                CU(c, c->dtype == NMFK_F64 ? launch_kl_resident_f64(a, s) : launch_kl_resident_f32(a, s));
             c->launches += 1;
         } else {
             if (!tiled_supported(a.k)) return fail(c, NMFK_E_UNSUPPORTED, "tiled engine: k > 32 is not supported");

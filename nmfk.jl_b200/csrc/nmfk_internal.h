@@ -35,6 +35,7 @@ struct SolveArgs {
     void* ximp;       // R x n x m imputed values (only when has_nan), X layout
     int32_t n, m, k, R;
     int32_t has_nan;
+    int32_t SH, SW;   // DMMA resident engine: slices of the reduction range per half-update (host heuristic)
     int32_t maxiter, maxbad, maxre, stopconv, check_every, Wfixed, Hfixed, normalize, iter_limit;
     double lambda, tol, tolOF, eps_clamp, weight;
 };
@@ -59,6 +60,9 @@ size_t resident_smem_bytes(int n, int m, int Ktemplate, size_t sizeofTC);
 // launchers (one translation unit per dtype), return cudaError_t
 cudaError_t launch_kl_resident_f64(const SolveArgs& a, cudaStream_t s);
 cudaError_t launch_kl_resident_f32(const SolveArgs& a, cudaStream_t s);
+// Float64 tensor-pipe (DMMA) formulation of the resident engine (kl_dmma.cuh)
+cudaError_t launch_kl_resident_dmma(const SolveArgs& a, cudaStream_t s);
+bool resident_dmma_fits(int n, int m, int k);
 // can the resident engine take this shape?  (smem budget of one CTA)
 bool resident_fits(int n, int m, int k, size_t sizeofTC);
 

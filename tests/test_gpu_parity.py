@@ -72,6 +72,18 @@ def test_trace_parity_f32(ctx, n, m, k, niter):
         assert relerr(Ht[t], Hr[t]) < RTOL32, ("H", t)
 
 
+@pytest.mark.parametrize("n,m,k,niter", [(15, 5, 3, 40), (1000, 200, 10, 22), (203, 77, 6, 22), (300, 64, 13, 22),
+                                         (90, 40, 32, 15), (64, 9, 1, 20)])
+def test_trace_parity_f64_scalar_formulation(ctx, n, m, k, niter):
+    """engine=3: the scalar-FMA formulation of the resident engine (the default for Float64 is DMMA)."""
+    X = synth.mixture(n, m, 3, seed=7)
+    W0, H0 = synth.philox_inits(11, 1, n, k, m)
+    Wt, Ht, ob = nb.trace(X, k, W0[0], H0[0], niter, ctx=ctx, engine=3)
+    Wr, Hr, obr = oracle_trace(X, k, W0[0], H0[0], niter)
+    for t in range(niter):
+        assert relerr(Wt[t], Wr[t]) < RTOL64 and relerr(Ht[t], Hr[t]) < RTOL64, t
+
+
 def test_full_stop_rule_matches_oracle(ctx):
     """Reference stop rule (tolOF/baditers/reattempts state machine): same iteration counts,
     stop reasons, objective and normalised factors for every restart."""
@@ -287,14 +299,15 @@ def test_tiled_full_stop_rule_matches_resident_and_oracle(ctx):
     W0, H0 = synth.philox_inits(100, R, 15, k, 5)
     ctx.set_X(X)
     res = {}
-    for eng in (1, 2):
+    for eng in (1, 2, 3):
         b = ctx.batch(k, R)
         b.set_init(W0, H0)
         ctx.solve([b], nb.default_params(engine=eng))
         res[eng] = b.get()
         b.close()
-    assert np.array_equal(res[1]["iters"], res[2]["iters"])
+    assert np.array_equal(res[1]["iters"], res[2]["iters"]) and np.array_equal(res[1]["iters"], res[3]["iters"])
     assert np.array_equal(res[1]["stop_reason"], res[2]["stop_reason"])
+    assert relerr(res[3]["W"], res[1]["W"]) < 1e-8 and relerr(res[3]["H"], res[1]["H"]) < 1e-8
     assert relerr(res[2]["W"], res[1]["W"]) < 1e-8 and relerr(res[2]["H"], res[1]["H"]) < 1e-8
     assert np.allclose(res[2]["obj_norm"], res[1]["obj_norm"], rtol=1e-6, atol=1e-12)
     for r in range(R):

@@ -55,6 +55,9 @@ res.append(dict(tag="warmup k=2 R=8 100it", **run([2], 8, maxiter=100)))
 for k in (2, 4, 6, 8, 10):
     res.append(dict(tag="fixed100 k=%d R=296" % k, **run([k], 296, maxiter=100)))
 res.append(dict(tag="fixed100 k=10 R=100", **run([10], 100, maxiter=100)))
+for k in (2, 6, 10):
+    res.append(dict(tag="SCALAR fixed100 k=%d R=148" % k, **run([k], 148, maxiter=100, engine=3)))
+    res.append(dict(tag="DMMA   fixed100 k=%d R=148" % k, **run([k], 148, maxiter=100, engine=1)))
 res.append(dict(tag="fixed100 k=10 R=148", **run([10], 148, maxiter=100)))
 res.append(dict(tag="fixed100 k=2:10 R=100", **run(range(2, 11), 100, maxiter=100)))
 res.append(dict(tag="C2 full stop rule k=2:10 R=100", **run(range(2, 11), 100)))
