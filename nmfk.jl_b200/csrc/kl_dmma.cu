@@ -17,12 +17,12 @@ struct DmmaPlan {
 // Minimise the per-iteration critical path (in 8-step tiles) of one warp: a half-update has
 // G = ceil(own/8) row groups x S slices work items dealt round-robin to NW warps.
 DmmaPlan plan_dmma(int n, int m, int KC) {
-    const int maxthreads = KC <= 3 ? 1024 : 512;
+    const int maxthreads = dmma_max_threads(KC);
     const int GH = (m + 7) / 8, TH = (n + 7) / 8;  // H-update: own = columns, reduction = rows
     const int GW = (n + 7) / 8, TW = (m + 7) / 8;
     DmmaPlan best{0, 1, 1, 0, false};
     long long bestcost = -1;
-    for (int NW = 8; NW * 32 <= maxthreads; NW += 4) {
+    for (int NW = 8; NW * 32 <= maxthreads; ++NW) {
         for (int SH = 1; SH <= 4 && SH <= TH; ++SH)
             for (int SW = 1; SW <= 4 && SW <= TW; ++SW) {
                 const size_t smem = DmmaSmem::make(n, m, KC, SH, SW).total;

@@ -29,6 +29,7 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
         : "d"(a), "d"(b));
 }
 
+__host__ __device__ constexpr int dmma_max_threads(int KC) { return KC <= 3 ? 800 : 512; }
 __host__ __device__ constexpr int dmma_pitch(int KC) { return (KC & 1) ? KC * 4 : KC * 4 + 4; }
 
 struct DmmaSmem {
@@ -71,7 +72,46 @@ __device__ __forceinline__ void factor_sums_p(const double* __restrict__ V, int 
     }
 }
 
-// One half-update with DMMA tiles.  D: own-contiguous data (element (o,t) at D[o + t*nown]).
+// 1/p by MUFU.RCP64H + two Newton steps (relative error ~2^-52), no range check: operands outside
+// the valid range (0, subnormal, Inf, NaN) turn the quotient into NaN, which the caller detects.
+__device__ __forceinline__ double rcp_nr(double p) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
+    double e = fma(-p, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-p, r, 1.0);
+    return fma(r, e, r);
+}
+
+// One 8-own x 8-step tile: P = U V^T (KC DMMAs), Q = X ./ P, ACC += Q V (2*NA DMMAs).
+// vp1 -> V[t0+g][q], vp2 -> V[t0+2q][g]; x = this lane's X values at steps t0+2q, t0+2q+1.
+template <int KC>
+__device__ __forceinline__ void dmma_tile(const double (&ua)[KC], double x0, double x1, const double* __restrict__ vp1,
+                                          const double* __restrict__ vp2a, const double* __restrict__ vp2b,
+                                          bool last_ok, double (&acc)[(KC + 1) / 2][2]) {
+    constexpr int NA = (KC + 1) / 2;
+    constexpr int pitch = dmma_pitch(KC);
+    double p[2] = {0.0, 0.0};
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) dmma884(p, ua[kc], vp1[kc * 4]);
+    double q0 = x0 * rcp_nr(p[0]);
+    double q1 = x1 * rcp_nr(p[1]);
+    const double chk = q0 + q1;
+    if (__any_sync(0xffffffffu, chk != chk)) {  // rare: redo with IEEE semantics (x/0 = Inf, 0/0 = NaN, ...)
+        q0 = div_cold<double>(x0, p[0]);
+        q1 = div_cold<double>(x1, p[1]);
+    }
+#pragma unroll
+    for (int na = 0; na < NA; ++na) {
+        const bool ok = (na * 8 + 8 <= pitch) || last_ok;
+        const double b0 = ok ? vp2a[na * 8] : 0.0;
+        const double b1 = ok ? vp2b[na * 8] : 0.0;
+        dmma884(acc[na], q0, b0);
+        dmma884(acc[na], q1, b1);
+    }
+}
+
+// One half-update with DMMA tiles.  D: STEP-contiguous data (element (o,t) at D[t + o*nred]).
 template <int KC, bool TRANSPOSED, bool HASNAN>
 __device__ __forceinline__ void dmma_half_update(const double* __restrict__ D, int nown, int nred, int k, int S,
                                                  double* __restrict__ U, const double* __restrict__ V,
@@ -80,82 +120,74 @@ __device__ __forceinline__ void dmma_half_update(const double* __restrict__ D, i
                                                  int ldimp) {
     constexpr int NA = (KC + 1) / 2;
     constexpr int pitch = dmma_pitch(KC);
+    constexpr int PF = 4;  // tiles of X kept in flight per lane (X is L2-resident but far away)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int G = (nown + 7) >> 3;
     const int tiles_total = (nred + 7) >> 3;
+    const int tiles_full = nred >> 3;
     const int items = G * S;
+    const bool vec_ok = ((nred & 1) == 0);
+    const bool last_ok = (NA * 8 - 8 + g) < pitch;
     for (int item = warp; item < items; item += NW) {
         const int grp = item % G, slice = item / G;
         const int row = grp * 8 + g;
         const bool rvalid = row < nown;
+        const int rowc = rvalid ? row : nown - 1;  // invalid rows shadow the last valid one; never stored
         const int tb = (int)(((long long)tiles_total * slice) / S), te = (int)(((long long)tiles_total * (slice + 1)) / S);
+        const int tef = min(te, tiles_full);  // tiles [tb, tef) are complete
         double ua[KC];
 #pragma unroll
-        for (int kc = 0; kc < KC; ++kc) ua[kc] = rvalid ? U[(size_t)row * pitch + kc * 4 + q] : 0.0;
+        for (int kc = 0; kc < KC; ++kc) ua[kc] = U[(size_t)rowc * pitch + kc * 4 + q];
         double acc[NA][2];
 #pragma unroll
         for (int na = 0; na < NA; ++na) acc[na][0] = acc[na][1] = 0.0;
-        const double* dcol = D + (rvalid ? row : 0);
-        // register prefetch of this lane's two X values of the next tile
-        double xn[2];
-        {
-            const int t = tb * 8 + 2 * q;
+        const double* xp = D + (size_t)rowc * nred + (size_t)tb * 8 + 2 * q;
+        const double* vp1 = V + (size_t)(tb * 8 + g) * pitch + q;
+        const double* vp2 = V + (size_t)(tb * 8 + 2 * q) * pitch + g;
+        auto load_x = [&](const double* ptr) -> double2 {
+            if (vec_ok) return __ldg(reinterpret_cast<const double2*>(ptr));
+            return make_double2(__ldg(ptr), __ldg(ptr + 1));
+        };
+        auto fix_nan = [&](double& x, int t) {
+            if (HASNAN) {
+                if (x != x)
+                    x = first_iter ? lambda
+                                   : ximp[TRANSPOSED ? ((size_t)t + (size_t)rowc * ldimp) : ((size_t)rowc + (size_t)t * ldimp)];
+            }
+        };
+        double2 xq[PF];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) xn[e] = (rvalid && tb < te && t + e < nred) ? __ldg(dcol + (size_t)(t + e) * nown) : 0.0;
+        for (int u = 0; u < PF; ++u) xq[u] = (tb + u < tef) ? load_x(xp + u * 8) : make_double2(0.0, 0.0);
+        for (int tile0 = tb; tile0 < tef; tile0 += PF) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int tile = tile0 + u;
+                if (tile < tef) {  // warp-uniform
+                    double x0 = xq[u].x, x1 = xq[u].y;
+                    xq[u] = (tile + PF < tef) ? load_x(xp + PF * 8) : make_double2(0.0, 0.0);
+                    fix_nan(x0, tile * 8 + 2 * q);
+                    fix_nan(x1, tile * 8 + 2 * q + 1);
+                    dmma_tile<KC>(ua, x0, x1, vp1, vp2, vp2 + pitch, last_ok, acc);
+                    xp += 8;
+                    vp1 += 8 * pitch;
+                    vp2 += 8 * pitch;
+                }
+            }
         }
-        for (int tile = tb; tile < te; ++tile) {
-            const int t0 = tile * 8;
-            double x[2] = {xn[0], xn[1]};
-            {
-                const int t = t0 + 8 + 2 * q;
-#pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    xn[e] = (rvalid && tile + 1 < te && t + e < nred) ? __ldg(dcol + (size_t)(t + e) * nown) : 0.0;
-            }
-            // P = U_group * V[t0..t0+8, :]^T
-            double p[2] = {0.0, 0.0};
-            {
-                const int tg = min(t0 + g, nred - 1);
-                const double* vrow = V + (size_t)tg * pitch + q;
-#pragma unroll
-                for (int kc = 0; kc < KC; ++kc) dmma884(p, ua[kc], vrow[kc * 4]);
-            }
-            // Q = X ./ P on this lane's (row g, steps t0+2q, t0+2q+1)
-            double qv[2];
-            bool bad = false;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int t = t0 + 2 * q + e;
-                const bool live = rvalid && (t < nred);
-                if (HASNAN) {
-                    if (x[e] != x[e])
-                        x[e] = first_iter ? lambda
-                                          : ximp[TRANSPOSED ? ((size_t)t + (size_t)row * ldimp)
-                                                            : ((size_t)row + (size_t)t * ldimp)];
-                }
-                const double xs = live ? x[e] : 0.0, ps = live ? p[e] : 1.0;
-                bool uq;
-                qv[e] = fast_div(xs, ps, uq);
-                bad |= uq;
-                x[e] = xs;
-                p[e] = ps;
-            }
-            if (__any_sync(0xffffffffu, bad)) {  // rare: IEEE semantics for operands outside the fast path
-#pragma unroll
-                for (int e = 0; e < 2; ++e) qv[e] = div_cold<double>(x[e], p[e]);
-            }
-            // ACC += Q * V : the second product's k-index q is bound to step 2q+s
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int ts = min(t0 + 2 * q + s, nred - 1);
-                const double* vrow = V + (size_t)ts * pitch + g;
-#pragma unroll
-                for (int na = 0; na < NA; ++na) {
-                    const double b2 = (na * 8 + 8 <= pitch || na * 8 + g < pitch) ? vrow[na * 8] : 0.0;
-                    dmma884(acc[na], qv[s], b2);
-                }
-            }
+        if (te > tef) {
+            // the partial last tile of the reduction range: clamp the rows of V, zero X beyond the end
+            const int t0 = tef * 8;
+            const int ta = t0 + 2 * q;
+            double x0 = (ta < nred) ? __ldg(D + (size_t)rowc * nred + ta) : 0.0;
+            double x1 = (ta + 1 < nred) ? __ldg(D + (size_t)rowc * nred + ta + 1) : 0.0;
+            if (ta < nred) fix_nan(x0, ta);
+            if (ta + 1 < nred) fix_nan(x1, ta + 1);
+            const double* t1p = V + (size_t)min(t0 + g, nred - 1) * pitch + q;
+            const double* t2a = V + (size_t)min(ta, nred - 1) * pitch + g;
+            const double* t2b = V + (size_t)min(ta + 1, nred - 1) * pitch + g;
+            // steps beyond the end see x = 0 and a real (clamped) row of V: q = 0 / p = 0
+            dmma_tile<KC>(ua, x0, x1, t1p, t2a, t2b, last_ok, acc);
         }
         if (S == 1) {
             // (U .* acc) ./ den : the rows of this group are read by this warp only
@@ -254,7 +286,7 @@ __device__ __forceinline__ double2 dmma_residual_pass(const double* __restrict__
 }
 
 template <int KC, bool HASNAN>
-__global__ void __launch_bounds__((KC <= 3 ? 1024 : 512), 1) kl_resident_dmma_kernel(const SolveArgs a) {
+__global__ void __launch_bounds__(dmma_max_threads(KC), 1) kl_resident_dmma_kernel(const SolveArgs a) {
     constexpr int pitch = dmma_pitch(KC);
     extern __shared__ __align__(16) unsigned char smem[];
     const int n = a.n, m = a.m, k = a.k;
@@ -313,12 +345,12 @@ __global__ void __launch_bounds__((KC <= 3 ? 1024 : 512), 1) kl_resident_dmma_ke
         if (!a.Hfixed) {  // :66-68
             factor_sums_p(Ws, n, pitch, k, den);
             __syncthreads();
-            dmma_half_update<KC, true, HASNAN>(Xt, m, n, k, a.SH, Hs, Ws, den, scr, first_iter, lambda, ximp, n);
+            dmma_half_update<KC, true, HASNAN>(X, m, n, k, a.SH, Hs, Ws, den, scr, first_iter, lambda, ximp, n);
         }
         if (!a.Wfixed) {  // :69-71
             factor_sums_p(Hs, m, pitch, k, den);
             __syncthreads();
-            dmma_half_update<KC, false, HASNAN>(X, n, m, k, a.SW, Ws, Hs, den, scr, first_iter, lambda, ximp, n);
+            dmma_half_update<KC, false, HASNAN>(Xt, n, m, k, a.SW, Ws, Hs, den, scr, first_iter, lambda, ximp, n);
         }
         if (HASNAN) dmma_residual_pass<KC, 1, false>(X, n, m, Ws, Hs, lambda, 1.0, ximp, red);  // :72
         if (it % a.check_every == 0) {                                                           // :73
