@@ -289,7 +289,8 @@ def main():
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": None,
-                         "kernel": "kl_resident_kernel<double,double,K> (9 instantiations, one per k, concurrent streams)",
+                         "kernel": "kl_resident_dmma_kernel<K,false> (9 instantiations, one per k, concurrent streams; "
+                                   "DMMA m8n8k4 + DFMA remainder columns share the FP64 pipe)",
                          "note": "FP64 work: MEASURED_PEAKS.json holds only HBM and bf16 peaks, so the denominator is the "
                                  "FP64 DMMA (mma.sync m8n8k4) throughput measured by nmfk_measure_peak in this run; the "
                                  "DFMA pipe measured %.1f TFLOP/s. achieved = 8*n*m*k flops per restart-iteration / "

@@ -425,12 +425,20 @@ int32_t nmfk_solve(nmfk_ctx* c, nmfk_batch* const* batches, int32_t nb, const nm
     std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return batches[x]->k > batches[y]->k; });
     const size_t es = esize(c->dtype);
     CU(c, cudaEventRecord(c->ev0, c->stream));
+    // Resident engine: one CTA runs one restart to its stop, and restarts of one sweep stop anywhere
+    // between a few hundred and maxiter iterations.  To keep the tail of the sweep short, a solve is
+    // enqueued as a sequence of launches that each advance every unfinished restart by at most
+    // kResidentChunk iterations (the state is resumable; finished restarts exit at once): SMs freed by
+    // short restarts are refilled at chunk granularity and the last wave is at most one chunk long.
+    constexpr int kResidentChunk = 500;
+    const int user_limit = p->iter_limit > 0 ? std::min(p->iter_limit, p->maxiter) : p->maxiter;
+    std::vector<int> mode(nb, 0);  // 1 dmma, 2 scalar resident, 3 tiled
+    std::vector<SolveArgs> args(nb);
     for (int q = 0; q < nb; ++q) {
         nmfk_batch* b = batches[ord[q]];
-        SolveArgs a;
+        SolveArgs& a = args[q];
         fill_args(b, p, a);
-        cudaStream_t s = c->pool[q];
-        CU(c, cudaStreamWaitEvent(s, c->ev0, 0));
+        CU(c, cudaStreamWaitEvent(c->pool[q], c->ev0, 0));
         const bool want_scalar = (p->engine == NMFK_ENGINE_RESIDENT_SCALAR) || c->dtype != NMFK_F64;
         const bool fits_dmma = !want_scalar && resident_dmma_fits(a.n, a.m, a.k);
         const bool fits_scalar = resident_fits(a.n, a.m, a.k, es);
@@ -438,17 +446,25 @@ int32_t nmfk_solve(nmfk_ctx* c, nmfk_batch* const* batches, int32_t nb, const nm
         if (p->engine == NMFK_ENGINE_TILED) resident = false;
         if ((p->engine == NMFK_ENGINE_RESIDENT || p->engine == NMFK_ENGINE_RESIDENT_SCALAR) && !resident)
             return fail(c, NMFK_E_UNSUPPORTED, "resident engine: factors do not fit in shared memory (or k > 32)");
-        if (resident) {
-            if (fits_dmma)
-                CU(c, launch_kl_resident_dmma(a, s));
+        if (!resident && !tiled_supported(a.k)) return fail(c, NMFK_E_UNSUPPORTED, "tiled engine: k > 32 is not supported");
+        mode[q] = resident ? (fits_dmma ? 1 : 2) : 3;
+    }
+    for (int lim = std::min(kResidentChunk, user_limit);; lim = std::min(lim + kResidentChunk, user_limit)) {
+        for (int q = 0; q < nb; ++q) {
+            if (mode[q] == 3) continue;
+            SolveArgs a = args[q];
+            a.iter_limit = lim < p->maxiter ? lim : p->iter_limit;  // the last launch runs to the real stop
+            if (mode[q] == 1)
+                CU(c, launch_kl_resident_dmma(a, c->pool[q]));
             else
-                CU(c, c->dtype == NMFK_F64 ? launch_kl_resident_f64(a, s) : launch_kl_resident_f32(a, s));
+                CU(c, c->dtype == NMFK_F64 ? launch_kl_resident_f64(a, c->pool[q]) : launch_kl_resident_f32(a, c->pool[q]));
             c->launches += 1;
-        } else {
-            if (!tiled_supported(a.k)) return fail(c, NMFK_E_UNSUPPORTED, "tiled engine: k > 32 is not supported");
-            CU(c, solve_tiled(a, c->dtype, s, &c->launches));
         }
-        CU(c, cudaEventRecord(c->pool_ev[q], s));
+        if (lim >= user_limit) break;
+    }
+    for (int q = 0; q < nb; ++q) {
+        if (mode[q] == 3) CU(c, solve_tiled(args[q], c->dtype, c->pool[q], &c->launches));
+        CU(c, cudaEventRecord(c->pool_ev[q], c->pool[q]));
         CU(c, cudaStreamWaitEvent(c->stream, c->pool_ev[q], 0));
     }
     CU(c, cudaEventRecord(c->ev1, c->stream));

@@ -414,6 +414,7 @@ __global__ void __launch_bounds__(resident_threads(K), 1) kl_resident_kernel(con
     const int tid = threadIdx.x, NT = blockDim.x;
     UnitState* stg = a.st + r;
     if (stg->done) return;  // finished in an earlier (resumed) solve
+    if (a.iter_limit > 0 && a.iter_limit < a.maxiter && stg->it >= a.iter_limit) return;  // paused beyond this launch
 
     const ResidentSmem L = ResidentSmem::make(n, m, KP, sizeof(TC), sizeof(TX), NT);
     TC* Ws = reinterpret_cast<TC*>(smem + L.off_W);

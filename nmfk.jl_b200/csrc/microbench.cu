@@ -67,6 +67,51 @@ __global__ void latency_kernel(double* out, int iters, int which, double a, doub
     }
 }
 
+// throughput of single instructions / short sequences, 8 independent chains per thread:
+// MODE 0 MUFU.RCP64H, 1 MUFU.RCP (f32), 2 one DMMA + 8 DFMA per step (equal FP64-pipe time if shared),
+// 3 the reciprocal sequence of the KL hot loop (RCP64H + 4 DFMA + DMUL)
+template <int MODE>
+__global__ void __launch_bounds__(256) op_peak_kernel(double* out, int iters, double a, double b) {
+    double x[8];
+    float xf[8];
+    double c0[2] = {0.0, 0.0};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        x[c] = a + 0.001 * (threadIdx.x + c);
+        xf[c] = (float)x[c];
+    }
+    for (int i = 0; i < iters; ++i) {
+        if (MODE == 0) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) asm volatile("rcp.approx.ftz.f64 %0, %0;" : "+d"(x[c]));
+        } else if (MODE == 1) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(xf[c]));
+        } else if (MODE == 2) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c0[0]), "+d"(c0[1])
+                         : "d"(a), "d"(b));
+#pragma unroll
+            for (int c = 0; c < 8; ++c) x[c] = fma(x[c], a, b);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                double r;
+                asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x[c]));
+                double e = fma(-x[c], r, 1.0);
+                r = fma(r, e, r);
+                e = fma(-x[c], r, 1.0);
+                r = fma(r, e, r);
+                x[c] = r * b;
+            }
+        }
+    }
+    double s = c0[0] + c0[1];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s += x[c] + (double)xf[c];
+    if (s == -1.2345) out[0] = s;
+}
+
 __global__ void copy_kernel(const double4* __restrict__ src, double4* __restrict__ dst, long long n4) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
         dst[i] = src[i];
@@ -158,6 +203,34 @@ cudaError_t measure_peak(int which, double* value, cudaStream_t s) {
         cudaFree(out);
         if (e != cudaSuccess) return e;
         *value = h[0];
+        return cudaSuccess;
+    }
+    if (which >= 7 && which <= 10) {
+        // 7: MUFU.RCP64H, 8: MUFU.RCP f32, 10: KL reciprocal sequence -> SM cycles per warp instruction (sequence)
+        // per scheduler; 9: DMMA + DFMA mixed -> TFLOP/s of the two together
+        double* out = nullptr;
+        if ((e = cudaMalloc(&out, 64)) != cudaSuccess) return e;
+        const int blocks = sms * 8, threads = 256, iters = 2048;
+        if (which == 7)
+            e = time_best([&] { op_peak_kernel<0><<<blocks, threads, 0, s>>>(out, iters, 1.5, 0.75); }, 3, &ms, s);
+        else if (which == 8)
+            e = time_best([&] { op_peak_kernel<1><<<blocks, threads, 0, s>>>(out, iters, 1.5, 0.75); }, 3, &ms, s);
+        else if (which == 9)
+            e = time_best([&] { op_peak_kernel<2><<<blocks, threads, 0, s>>>(out, iters, 1.0000001, 1e-9); }, 3, &ms, s);
+        else
+            e = time_best([&] { op_peak_kernel<3><<<blocks, threads, 0, s>>>(out, iters, 1.5, 0.75); }, 3, &ms, s);
+        cudaFree(out);
+        if (e != cudaSuccess) return e;
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+        if (which == 9) {
+            const double flops = (512.0 + 8.0 * 64.0) * iters * (double)blocks * (threads / 32);
+            *value = flops / (ms * 1e-3) / 1e12;
+        } else {
+            // warp instructions (sequences) issued per scheduler, at the maximum SM clock
+            const double per_smsp = 8.0 * iters * (double)blocks * (threads / 32) / (sms * 4.0);
+            *value = (ms * 1e-3) * (double)khz * 1e3 / per_smsp;
+        }
         return cudaSuccess;
     }
     return cudaErrorInvalidValue;
