@@ -148,6 +148,21 @@ int32_t nmfk_batch_import(nmfk_batch* b, const void* W, const void* H, const dou
 /* phi = normnan(X - W*H) with NaN residuals dropped (NMFkExecute.jl:664-668) for host factors */
 int32_t nmfk_fit(nmfk_ctx* ctx, int32_t k, const void* W, const void* H, double* phi);
 
+/* ---- row-sharded X (BASELINE config C5; NMFmultiplicative(::DArray), NMFkMultiplicative.jl:129-197) ------
+ * One process per GPU.  After nmfk_ctx_comm_init the ctx holds a BLOCK OF ROWS: nmfk_set_X receives the
+ * local rows [row0, row0 + n_local) of the n_global x m matrix, W stacks are n_local x k x R, H stacks are
+ * replicated (k x m x R, identical on every rank).  nmfk_solve then runs the tiled engine and, per
+ * iteration, sum-all-reduces (NCCL, on the ctx stream) the stacked R x (k x m) numerators W'(X./(WH)) together
+ * with the R x k column sums of W - the exchange the reference does with collect/distribute at :160-167 -
+ * and, at every check, the 2R objective sums.  The W-update needs no exchange.  Objectives, iteration
+ * counts and stop reasons are identical on all ranks; nmfk_batch_get returns the local rows of W.
+ * nmfk_batch_init_random draws the streams of the GLOBAL matrices and keeps this rank's rows.
+ * id128: 128-byte NCCL unique id made by nmfk_comm_unique_id on one rank and sent to the others by the
+ * caller (any side channel).  nranks == 1 with id128 == NULL runs the same code path without NCCL. */
+int32_t nmfk_comm_unique_id(void* id128);
+int32_t nmfk_ctx_comm_init(nmfk_ctx* ctx, int32_t nranks, int32_t rank, const void* id128, int64_t row0, int64_t n_global);
+int32_t nmfk_ctx_comm_destroy(nmfk_ctx* ctx);
+
 /* ---- robustness: replaces sortperm + clustersolutions + finalize (NMFkExecute.jl:545-638,
  *      NMFkCluster.jl:425-517, NMFkFinalize.jl:36-79) on the device-resident H stack ----------
  * order        R      0-based restart indices sorted by objective (stable), order[0] = best

@@ -2,6 +2,9 @@
 // restarts, solve, robustness, and the one-call forms that mirror the reference's
 // execute_run / execute (/root/reference/src/NMFkExecute.jl:178-233, 483-711).
 // Host-side logic only; every numeric step runs in the CUDA kernels of this directory.
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: the library is bound at run time (dlopen), see ShardNccl
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -35,6 +38,10 @@ struct nmfk_ctx {
     double last_solve_ms = 0.0;
     double* d_partials = nullptr;  // residual partial sums
     size_t partials_cap = 0;
+    // row-sharded X (nmfk_ctx_comm_init): this ctx holds rows [row0, row0 + n) of an n_global x m matrix
+    ShardComm shard{nullptr, 1, 0, nullptr};
+    bool sharded = false;
+    int64_t row0 = 0, n_global = 0;
 };
 
 struct nmfk_batch {
@@ -66,7 +73,96 @@ static int32_t fail(nmfk_ctx* c, int32_t code, const std::string& msg) {
             return fail((ctx), (int32_t)e__, std::string(#call) + ": " + cudaGetErrorString(e__));      \
     } while (0)
 
+// NCCL is bound with dlopen at the first nmfk_comm_* call: in a process that already loaded a
+// libnccl.so.2 (torch ships its own) that copy is reused, otherwise the system library is loaded;
+// libnmfk_b200.so itself has no link-time dependency on NCCL.
+namespace {
+struct ShardNccl {
+    void* lib = nullptr;
+    decltype(&ncclGetUniqueId) getUniqueId = nullptr;
+    decltype(&ncclCommInitRank) commInitRank = nullptr;
+    decltype(&ncclAllReduce) allReduce = nullptr;
+    decltype(&ncclCommDestroy) commDestroy = nullptr;
+    decltype(&ncclGetErrorString) getErrorString = nullptr;
+    std::string err;
+    bool load() {
+        if (lib) return true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) {
+            err = std::string("cannot load NCCL: ") + dlerror();
+            return false;
+        }
+        getUniqueId = reinterpret_cast<decltype(getUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+        commInitRank = reinterpret_cast<decltype(commInitRank)>(dlsym(lib, "ncclCommInitRank"));
+        allReduce = reinterpret_cast<decltype(allReduce)>(dlsym(lib, "ncclAllReduce"));
+        commDestroy = reinterpret_cast<decltype(commDestroy)>(dlsym(lib, "ncclCommDestroy"));
+        getErrorString = reinterpret_cast<decltype(getErrorString)>(dlsym(lib, "ncclGetErrorString"));
+        if (!getUniqueId || !commInitRank || !allReduce || !commDestroy || !getErrorString) {
+            err = "NCCL library lacks a required symbol";
+            lib = nullptr;
+            return false;
+        }
+        return true;
+    }
+};
+ShardNccl g_nccl;
+
+cudaError_t nccl_allreduce(void* comm, void* buf, size_t count, int dtype, cudaStream_t s) {
+    const ncclResult_t r = g_nccl.allReduce(buf, buf, count, dtype == 1 ? ncclDouble : ncclFloat, ncclSum,
+                                            static_cast<ncclComm_t>(comm), s);
+    return r == ncclSuccess ? cudaSuccess : cudaErrorUnknown;
+}
+// single-rank stand-in (nranks == 1): the sum over one rank is the buffer itself
+cudaError_t identity_allreduce(void*, void*, size_t, int, cudaStream_t) { return cudaSuccess; }
+}  // namespace
+
 // Definitions below inherit C linkage from their declarations in include/nmfk_b200.h.
+
+int32_t nmfk_comm_unique_id(void* id128) {
+    if (!id128) return fail(nullptr, NMFK_E_INVALID, "nmfk_comm_unique_id: NULL buffer");
+    if (!g_nccl.load()) return fail(nullptr, NMFK_E_UNSUPPORTED, g_nccl.err);
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    const ncclResult_t r = g_nccl.getUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, NMFK_E_UNSUPPORTED, std::string("ncclGetUniqueId: ") + g_nccl.getErrorString(r));
+    std::memcpy(id128, &id, 128);
+    return NMFK_OK;
+}
+
+int32_t nmfk_ctx_comm_init(nmfk_ctx* c, int32_t nranks, int32_t rank, const void* id128, int64_t row0, int64_t n_global) {
+    if (!c || nranks < 1 || rank < 0 || rank >= nranks || row0 < 0 || n_global < 1)
+        return fail(c, NMFK_E_INVALID, "nmfk_ctx_comm_init: bad arguments");
+    if (c->sharded) return fail(c, NMFK_E_INVALID, "nmfk_ctx_comm_init: ctx already has a communicator");
+    CU(c, cudaSetDevice(c->device));
+    if (nranks == 1 && !id128) {
+        c->shard = ShardComm{nullptr, 1, 0, identity_allreduce};
+    } else {
+        if (!id128) return fail(c, NMFK_E_INVALID, "nmfk_ctx_comm_init: NULL unique id");
+        if (!g_nccl.load()) return fail(c, NMFK_E_UNSUPPORTED, g_nccl.err);
+        ncclUniqueId id;
+        std::memcpy(&id, id128, 128);
+        ncclComm_t comm = nullptr;
+        const ncclResult_t r = g_nccl.commInitRank(&comm, nranks, id, rank);
+        if (r != ncclSuccess)
+            return fail(c, NMFK_E_UNSUPPORTED, std::string("ncclCommInitRank: ") + g_nccl.getErrorString(r));
+        c->shard = ShardComm{comm, nranks, rank, nccl_allreduce};
+    }
+    c->sharded = true;
+    c->row0 = row0;
+    c->n_global = n_global;
+    return NMFK_OK;
+}
+
+int32_t nmfk_ctx_comm_destroy(nmfk_ctx* c) {
+    if (!c) return fail(nullptr, NMFK_E_INVALID, "ctx is NULL");
+    if (c->sharded && c->shard.comm) g_nccl.commDestroy(static_cast<ncclComm_t>(c->shard.comm));
+    c->shard = ShardComm{nullptr, 1, 0, nullptr};
+    c->sharded = false;
+    return NMFK_OK;
+}
 
 int32_t nmfk_abi_version(void) { return NMFK_ABI_VERSION; }
 
@@ -115,6 +211,7 @@ int32_t nmfk_ctx_destroy(nmfk_ctx* c) {
     if (!c) return NMFK_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    nmfk_ctx_comm_destroy(c);
     if (c->Xp) cudaFree(c->Xp);
     if (c->Xpt) cudaFree(c->Xpt);
     if (c->d_partials) cudaFree(c->d_partials);
@@ -351,7 +448,10 @@ int32_t nmfk_batch_init_random(nmfk_batch* b, uint64_t seed0) {
     if (!b) return fail(nullptr, NMFK_E_INVALID, "nmfk_batch_init_random: NULL batch");
     nmfk_ctx* c = b->ctx;
     CU(c, cudaSetDevice(c->device));
-    CU(c, launch_philox_init(b->W, b->H, c->n, b->k, c->m, b->R, seed0, c->dtype, c->stream));
+    if (c->sharded && (c->row0 + c->n > c->n_global))
+        return fail(c, NMFK_E_SHAPE, "row-sharded ctx: row0 + local rows exceeds n_global");
+    CU(c, launch_philox_init(b->W, b->H, c->sharded ? c->n_global : c->n, c->sharded ? c->row0 : 0, c->n, b->k, c->m, b->R,
+                             seed0, c->dtype, c->stream));
     c->launches += 1;
     return reset_state(b);
 }
@@ -393,6 +493,7 @@ static void fill_args(const nmfk_batch* b, const nmfk_params* p, SolveArgs& a) {
     a.tolOF = p->tolOF;
     a.eps_clamp = p->eps_clamp;
     a.weight = p->weight;
+    a.shard = c->sharded ? &c->shard : nullptr;
 }
 
 // tiled engine (kl_tiled.cu): host-driven, for factors that do not fit in shared memory
@@ -444,6 +545,12 @@ int32_t nmfk_solve(nmfk_ctx* c, nmfk_batch* const* batches, int32_t nb, const nm
         const bool fits_scalar = resident_fits(a.n, a.m, a.k, es);
         bool resident = fits_dmma || fits_scalar;
         if (p->engine == NMFK_ENGINE_TILED) resident = false;
+        if (c->sharded) {  // rows of X / W live on several GPUs: only the tiled engine exchanges partials
+            if (p->engine == NMFK_ENGINE_RESIDENT || p->engine == NMFK_ENGINE_RESIDENT_SCALAR)
+                return fail(c, NMFK_E_UNSUPPORTED, "row-sharded ctx: only the tiled engine is available");
+            if (p->normalize == 2) return fail(c, NMFK_E_UNSUPPORTED, "row-sharded ctx: clusterWmatrix normalisation is not available");
+            resident = false;
+        }
         if ((p->engine == NMFK_ENGINE_RESIDENT || p->engine == NMFK_ENGINE_RESIDENT_SCALAR) && !resident)
             return fail(c, NMFK_E_UNSUPPORTED, "resident engine: factors do not fit in shared memory (or k > 32)");
         if (!resident && !tiled_supported(a.k)) return fail(c, NMFK_E_UNSUPPORTED, "tiled engine: k > 32 is not supported");

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kTiledThreads, (K <= 12 ? 2 : 1)) tiled_pass_k
     }
     cp_async_wait<0>();
     if (!valid) return;
-    if (a.S == 1) {
+    if (a.partial == nullptr) {
         const TC* den = static_cast<const TC*>(a.den) + (long long)r * 32;
 #pragma unroll
         for (int c = 0; c < K; ++c)
@@ -177,9 +177,11 @@ __global__ void __launch_bounds__(kTiledThreads, (K <= 12 ? 2 : 1)) tiled_pass_k
     }
 }
 
-// S > 1: U[o,a] <- (U[o,a] * sum_slices partial) / den, slices added in order
+// U[o,a] <- (U[o,a] * sum_slices partial) / den, slices added in order.
+// red != nullptr (row-sharded X): the slice sum is written to red[r][o][K] instead (the numerators of
+// this rank's rows; all-reduced across ranks before tiled_apply_kernel finishes the update).
 template <typename TC, int K>
-__global__ void tiled_combine_kernel(const TiledPassArgs a) {
+__global__ void tiled_combine_kernel(const TiledPassArgs a, TC* __restrict__ red) {
     const int r = blockIdx.y;
     if (a.st[r].stop != 0) return;
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
@@ -194,12 +196,49 @@ __global__ void tiled_combine_kernel(const TiledPassArgs a) {
 #pragma unroll
         for (int c = 0; c < K; ++c) acc[c] += src[c];
     }
+    if (red != nullptr) {
+        TC* dst = red + ((long long)r * a.nown + o) * K;
+#pragma unroll
+        for (int c = 0; c < K; ++c) dst[c] = acc[c];
+        return;
+    }
 #pragma unroll
     for (int c = 0; c < K; ++c)
         if (c < a.k) {
             const long long idx = (long long)o * a.su_o + (long long)c * a.su_a;
             U[idx] = div_cold<TC>(U[idx] * acc[c], den[c]);
         }
+}
+
+// row-sharded X: U[o,a] <- (U[o,a] * red[r][o][a]) / den[r][a] with the all-reduced numerators / sums
+template <typename TC, int K>
+__global__ void tiled_apply_kernel(const TiledPassArgs a, const TC* __restrict__ red) {
+    const int r = blockIdx.y;
+    if (a.st[r].stop != 0) return;
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= a.nown) return;
+    TC* U = static_cast<TC*>(a.U) + (long long)r * a.u_rstride;
+    const TC* den = static_cast<const TC*>(a.den) + (long long)r * 32;
+    const TC* src = red + ((long long)r * a.nown + o) * K;
+#pragma unroll
+    for (int c = 0; c < K; ++c)
+        if (c < a.k) {
+            const long long idx = (long long)o * a.su_o + (long long)c * a.su_a;
+            U[idx] = div_cold<TC>(U[idx] * src[c], den[c]);
+        }
+}
+
+// row-sharded X: obj2[r][0..1] = sum over this rank's row blocks of the objective partials
+static __global__ void tiled_objsum_kernel(const double* __restrict__ partials, int nblk, int R, double* __restrict__ obj2) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    double a0 = 0.0, a1 = 0.0;
+    for (int b = 0; b < nblk; ++b) {
+        a0 += partials[((long long)r * nblk + b) * 2];
+        a1 += partials[((long long)r * nblk + b) * 2 + 1];
+    }
+    obj2[2 * r] = a0;
+    obj2[2 * r + 1] = a1;
 }
 
 // den[r][a] = sum_t V_r[t,a] : grid (k, R), fixed-order block reduction
@@ -472,8 +511,10 @@ static __global__ void tiled_guard_kernel(UnitState* st, int R, int it, int maxi
         atomicAdd(active_count, 1);
 }
 
+// red == nullptr: the complete half-update.  red != nullptr (row-sharded X, H-update): the pass leaves
+// the numerators of this rank's rows in red[R][nown][K]; launch_tiled_apply_k finishes after the all-reduce.
 template <typename TX, typename TC, int K>
-cudaError_t launch_tiled_pass_k(const TiledPassArgs& a, cudaStream_t s) {
+cudaError_t launch_tiled_pass_k(const TiledPassArgs& a, void* red, cudaStream_t s) {
     constexpr int VEC = VecOf<TC>::N;
     constexpr int KP = (K + VEC - 1) / VEC * VEC;
     constexpr int TCH = TiledCfg<TX>::TCH;
@@ -491,12 +532,19 @@ cudaError_t launch_tiled_pass_k(const TiledPassArgs& a, cudaStream_t s) {
         tiled_pass_kernel<TX, TC, K, false><<<(unsigned)grid, kTiledThreads, smem, s>>>(a);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if (a.S > 1) {
+    if (a.partial != nullptr) {
         dim3 g((a.nown + 255) / 256, a.R);
-        tiled_combine_kernel<TC, K><<<g, 256, 0, s>>>(a);
+        tiled_combine_kernel<TC, K><<<g, 256, 0, s>>>(a, static_cast<TC*>(red));
         e = cudaGetLastError();
     }
     return e;
+}
+
+template <typename TX, typename TC, int K>
+cudaError_t launch_tiled_apply_k(const TiledPassArgs& a, void* red, cudaStream_t s) {
+    dim3 g((a.nown + 255) / 256, a.R);
+    tiled_apply_kernel<TC, K><<<g, 256, 0, s>>>(a, static_cast<const TC*>(red));
+    return cudaGetLastError();
 }
 
 }  // namespace nmfk
@@ -507,9 +555,14 @@ cudaError_t launch_tiled_pass_k(const TiledPassArgs& a, cudaStream_t s) {
 namespace nmfk {
 
 template <typename TX, typename TC>
-cudaError_t dispatch_tiled_pass(const TiledPassArgs& a, cudaStream_t s) {
+cudaError_t dispatch_tiled_pass(const TiledPassArgs& a, void* red, cudaStream_t s) {
     const int kt = resident_template_k(a.k);
-    NMFK_DISPATCH_K(launch_tiled_pass_k, TX, TC, kt, a, s)
+    NMFK_DISPATCH_K(launch_tiled_pass_k, TX, TC, kt, a, red, s)
+}
+template <typename TX, typename TC>
+cudaError_t dispatch_tiled_apply(const TiledPassArgs& a, void* red, cudaStream_t s) {
+    const int kt = resident_template_k(a.k);
+    NMFK_DISPATCH_K(launch_tiled_apply_k, TX, TC, kt, a, red, s)
 }
 
 #define NMFK_TRY(call)                      \
@@ -547,7 +600,12 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     const int SH = slices(nblkH, n), SW = slices(nblkW, m);
     const int nblkObj = (n + 127) / 128;
 
-    TC* den = nullptr;
+    // row-sharded X: den and the H-update numerators are contiguous so that one all-reduce moves both
+    const ShardComm* sh = a.shard;
+    const bool sharded = sh != nullptr;
+    TC* den = nullptr;  // R x 32, followed by red (R x m x kt) when sharded
+    TC* red = nullptr;
+    double* obj2 = nullptr;
     TC* partial = nullptr;
     double* objp = nullptr;
     int* d_active = nullptr;
@@ -555,9 +613,16 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     std::vector<UnitState> hst((size_t)R);
     int it = 0;
     bool any_running = false;
-    const size_t psz = std::max((size_t)(SH > 1 ? (size_t)SH * R * m * kt : 0), (size_t)(SW > 1 ? (size_t)SW * R * n * kt : 0));
+    const size_t psz = std::max((size_t)((SH > 1 || sharded) ? (size_t)SH * R * m * kt : 0),
+                                (size_t)(SW > 1 ? (size_t)SW * R * n * kt : 0));
+    const size_t redsz = sharded ? (size_t)R * m * kt : 0;
+    if (sharded && a.normalize == 2) return cudaErrorNotSupported;  // column sums of W would need another exchange
 
-    NMFK_TRY(cudaMalloc(&den, (size_t)R * 32 * sizeof(TC)));
+    NMFK_TRY(cudaMalloc(&den, ((size_t)R * 32 + redsz) * sizeof(TC)));
+    if (sharded) {
+        red = den + (size_t)R * 32;
+        NMFK_TRY(cudaMalloc(&obj2, (size_t)R * 2 * sizeof(double)));
+    }
     if (psz) NMFK_TRY(cudaMalloc(&partial, psz * sizeof(TC)));
     NMFK_TRY(cudaMalloc(&objp, (size_t)R * nblkObj * 2 * sizeof(double)));
     NMFK_TRY(cudaMalloc(&d_active, sizeof(int)));
@@ -576,7 +641,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
         ph.U = a.H;
         ph.V = a.W;
         ph.den = den;
-        ph.partial = SH > 1 ? partial : nullptr;
+        ph.partial = (SH > 1 || sharded) ? partial : nullptr;
         ph.st = a.st;
         ph.ximp = a.ximp;
         ph.u_rstride = (long long)k * m;
@@ -637,13 +702,19 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
             if (!a.Hfixed) {
                 tiled_sums_kernel<TC><<<dim3(k, R), 256, 0, s>>>(a.W, (long long)n * k, 1, n, n, a.st, den);
                 NMFK_TRY(cudaGetLastError());
-                NMFK_TRY((dispatch_tiled_pass<TX, TC>(ph, s)));
-                *launches += 2 + (SH > 1);
+                NMFK_TRY((dispatch_tiled_pass<TX, TC>(ph, red, s)));
+                *launches += 2 + (SH > 1 || sharded);
+                if (sharded) {
+                    // colsum(W) and W' * (X ./ (W*H)) over this rank's rows -> sums over all rows, then the update
+                    NMFK_TRY(sh->allreduce(sh->comm, den, (size_t)R * 32 + redsz, sizeof(TC) == 8 ? 1 : 0, s));
+                    NMFK_TRY((dispatch_tiled_apply<TX, TC>(ph, red, s)));
+                    ++*launches;
+                }
             }
             if (!a.Wfixed) {
                 tiled_sums_kernel<TC><<<dim3(k, R), 256, 0, s>>>(a.H, (long long)k * m, k, 1, m, a.st, den);
                 NMFK_TRY(cudaGetLastError());
-                NMFK_TRY((dispatch_tiled_pass<TX, TC>(pw, s)));
+                NMFK_TRY((dispatch_tiled_pass<TX, TC>(pw, nullptr, s)));
                 *launches += 2 + (SW > 1);
             }
             if (a.has_nan) {
@@ -658,16 +729,22 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
                 tiled_objective_kernel<TX, TC><<<g, 128, (size_t)k * 128 * sizeof(TC), s>>>(
                     (const TX*)a.X, n, m, k, (const TC*)a.W, (const TC*)a.H, a.st, (TC)a.lambda, 0, 1, a.weight, objp);
                 NMFK_TRY(cudaGetLastError());
+                if (sharded) {  // the objective is a sum over all rows
+                    tiled_objsum_kernel<<<(R + 127) / 128, 128, 0, s>>>(objp, nblkObj, R, obj2);
+                    NMFK_TRY(cudaGetLastError());
+                    NMFK_TRY(sh->allreduce(sh->comm, obj2, (size_t)R * 2, 1, s));
+                    ++*launches;
+                }
                 TiledCheckArgs c{};
                 c.W = a.W;
                 c.H = a.H;
                 c.st = a.st;
                 c.canon = a.canon;
-                c.partials = objp;
+                c.partials = sharded ? obj2 : objp;
                 c.n = n;
                 c.m = m;
                 c.k = k;
-                c.nblk = nblkObj;
+                c.nblk = sharded ? 1 : nblkObj;
                 c.it = it;
                 c.maxbad = a.maxbad;
                 c.stopconv = a.stopconv;
@@ -688,7 +765,14 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
         tiled_objective_kernel<TX, TC><<<g, 128, (size_t)k * 128 * sizeof(TC), s>>>(
             (const TX*)a.X, n, m, k, (const TC*)a.W, (const TC*)a.H, a.st, (TC)a.lambda, 1, 0, a.weight, objp);
         NMFK_TRY(cudaGetLastError());
-        tiled_finish_kernel<TC><<<R, 256, 0, s>>>(a.W, a.H, a.st, objp, n, m, k, nblkObj, a.normalize);
+        if (sharded) {
+            tiled_objsum_kernel<<<(R + 127) / 128, 128, 0, s>>>(objp, nblkObj, R, obj2);
+            NMFK_TRY(cudaGetLastError());
+            NMFK_TRY(sh->allreduce(sh->comm, obj2, (size_t)R * 2, 1, s));
+            ++*launches;
+        }
+        tiled_finish_kernel<TC><<<R, 256, 0, s>>>(a.W, a.H, a.st, sharded ? obj2 : objp, n, m, k, sharded ? 1 : nblkObj,
+                                                  a.normalize);
         NMFK_TRY(cudaGetLastError());
         *launches += 2;
         NMFK_TRY(cudaStreamSynchronize(s));
@@ -697,6 +781,7 @@ done:
     if (den) cudaFree(den);
     if (partial) cudaFree(partial);
     if (objp) cudaFree(objp);
+    if (obj2) cudaFree(obj2);
     if (d_active) cudaFree(d_active);
     if (h_active) cudaFreeHost(h_active);
     return err;

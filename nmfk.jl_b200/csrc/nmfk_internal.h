@@ -24,6 +24,15 @@ struct UnitState {
     double obj_norm;   // normnan(X - W*H) (NMFkExecute.jl:792)
 };
 
+// Row-sharded X (BASELINE config C5; reference analogue NMFmultiplicative(::DArray),
+// NMFkMultiplicative.jl:129-197): this rank holds a block of rows of X and of W, H is replicated.
+// sum-all-reduce of `count` elements (dtype 0 = f32, 1 = f64) in place, stream ordered.
+struct ShardComm {
+    void* comm;  // ncclComm_t
+    int nranks, rank;
+    cudaError_t (*allreduce)(void* comm, void* buf, size_t count, int dtype, cudaStream_t s);
+};
+
 // Arguments of one batched KL solve (R restarts at one k).
 struct SolveArgs {
     const void* X;    // n x m column-major, zeros -> lambda, NaN kept
@@ -38,6 +47,7 @@ struct SolveArgs {
     int32_t SH, SW;   // DMMA resident engine: slices of the reduction range per half-update (host heuristic)
     int32_t maxiter, maxbad, maxre, stopconv, check_every, Wfixed, Hfixed, normalize, iter_limit;
     double lambda, tol, tolOF, eps_clamp, weight;
+    const ShardComm* shard;  // non-null: n is the LOCAL row count, the tiled engine all-reduces the k x m partials
 };
 
 // threads per restart-CTA of the resident engine: 512 (<=128 registers) while u/acc fit, 256 beyond
@@ -81,8 +91,9 @@ cudaError_t launch_preprocess(const void* Xraw, void* Xp, void* Xpt, int64_t n, 
                               int nblockmin, cudaStream_t s);
 
 // device Philox4x64-10 U(0,1) streams identical to numpy.random.Generator(Philox(key=seed)).random()
-cudaError_t launch_philox_init(void* W, void* H, int64_t n, int k, int64_t m, int R, uint64_t seed0, int dtype,
-                               cudaStream_t s);
+// (row-sharded X: n = global rows, this rank keeps rows [row0, row0 + nloc); otherwise row0 = 0, nloc = n)
+cudaError_t launch_philox_init(void* W, void* H, int64_t n, int64_t row0, int64_t nloc, int k, int64_t m, int R,
+                               uint64_t seed0, int dtype, cudaStream_t s);
 
 // clustering / silhouettes (K10-K12)
 struct ClusterArgs {

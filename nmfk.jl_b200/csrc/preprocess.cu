@@ -117,9 +117,11 @@ cudaError_t launch_preprocess(const void* Xraw, void* Xp, void* Xpt, int64_t n, 
 // ---- Philox4x64-10 U(0,1) initialisation ------------------------------------------------------
 // stream element e of restart r = numpy.random.Generator(Philox(key=seed0+r+1)).random(...)[e];
 // the first n*k elements fill W (column-major), the next k*m fill H: W is drawn before H.
+// Row-sharded X: the stream is that of the GLOBAL n x k matrix; this rank keeps rows [row0, row0 + nloc).
 template <typename T>
-__global__ void philox_init_kernel(T* __restrict__ W, T* __restrict__ H, long long nk, long long km, int R,
-                                   unsigned long long seed0) {
+__global__ void philox_init_kernel(T* __restrict__ W, T* __restrict__ H, long long n, long long row0, long long nloc,
+                                   int k, long long km, int R, unsigned long long seed0) {
+    const long long nk = n * k;
     const long long per = nk + km;
     const long long blocks4 = (per + 3) / 4;
     const long long total = blocks4 * R;
@@ -134,25 +136,26 @@ __global__ void philox_init_kernel(T* __restrict__ W, T* __restrict__ H, long lo
             const long long e = b * 4 + q;
             if (e >= per) break;
             const double u = philox_to_double(out[q]);
-            if (e < nk)
-                W[(long long)r * nk + e] = (T)u;
-            else
+            if (e < nk) {
+                const long long i = e % n - row0, c = e / n;
+                if (i >= 0 && i < nloc) W[(long long)r * nloc * k + i + c * nloc] = (T)u;
+            } else
                 H[(long long)r * km + (e - nk)] = (T)u;
         }
     }
 }
 
-cudaError_t launch_philox_init(void* W, void* H, int64_t n, int k, int64_t m, int R, uint64_t seed0, int dtype,
-                               cudaStream_t s) {
+cudaError_t launch_philox_init(void* W, void* H, int64_t n, int64_t row0, int64_t nloc, int k, int64_t m, int R,
+                               uint64_t seed0, int dtype, cudaStream_t s) {
     const long long nk = n * k, km = (long long)k * m;
     const long long total = ((nk + km + 3) / 4) * R;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
     if (dtype == 1)
-        philox_init_kernel<double><<<blocks, 256, 0, s>>>((double*)W, (double*)H, nk, km, R, seed0);
+        philox_init_kernel<double><<<blocks, 256, 0, s>>>((double*)W, (double*)H, n, row0, nloc, k, km, R, seed0);
     else
-        philox_init_kernel<float><<<blocks, 256, 0, s>>>((float*)W, (float*)H, nk, km, R, seed0);
+        philox_init_kernel<float><<<blocks, 256, 0, s>>>((float*)W, (float*)H, n, row0, nloc, k, km, R, seed0);
     return cudaGetLastError();
 }
 

@@ -58,6 +58,9 @@ SIGNATURES = {
     "nmfk_batch_device_ptrs": (_i32, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "nmfk_batch_import": (_i32, [_P, _P, _P, _pdbl, _pi32, _i32]),
     "nmfk_fit": (_i32, [_P, _i32, _P, _P, _pdbl]),
+    "nmfk_comm_unique_id": (_i32, [_P]),
+    "nmfk_ctx_comm_init": (_i32, [_P, _i32, _i32, _P, _i64, _i64]),
+    "nmfk_ctx_comm_destroy": (_i32, [_P]),
     "nmfk_solve": (_i32, [_P, C.POINTER(_P), _i32, C.POINTER(Params)]),
     "nmfk_batch_get": (_i32, [_P, _P, _P, _pdbl, _pdbl, _pi32, _pi32]),
     "nmfk_batch_objective": (_i32, [_P, _dbl, _pdbl]),

@@ -79,6 +79,17 @@ class Context:
         check(self._lib.nmfk_set_X(self._h, _ptr(Xf), self.n, self.m, self.dtype, lam, None, 0), self._h)
         return self.xinfo()
 
+    def comm_init(self, nranks: int, rank: int, unique_id: Optional[bytes], row0: int, n_global: int):
+        """Row-sharded X (BASELINE C5; NMFmultiplicative(::DArray), NMFkMultiplicative.jl:129-197): this
+        context holds rows [row0, row0 + n_local) of an n_global x m matrix, H is replicated, the tiled
+        engine all-reduces the k x m numerators every iteration.  unique_id: 128 bytes from
+        `comm_unique_id()` on one rank (None with nranks == 1: same code path, no NCCL)."""
+        buf = None
+        if unique_id is not None:
+            assert len(unique_id) == 128
+            buf = C.create_string_buffer(bytes(unique_id), 128)
+        check(self._lib.nmfk_ctx_comm_init(self._h, int(nranks), int(rank), buf, int(row0), int(n_global)), self._h)
+
     def xinfo(self) -> XInfo:
         xi = XInfo()
         check(self._lib.nmfk_get_xinfo(self._h, C.byref(xi)), self._h)
@@ -105,6 +116,13 @@ class Context:
         v = C.c_double()
         check(self._lib.nmfk_measure_peak(self._h, which, C.byref(v)), self._h)
         return v.value
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL unique id (ncclGetUniqueId); send it to the other ranks by any side channel."""
+    buf = C.create_string_buffer(128)
+    check(_lib.load().nmfk_comm_unique_id(buf))
+    return buf.raw
 
 
 class Batch:

@@ -22,6 +22,51 @@ from . import api
 from ._lib import check
 
 
+def row_block(n: int, rank: int, world: int):
+    """Rows [r0, r1) of an n-row matrix owned by `rank` (contiguous blocks, sizes differ by at most 1)."""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def exchange_unique_id(rank: int, group=None) -> bytes:
+    """NCCL unique id of the library's own communicator: made on rank 0, broadcast with torch.distributed
+    (any backend: 128 bytes on the host)."""
+    import torch.distributed as td
+
+    box = [api.comm_unique_id() if rank == 0 else None]
+    td.broadcast_object_list(box, src=0, group=group)
+    return box[0]
+
+
+def solve_rowsharded(ctx, X_local, k: int, R: int, *, rank: int, world: int, n_global: int, unique_id=None,
+                     Winit_local=None, Hinit=None, seed0: Optional[int] = None, params=None):
+    """NMFmultiplicative for R restarts at one k on a matrix whose ROWS are split over `world` GPUs
+    (one process per GPU; reference analogue: NMFmultiplicative(::DArray), NMFkMultiplicative.jl:129-197,
+    with the full stop rule of the dense method).
+
+    X_local: this rank's rows (row_block(n_global, rank, world)); Winit_local (R, n_local, k) and Hinit
+    (R, k, m, identical on all ranks) or seed0 for the device Philox streams of the global matrices.
+    Returns dict(W_local (R, n_local, k), H (R, k, m), obj_norm, obj_ssq, iters, stop_reason): everything
+    but W_local is identical on all ranks."""
+    r0, r1 = row_block(n_global, rank, world)
+    assert X_local.shape[0] == r1 - r0, "X_local must hold rows row_block(n_global, rank, world)"
+    ctx.comm_init(world, rank, unique_id, r0, n_global)
+    ctx.set_X(X_local)
+    p = params or api.default_params()
+    p.engine = 2  # NMFK_ENGINE_TILED: the engine that exchanges partial sums
+    b = ctx.batch(k, R)
+    try:
+        if Winit_local is not None:
+            b.set_init(Winit_local, Hinit)
+        else:
+            b.init_random(int(seed0 or 0))
+        ctx.solve([b], p)
+        out = b.get()
+    finally:
+        b.close()
+    return dict(W_local=out["W"], H=out["H"], obj_norm=out["obj_norm"], obj_ssq=out["obj_ssq"], iters=out["iters"],
+                stop_reason=out["stop_reason"], solve_ms=ctx.last_solve_ms)
+
+
 def owner_of(k_index: int, world: int) -> int:
     """Rank that clusters the solutions of the k_index-th entry of the sweep."""
     return k_index % world

@@ -93,3 +93,72 @@ def test_merge_sweep_and_aic_match_oracle_rules():
     # aic formula of NMFkExecute.jl:697-708
     assert nbdist.aic(15, 5, 2, 0, 3.733236078245728) == pytest.approx(-145.01595060344386, rel=1e-12)
     assert nbdist.aic(15, 5, 2, 5, 2.0) == pytest.approx(2 * (30 + 10) + 70 * np.log(2.0 / 70))
+
+
+# ---------------------------------------------------------------------------------------------
+# row-sharded X (BASELINE C5; NMFmultiplicative(::DArray), NMFkMultiplicative.jl:129-197): the exchange
+# the tiled engine performs - sum-all-reduce of the k x m numerators and of colsum(W), W-update local -
+# restated in NumPy over gloo must reproduce the dense iteration of the oracle.
+# ---------------------------------------------------------------------------------------------
+def test_row_block_partition():
+    for n in (1, 7, 10, 1000, 2_000_000):
+        for world in (1, 2, 3, 8):
+            blocks = [nbdist.row_block(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _rowshard_worker(rank, world, port, n, m, k, niter, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)
+        X = rng.random((n, 3)) @ rng.random((3, m))
+        W = rng.random((n, k))
+        H = rng.random((k, m))
+        r0, r1 = nbdist.row_block(n, rank, world)
+        Xl, Wl = X[r0:r1], W[r0:r1].copy()
+        for _ in range(niter):
+            num = Wl.T @ (Xl / (Wl @ H))          # k x m numerators of this rank's rows
+            den = Wl.sum(axis=0)                  # colsum(W) of this rank's rows
+            buf = torch.from_numpy(np.concatenate([den, num.ravel()]))
+            td.all_reduce(buf)                    # the one exchange of an iteration
+            den, num = buf.numpy()[:k], buf.numpy()[k:].reshape(k, m)
+            H = H * num / den[:, None]            # :67, identical on every rank
+            Wl = Wl * ((Xl / (Wl @ H)) @ H.T) / H.sum(axis=1)[None, :]   # :70, rows are independent
+        ssq = torch.tensor([float(np.sum((Xl - Wl @ H) ** 2))], dtype=torch.float64)
+        td.all_reduce(ssq)                        # :74 objective = sum over all rows
+        q.put((rank, r0, r1, Wl, H, float(ssq[0])))
+    finally:
+        td.destroy_process_group()
+
+
+def test_rowsharded_exchange_reproduces_dense_iteration_gloo():
+    world, n, m, k, niter = 2, 37, 9, 3, 12
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rowshard_worker, args=(r, world, port, n, m, k, niter, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(5)
+    X = rng.random((n, 3)) @ rng.random((3, m))
+    W0 = rng.random((n, k))
+    H0 = rng.random((k, m))
+    Ws, Hs = [], []
+    o.nmf_multiplicative(np.asfortranarray(X.copy()), k, Winit=W0, Hinit=H0, maxiter=niter,
+                         trace=lambda it, W, H, obj: (Ws.append(W.copy()), Hs.append(H.copy())))
+    Wd, Hd = Ws[niter - 1], Hs[niter - 1]
+    Wsh = np.concatenate([g[3] for g in got])
+    assert [g[1:3] for g in got] == [nbdist.row_block(n, r, world) for r in range(world)]
+    assert np.allclose(got[0][4], got[1][4], rtol=0, atol=0)          # H replicated bit for bit
+    assert np.max(np.abs(got[0][4] - Hd)) <= 1e-12 * np.max(Hd)
+    assert np.max(np.abs(Wsh - Wd)) <= 1e-12 * np.max(Wd)
+    assert got[0][5] == got[1][5] == pytest.approx(float(np.sum((X - Wd @ Hd) ** 2)), rel=1e-10)

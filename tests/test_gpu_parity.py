@@ -315,3 +315,56 @@ def test_tiled_full_stop_rule_matches_resident_and_oracle(ctx):
         W, H, of = o.execute_singlerun_compute(X.copy(), k, Winit=W0[r].copy(), Hinit=H0[r].copy(), info=inf)
         assert res[2]["iters"][r] == inf["iters"]
         assert relerr(res[2]["W"][r], W) < 1e-7 and relerr(res[2]["H"][r], H) < 1e-7
+
+
+# ---------------------------------------------------------------------------------------------
+# row-sharded X code path (nmfk_ctx_comm_init): on one GPU with nranks == 1 the tiled engine runs
+# the same kernels as the multi-GPU run (numerators to a buffer, "all-reduce", apply) without NCCL;
+# tests/multigpu/rowshard_ranks.py is the 2-GPU run of the same thing under torchrun.
+# ---------------------------------------------------------------------------------------------
+def test_rowsharded_path_single_rank_trace_parity():
+    n, m, k, niter = 300, 64, 5, 25
+    X = synth.mixture(n, m, 3, seed=7)
+    W0, H0 = synth.philox_inits(11, 1, n, k, m)
+    with nb.Context() as c:
+        c.comm_init(1, 0, None, 0, n)
+        Wt, Ht, ob = nb.trace(X, k, W0[0], H0[0], niter, ctx=c, engine=2)
+    Wr, Hr, obr = oracle_trace(X, k, W0[0], H0[0], niter)
+    for t in range(niter):
+        assert relerr(Wt[t], Wr[t]) < RTOL64, ("W", t)
+        assert relerr(Ht[t], Hr[t]) < RTOL64, ("H", t)
+    assert relerr(ob, obr) < 1e-8
+
+
+def test_rowsharded_init_random_keeps_own_rows_of_the_global_stream():
+    n_global, m, k, R = 400, 30, 4, 3
+    r0, r1 = 100, 300
+    X = synth.mixture(n_global, m, 3, seed=3)
+    W0, H0 = synth.philox_inits(21, R, n_global, k, m)
+    with nb.Context() as c:
+        c.comm_init(1, 0, None, r0, n_global)
+        c.set_X(X[r0:r1])
+        b = c.batch(k, R)
+        b.init_random(21)
+        c.solve([b], nb.default_params(engine=2, maxiter=0, normalize=0))
+        out = b.get()
+        b.close()
+    assert np.array_equal(out["W"], W0[:, r0:r1, :])
+    assert np.array_equal(out["H"], H0)
+
+
+def test_rowsharded_two_gpus_torchrun():
+    """Real exchange over NCCL: needs two GPUs (skipped on a one-GPU box; run with gpurun --gpus 2)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611",
+                        os.path.join(root, "tests", "multigpu", "rowshard_ranks.py")], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ROWSHARD OK" in r.stdout
