@@ -56,8 +56,17 @@ enum nmfk_stop_reason {
 
 /* AUTO: resident when the factors fit in one SM's shared memory, else tiled.  RESIDENT uses the
  * tensor-pipe (DMMA m8n8k4) formulation for Float64 and the scalar-FMA one for Float32;
- * RESIDENT_SCALAR forces the scalar-FMA formulation (kept for A/B measurements and parity). */
-enum nmfk_engine { NMFK_ENGINE_AUTO = 0, NMFK_ENGINE_RESIDENT = 1, NMFK_ENGINE_TILED = 2, NMFK_ENGINE_RESIDENT_SCALAR = 3 };
+ * RESIDENT_SCALAR forces the scalar-FMA formulation (kept for A/B measurements and parity).
+ * TILED: Float32 data without NaN (row and column counts multiples of 4) run both half-updates on the
+ * 5th-generation tensor cores (tcgen05.mma kind::tf32, 3-term split, tensor-memory accumulators);
+ * Float64, NaN-imputing and odd-sized problems use the scalar-FMA pass kernel. */
+enum nmfk_engine {
+    NMFK_ENGINE_AUTO = 0,
+    NMFK_ENGINE_RESIDENT = 1,
+    NMFK_ENGINE_TILED = 2,
+    NMFK_ENGINE_RESIDENT_SCALAR = 3,
+    NMFK_ENGINE_TILED_SCALAR = 4 /* tiled engine with the scalar-FMA pass kernel also for Float32 (A/B, parity) */
+};
 
 /* Keyword arguments of NMFmultiplicative (NMFkMultiplicative.jl:24) and of
  * execute_singlerun_compute (NMFkExecute.jl:729), one field per keyword. */
@@ -216,6 +225,14 @@ double nmfk_last_solve_ms(const nmfk_ctx* ctx);
  * which: 0 = FP64 DFMA TFLOP/s, 1 = FP64 DMMA (mma.sync m8n8k4) TFLOP/s, 2 = FP32 FFMA TFLOP/s,
  *        3 = device-to-device copy GB/s (read+write bytes) */
 int32_t nmfk_measure_peak(nmfk_ctx* ctx, int32_t which, double* value);
+/* Device self-test of the tcgen05 / tensor-memory building blocks of the Float32 tiled engine (no reference
+ * counterpart): U 128x16, V 64x16 row-major; mode bits: 1 P=UV' (A,B shared), 2 P (A tensor memory),
+ * 4 / 8 ACC = 0.5 P V with the 2-term TF32 split of the A operand (B K-major copy / B MN-major alias). */
+/* cycle counts of the same building blocks (tools/umma_selftest.py --timing documents the 8 slots) and the
+ * accumulator of reps*8 chained K-steps (round-toward-zero accumulation test) */
+int32_t nmfk_umma_timing(nmfk_ctx* ctx, const float* U, const float* V, int32_t reps, int64_t* cycles8, float* acc);
+int32_t nmfk_umma_selftest(nmfk_ctx* ctx, const float* U, const float* V, int32_t mode, float* Pss, float* Pts, float* ACCa,
+                           float* ACCb, int32_t* err);
 
 /* first `count` doubles of numpy.random.Generator(Philox(key=seed)).random(), computed on the HOST with the
  * same code the device initialiser uses (test hook: bit-compatibility of the init streams without a GPU) */

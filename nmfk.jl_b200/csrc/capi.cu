@@ -493,6 +493,7 @@ static void fill_args(const nmfk_batch* b, const nmfk_params* p, SolveArgs& a) {
     a.tolOF = p->tolOF;
     a.eps_clamp = p->eps_clamp;
     a.weight = p->weight;
+    a.tiled_tc = p->engine != NMFK_ENGINE_TILED_SCALAR;
     a.shard = c->sharded ? &c->shard : nullptr;
 }
 
@@ -544,7 +545,7 @@ int32_t nmfk_solve(nmfk_ctx* c, nmfk_batch* const* batches, int32_t nb, const nm
         const bool fits_dmma = !want_scalar && resident_dmma_fits(a.n, a.m, a.k);
         const bool fits_scalar = resident_fits(a.n, a.m, a.k, es);
         bool resident = fits_dmma || fits_scalar;
-        if (p->engine == NMFK_ENGINE_TILED) resident = false;
+        if (p->engine == NMFK_ENGINE_TILED || p->engine == NMFK_ENGINE_TILED_SCALAR) resident = false;
         if (c->sharded) {  // rows of X / W live on several GPUs: only the tiled engine exchanges partials
             if (p->engine == NMFK_ENGINE_RESIDENT || p->engine == NMFK_ENGINE_RESIDENT_SCALAR)
                 return fail(c, NMFK_E_UNSUPPORTED, "row-sharded ctx: only the tiled engine is available");
@@ -1025,6 +1026,24 @@ int32_t nmfk_measure_peak(nmfk_ctx* c, int32_t which, double* value) {
     if (!c || !value) return fail(c, NMFK_E_INVALID, "nmfk_measure_peak: NULL argument");
     CU(c, cudaSetDevice(c->device));
     CU(c, measure_peak(which, value, c->stream));
+    return NMFK_OK;
+}
+
+// tcgen05 / tensor-memory building blocks of the Float32 tiled engine, checked on the device (tc_selftest.cu)
+int32_t nmfk_umma_selftest(nmfk_ctx* c, const float* U, const float* V, int32_t mode, float* Pss, float* Pts, float* ACCa,
+                           float* ACCb, int32_t* err) {
+    if (!c || !U || !V || !Pss || !Pts || !ACCa || !ACCb || !err) return fail(c, NMFK_E_INVALID, "nmfk_umma_selftest: NULL argument");
+    CU(c, cudaSetDevice(c->device));
+    int e = 0;
+    CU(c, umma_selftest(U, V, mode, Pss, Pts, ACCa, ACCb, &e, c->stream));
+    *err = e;
+    return NMFK_OK;
+}
+
+int32_t nmfk_umma_timing(nmfk_ctx* c, const float* U, const float* V, int32_t reps, int64_t* cycles8, float* acc) {
+    if (!c || !U || !V || !cycles8 || !acc) return fail(c, NMFK_E_INVALID, "nmfk_umma_timing: NULL argument");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, umma_timing(U, V, reps, reinterpret_cast<long long*>(cycles8), acc, c->stream));
     return NMFK_OK;
 }
 

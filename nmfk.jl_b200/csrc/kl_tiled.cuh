@@ -21,9 +21,12 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <cstdio>
+#include <type_traits>
 #include <vector>
 
 #include "kl_resident.cuh"  // load_row, warp_sum, block_sum, div_cold, VecOf
+#include "kl_tiled_args.h"
 
 namespace nmfk {
 
@@ -35,22 +38,6 @@ struct TiledCfg {
     static constexpr int TCH = sizeof(TX) == 8 ? 16 : 32;  // reduction indices per pipeline stage
 };
 
-struct TiledPassArgs {
-    const void* D;      // data in "own-contiguous" layout: element (o,t) at D[o + t*nown]
-    void* U;            // own factor stack
-    const void* V;      // broadcast factor stack
-    const void* den;    // R x 32 : sum_t V[t,a]
-    void* partial;      // slices x R x nown x K partial numerators (S > 1) or nullptr
-    const UnitState* st;
-    const void* ximp;   // R x n x m (X layout) or nullptr
-    long long u_rstride, v_rstride;  // elements between restarts
-    long long su_o, su_a, sv_t, sv_a;
-    int nown, nred, k, R, S, nblocks;
-    int transposed;     // 1: D is X^T (H-update) -> imputation index = t + o*ldimp
-    int ldimp;
-    int has_nan, first_iter;
-    double lambda;
-};
 
 template <typename TX, typename TC, int K, bool HASNAN>
 __global__ void __launch_bounds__(kTiledThreads, (K <= 12 ? 2 : 1)) tiled_pass_kernel(const TiledPassArgs a) {
@@ -541,6 +528,13 @@ cudaError_t launch_tiled_pass_k(const TiledPassArgs& a, void* red, cudaStream_t 
 }
 
 template <typename TX, typename TC, int K>
+cudaError_t launch_tiled_combine_k(const TiledPassArgs& a, void* red, cudaStream_t s) {
+    dim3 g((a.nown + 255) / 256, a.R);
+    tiled_combine_kernel<TC, K><<<g, 256, 0, s>>>(a, static_cast<TC*>(red));
+    return cudaGetLastError();
+}
+
+template <typename TX, typename TC, int K>
 cudaError_t launch_tiled_apply_k(const TiledPassArgs& a, void* red, cudaStream_t s) {
     dim3 g((a.nown + 255) / 256, a.R);
     tiled_apply_kernel<TC, K><<<g, 256, 0, s>>>(a, static_cast<const TC*>(red));
@@ -555,8 +549,19 @@ cudaError_t launch_tiled_apply_k(const TiledPassArgs& a, void* red, cudaStream_t
 namespace nmfk {
 
 template <typename TX, typename TC>
-cudaError_t dispatch_tiled_pass(const TiledPassArgs& a, void* red, cudaStream_t s) {
+cudaError_t dispatch_tiled_combine(const TiledPassArgs& a, void* red, cudaStream_t s) {
     const int kt = resident_template_k(a.k);
+    NMFK_DISPATCH_K(launch_tiled_combine_k, TX, TC, kt, a, red, s)
+}
+// use_tc: Float32 without NaN -> the tcgen05 kernel of kl_tiled_tc.cu (a.nblocks counts 128-index tiles)
+template <typename TX, typename TC>
+cudaError_t dispatch_tiled_pass(const TiledPassArgs& a, void* red, cudaStream_t s, bool use_tc, int* errflag) {
+    const int kt = resident_template_k(a.k);
+    if (use_tc) {
+        cudaError_t e = launch_tc_pass(a, errflag, s);
+        if (e != cudaSuccess || a.partial == nullptr) return e;
+        return dispatch_tiled_combine<TX, TC>(a, red, s);
+    }
     NMFK_DISPATCH_K(launch_tiled_pass_k, TX, TC, kt, a, red, s)
 }
 template <typename TX, typename TC>
@@ -586,13 +591,28 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int nblkH = (m + kTiledThreads - 1) / kTiledThreads;  // H-update: own = columns
-    const int nblkW = (n + kTiledThreads - 1) / kTiledThreads;  // W-update: own = rows
+    // Float32 without NaN: both half-updates run on the tensor cores (kl_tiled_tc.cu), 128 own indices per CTA and
+    // groups of restarts that share the X tiles; everything else (sums, combine, objective, check) is unchanged
+    bool use_tc = false;
+    if (std::is_same<TX, float>::value && std::is_same<TC, float>::value && a.tiled_tc && !a.has_nan) {
+        TiledPassArgs probe{};
+        probe.k = k;
+        probe.nown = m;
+        probe.D = a.Xt;
+        use_tc = tc_pass_supported(probe);
+        probe.nown = n;
+        probe.D = a.X;
+        use_tc = use_tc && tc_pass_supported(probe);
+    }
+    const int ownper = use_tc ? 128 : kTiledThreads;
+    const int units = use_tc ? (R + tc_pass_group(k) - 1) / tc_pass_group(k) : R;  // CTAs per own block and slice
+    const int nblkH = (m + ownper - 1) / ownper;  // H-update: own = columns
+    const int nblkW = (n + ownper - 1) / ownper;  // W-update: own = rows
     constexpr int TCH = TiledCfg<TX>::TCH;
     auto slices = [&](int nblk, int nred) {
-        const long long target = 4ll * sms;
-        long long S = (target + (long long)nblk * R - 1) / ((long long)nblk * R);
-        const long long smax = std::max(1, nred / (TCH * 8));
+        const long long target = (use_tc ? 3ll : 4ll) * sms;
+        long long S = (target + (long long)nblk * units - 1) / ((long long)nblk * units);
+        const long long smax = std::max(1, nred / ((use_tc ? 64 : TCH) * 8));
         if (S > smax) S = smax;
         if (S < 1) S = 1;
         return (int)S;
@@ -609,7 +629,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     TC* partial = nullptr;
     double* objp = nullptr;
     int* d_active = nullptr;
-    int* h_active = nullptr;
+    int* h_active = nullptr;  // [0] running restarts, [1] barrier time-out site reported by the tcgen05 kernel
     std::vector<UnitState> hst((size_t)R);
     int it = 0;
     bool any_running = false;
@@ -626,7 +646,8 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     if (psz) NMFK_TRY(cudaMalloc(&partial, psz * sizeof(TC)));
     NMFK_TRY(cudaMalloc(&objp, (size_t)R * nblkObj * 2 * sizeof(double)));
     NMFK_TRY(cudaMalloc(&d_active, sizeof(int)));
-    NMFK_TRY(cudaMallocHost(&h_active, sizeof(int)));
+    NMFK_TRY(cudaMallocHost(&h_active, 2 * sizeof(int)));
+    h_active[1] = 0;
     NMFK_TRY(cudaMemcpyAsync(hst.data(), a.st, (size_t)R * sizeof(UnitState), cudaMemcpyDeviceToHost, s));
     NMFK_TRY(cudaStreamSynchronize(s));
     for (auto& u : hst)
@@ -660,6 +681,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
         ph.ldimp = n;
         ph.has_nan = a.has_nan;
         ph.lambda = a.lambda;
+        ph.ktmpl = kt;
         pw = ph;
         pw.D = a.X;
         pw.U = a.W;
@@ -702,7 +724,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
             if (!a.Hfixed) {
                 tiled_sums_kernel<TC><<<dim3(k, R), 256, 0, s>>>(a.W, (long long)n * k, 1, n, n, a.st, den);
                 NMFK_TRY(cudaGetLastError());
-                NMFK_TRY((dispatch_tiled_pass<TX, TC>(ph, red, s)));
+                NMFK_TRY((dispatch_tiled_pass<TX, TC>(ph, red, s, use_tc, h_active + 1)));
                 *launches += 2 + (SH > 1 || sharded);
                 if (sharded) {
                     // colsum(W) and W' * (X ./ (W*H)) over this rank's rows -> sums over all rows, then the update
@@ -714,7 +736,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
             if (!a.Wfixed) {
                 tiled_sums_kernel<TC><<<dim3(k, R), 256, 0, s>>>(a.H, (long long)k * m, k, 1, m, a.st, den);
                 NMFK_TRY(cudaGetLastError());
-                NMFK_TRY((dispatch_tiled_pass<TX, TC>(pw, nullptr, s)));
+                NMFK_TRY((dispatch_tiled_pass<TX, TC>(pw, nullptr, s, use_tc, h_active + 1)));
                 *launches += 2 + (SW > 1);
             }
             if (a.has_nan) {
@@ -778,6 +800,8 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
         NMFK_TRY(cudaStreamSynchronize(s));
     }
 done:
+    if (h_active && h_active[1] != 0)
+        fprintf(stderr, "[nmfk] tc_pass_kernel: barrier time-out at site %d (protocol error)\n", h_active[1]);
     if (den) cudaFree(den);
     if (partial) cudaFree(partial);
     if (objp) cudaFree(objp);

@@ -1,0 +1,32 @@
+// Arguments of one half-update launch of the tiled KL engine (kl_tiled.cuh, kl_tiled_tc.cu).
+#pragma once
+#include "nmfk_internal.h"
+
+namespace nmfk {
+
+struct TiledPassArgs {
+    const void* D;      // data in "own-contiguous" layout: element (o,t) at D[o + t*nown]
+    void* U;            // own factor stack
+    const void* V;      // broadcast factor stack
+    const void* den;    // R x 32 : sum_t V[t,a]
+    void* partial;      // slices x R x nown x K partial numerators (S > 1) or nullptr
+    const UnitState* st;
+    const void* ximp;   // R x n x m (X layout) or nullptr
+    long long u_rstride, v_rstride;  // elements between restarts
+    long long su_o, su_a, sv_t, sv_a;
+    int nown, nred, k, R, S, nblocks;
+    int transposed;     // 1: D is X^T (H-update) -> imputation index = t + o*ldimp
+    int ldimp;
+    int has_nan, first_iter;
+    double lambda;
+    int ktmpl;          // column stride of `partial` (the template K of the combine kernel)
+};
+
+// Float32 half-update on the 5th-generation tensor cores (kl_tiled_tc.cu): tcgen05.mma kind::tf32 with the
+// 3-term split, accumulators / quotient tiles in tensor memory.  nblocks = ceil(nown / 128), grid =
+// S x nblocks x ceil(R / tc_pass_group(k)).
+bool tc_pass_supported(const TiledPassArgs& a);
+int tc_pass_group(int k);  // restarts that share one X tile inside a CTA
+cudaError_t launch_tc_pass(const TiledPassArgs& a, int* d_errflag, cudaStream_t s);
+
+}  // namespace nmfk

@@ -112,6 +112,37 @@ __global__ void __launch_bounds__(256) op_peak_kernel(double* out, int iters, do
     if (s == -1.2345) out[0] = s;
 }
 
+// legacy tensor path for Float32 data: mma.sync m16n8k8 TF32 (the 3xTF32 split of the tiled f32 engine)
+// and m16n8k16 BF16 for comparison; 4 independent accumulator sets per warp
+template <int MODE>
+__global__ void __launch_bounds__(256) hmma_peak_kernel(float* out, int iters, unsigned a, unsigned b) {
+    float c[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[q][e] = 0.f;
+    const unsigned a0 = a + threadIdx.x, a1 = a, a2 = a ^ 1u, a3 = a, b0 = b, b1 = b ^ 3u;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (MODE == 0)
+                asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(c[q][0]), "+f"(c[q][1]), "+f"(c[q][2]), "+f"(c[q][3])
+                             : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+            else
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(c[q][0]), "+f"(c[q][1]), "+f"(c[q][2]), "+f"(c[q][3])
+                             : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s += c[q][e];
+    if (s == -1.2345f) out[0] = s;
+}
+
 __global__ void copy_kernel(const double4* __restrict__ src, double4* __restrict__ dst, long long n4) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
         dst[i] = src[i];
@@ -231,6 +262,20 @@ cudaError_t measure_peak(int which, double* value, cudaStream_t s) {
             const double per_smsp = 8.0 * iters * (double)blocks * (threads / 32) / (sms * 4.0);
             *value = (ms * 1e-3) * (double)khz * 1e3 / per_smsp;
         }
+        return cudaSuccess;
+    }
+    if (which == 11 || which == 12) {  // mma.sync TF32 m16n8k8 / BF16 m16n8k16 -> TFLOP/s
+        float* out = nullptr;
+        if ((e = cudaMalloc(&out, 64)) != cudaSuccess) return e;
+        const int blocks = sms * 8, threads = 256, iters = 4096;
+        if (which == 11)
+            e = time_best([&] { hmma_peak_kernel<0><<<blocks, threads, 0, s>>>(out, iters, 0x3f800000u, 0x3f000000u); }, 5, &ms, s);
+        else
+            e = time_best([&] { hmma_peak_kernel<1><<<blocks, threads, 0, s>>>(out, iters, 0x3f803f80u, 0x3f003f00u); }, 5, &ms, s);
+        cudaFree(out);
+        if (e != cudaSuccess) return e;
+        const double flops = (which == 11 ? 2048.0 : 4096.0) * 4.0 * iters * (double)blocks * (threads / 32);
+        *value = flops / (ms * 1e-3) / 1e12;
         return cudaSuccess;
     }
     return cudaErrorInvalidValue;

@@ -47,6 +47,7 @@ struct SolveArgs {
     int32_t SH, SW;   // DMMA resident engine: slices of the reduction range per half-update (host heuristic)
     int32_t maxiter, maxbad, maxre, stopconv, check_every, Wfixed, Hfixed, normalize, iter_limit;
     double lambda, tol, tolOF, eps_clamp, weight;
+    int32_t tiled_tc;        // tiled engine, Float32 without NaN: 1 = tcgen05 kernel (kl_tiled_tc.cu), 0 = scalar-FMA kernel
     const ShardComm* shard;  // non-null: n is the LOCAL row count, the tiled engine all-reduces the k x m partials
 };
 
@@ -116,5 +117,9 @@ cudaError_t launch_zero_nan(void* p, long long len, int dtype, cudaStream_t s);
 
 // micro-benchmarks
 cudaError_t measure_peak(int which, double* value, cudaStream_t s);
+// tcgen05 building-block self-test (tc_selftest.cu)
+cudaError_t umma_timing(const float* U, const float* V, int reps, long long* out8, float* bias, cudaStream_t s);
+cudaError_t umma_selftest(const float* U, const float* V, int mode, float* Pss, float* Pts, float* ACCa, float* ACCb, int* err,
+                          cudaStream_t s);
 
 }  // namespace nmfk

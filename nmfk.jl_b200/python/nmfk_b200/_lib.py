@@ -75,6 +75,8 @@ SIGNATURES = {
     "nmfk_launch_count": (_i64, [_P]),
     "nmfk_last_solve_ms": (_dbl, [_P]),
     "nmfk_measure_peak": (_i32, [_P, _i32, _pdbl]),
+    "nmfk_umma_timing": (_i32, [_P, _P, _P, _i32, _P, _P]),
+    "nmfk_umma_selftest": (_i32, [_P, _P, _P, _i32, _P, _P, _P, _P, _pi32]),
     "nmfk_philox_host": (_i32, [_u64, _i64, _pdbl]),
 }
 

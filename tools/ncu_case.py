@@ -1,5 +1,5 @@
 """Short, fixed-iteration cases for ncu captures (one kernel launch each).
-usage: ncu_case.py resident K [R] | tiled"""
+usage: ncu_case.py resident K [R] | tiled | tc n m k R"""
 import os
 import sys
 
@@ -19,6 +19,13 @@ with nb.Context(0) as ctx:
         b.init_random(2015)
         ctx.solve([b], nb.default_params(maxiter=30))
         print("resident k=%d R=%d ms=%.3f" % (k, R, ctx.last_solve_ms))
+    elif mode == "tc":  # tcgen05 Float32 tiled pass: tc n m k R
+        n, m, k, R = (int(v) for v in sys.argv[2:6])
+        ctx.set_X(synth.mixture(n, m, 8, seed=3, dtype=np.float32))
+        b = ctx.batch(k, R)
+        b.init_random(1)
+        ctx.solve([b], nb.default_params(maxiter=2, engine=2))
+        print("tc tiled ms=%.3f" % ctx.last_solve_ms)
     else:
         ctx.set_X(synth.mixture(20000, 1000, 8, seed=3))
         b = ctx.batch(16, 16)
