@@ -12,10 +12,10 @@
 //   quot.  Q = X_tile ./ P  in registers (tcgen05.ld, MUFU.RCP, tcgen05.st), split Q = Qhi + Qlo (TF32 + rest)
 //   MMA#2  ACC_r[128 x k] += Q[128 x 64] V_r[64 x k]      A = Q (hi, lo) in tensor memory, B = V chunk in smem
 // Both products use the 3-term TF32 split (hi*hi + lo*hi + hi*lo, FP32 accumulation; never plain TF32).
-// Warp roles (384 threads): warp 0 = bulk-copy producer of X tiles (cp.async.bulk + mbarrier transaction
-// counts, 3 stages), warp 1 = tcgen05.mma issuer, warps 2-3 = V stagers (global -> hi/lo split -> the two
-// canonical un-swizzled K-major images MMA#1 and MMA#2 read), warps 4-11 = quotient warps (lane quarter =
-// warp % 4, column half = (warp - 4) / 4).  P/Q tiles are double-buffered in tensor memory so the tensor pipe
+// Warp roles (704 threads): warp 0 = bulk-copy producer of X tiles (cp.async.bulk + mbarrier transaction
+// counts, 3 stages), warp 1 = tcgen05.mma issuer (elect.sync regions), warps 2-5 = V stagers (cp.async two units
+// ahead -> hi/lo split -> the two canonical un-swizzled K-major images MMA#1 and MMA#2 read), warps 6-21 =
+// quotient warps (lane quarter = warp % 4, 16 of the 64 columns each).  P/Q tiles are double-buffered in tensor memory so the tensor pipe
 // works on unit u+1 / u+2 while the quotient warps divide unit u.
 // tcgen05.mma accumulates with round-toward-zero (measured: -0.47 ulp per chained instruction, tools/umma_selftest.py
 // --timing), so numerators are NOT chained across units: MMA#2 of every unit starts a fresh tensor-memory
@@ -31,8 +31,12 @@
 namespace nmfk {
 namespace {
 
-constexpr int TC_M = 128, TC_TS = 64, TC_THREADS = 384;
-constexpr int TC_NXS = 3, TC_NVB = 3;
+constexpr int TC_M = 128, TC_TS = 64;
+constexpr int TC_QWARPS = 16;                       // quotient warps: lane quarter = warp % 4, 16 columns each
+constexpr int TC_SWARPS = 4;                        // V stager warps
+constexpr int TC_QW0 = 2 + TC_SWARPS;               // first quotient warp
+constexpr int TC_THREADS = (TC_QW0 + TC_QWARPS) * 32;
+constexpr int TC_NXS = 3, TC_NVB = 3, TC_NRAW = 4;
 constexpr uint32_t TC_LBO = 128;
 
 template <int K8, int N2>
@@ -41,15 +45,20 @@ struct TcCfg {
     static constexpr int ACOLS = NST * N2;                            // columns of one per-unit numerator buffer
     static constexpr int ABASE = 256, UBASE = 256 + 2 * ACOLS;        // tensor-memory columns
     static constexpr int PERB = 2 * K8;                               // U hi | U lo per restart
+    static constexpr int NCQ = N2 / 4;                                // numerator columns per quotient thread
     static constexpr int RBT = (512 - UBASE) / PERB;
-    static constexpr int RB = RBT < 4 ? RBT : 4;                      // restarts per CTA (they share the X tiles)
+    static constexpr int RBR = 16 / NCQ;                              // 16 accumulator registers per quotient thread
+    static constexpr int RB = RBT < RBR ? RBT : RBR;                  // restarts per CTA (they share the X tiles)
     static constexpr uint32_t SBO1 = (K8 / 4) * 128;                  // MMA#1 B: rows = steps, K extent = K8
     static constexpr uint32_t SBO2 = (TC_TS / 4) * 128;               // MMA#2 B: rows = columns a, K extent = TS
     static constexpr uint32_t B1_BYTES = TC_TS * K8 * 4;
     static constexpr uint32_t B2_BYTES = N2 * TC_TS * 4;
     static constexpr uint32_t V_BYTES = 2 * B1_BYTES + 2 * B2_BYTES;  // B1 hi | B1 lo | B2 hi | B2 lo
     static constexpr uint32_t X_BYTES = TC_TS * TC_M * 4;
-    static constexpr size_t SMEM = (size_t)TC_NXS * X_BYTES + (size_t)TC_NVB * V_BYTES + 32 * 8 + 64;
+    static constexpr uint32_t RAW_BYTES = TC_TS * K8 * 4;             // un-split V chunk [step][column]
+    static constexpr size_t SMEM =
+        (size_t)TC_NXS * X_BYTES + (size_t)TC_NVB * V_BYTES + (size_t)TC_NRAW * RAW_BYTES + 32 * 8 + 64;
+    static_assert(RB >= 1 && RB <= 4, "restart group");
 };
 
 __device__ __forceinline__ float rcp_fast(float p) {
@@ -62,11 +71,12 @@ template <int K8, int N2>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassArgs a, int* errflag) {
     using C = TcCfg<K8, N2>;
     constexpr int RB = C::RB;
-    constexpr int NC = N2 / 2;  // numerator columns per quotient thread (the two column-half warps split them)
+    constexpr int NC = C::NCQ;
     extern __shared__ __align__(1024) unsigned char smem[];
     float* Xs = reinterpret_cast<float*>(smem);                         // [NXS][TS][M]
     unsigned char* Vs = smem + (size_t)TC_NXS * C::X_BYTES;              // [NVB][V_BYTES]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + (size_t)TC_NVB * C::V_BYTES);
+    float* Raw = reinterpret_cast<float*>(Vs + (size_t)TC_NVB * C::V_BYTES);  // [NRAW][TS][K8]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(Raw) + (size_t)TC_NRAW * C::RAW_BYTES);
     uint64_t* x_full = bars;                 // [NXS]  X tile landed (bulk-copy transaction count)
     uint64_t* x_empty = x_full + TC_NXS;     // [NXS]  quotient warps are done with the tile
     uint64_t* v_full = x_empty + TC_NXS;     // [NVB]  V images staged
@@ -85,8 +95,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
     const int slice = rest / a.nblocks;
     const int o0 = ob * TC_M;
     const int k = a.k;
-    const int t_begin = (int)(((long long)a.nred * slice) / a.S);
-    const int t_end = (int)(((long long)a.nred * (slice + 1)) / a.S);
+    // slices are whole chunks: every chunk starts at a multiple of 64 steps (16-byte aligned V rows)
+    const int chunks_all = (a.nred + TC_TS - 1) / TC_TS;
+    const int t_begin = (int)(((long long)chunks_all * slice) / a.S) * TC_TS;
+    const int t_end = min(a.nred, (int)(((long long)chunks_all * (slice + 1)) / a.S) * TC_TS);
     const int nchunks = (t_end - t_begin + TC_TS - 1) / TC_TS;
 
     if (tid == 0) {
@@ -106,15 +118,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
     if (tid == 32) {
         for (int i = 0; i < TC_NXS; ++i) {
             tc::mbar_init(&x_full[i], 1);
-            tc::mbar_init(&x_empty[i], 8);
+            tc::mbar_init(&x_empty[i], TC_QWARPS);
         }
         for (int i = 0; i < TC_NVB; ++i) {
-            tc::mbar_init(&v_full[i], 2);
+            tc::mbar_init(&v_full[i], TC_SWARPS);
             tc::mbar_init(&v_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&p_full[i], 1);
-            tc::mbar_init(&q_full[i], 8);
+            tc::mbar_init(&q_full[i], TC_QWARPS);
             tc::mbar_init(&a_full[i], 1);
         }
         tc::mbar_fence_init();
@@ -134,27 +146,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
     const float* Vg = static_cast<const float*>(a.V);
     float* Ug = static_cast<float*>(a.U);
 
-    // own factor rows -> tensor memory (A operand of MMA#1), split hi / lo; quotient warps, restart b by column half.
-    // Own indices past the edge get U = 1 (finite P, their X is 0, their rows are never stored).
-    if (warp >= 4) {
-        const int lq = warp & 3, ch = (warp - 4) >> 2;
+    // own factor rows -> tensor memory (A operand of MMA#1), split hi / lo: quotient warp group cs loads restart
+    // slot cs.  Own indices past the edge get U = 1 (finite P; their X is 0 and their rows are never stored).
+    if (warp >= TC_QW0) {
+        const int lq = warp & 3, cs = (warp - TC_QW0) >> 2;
         const int o = o0 + lq * 32 + lane;
         const bool valid = o < a.nown;
         const uint32_t lane_base = tbase + ((uint32_t)(lq * 32) << 16);
-        for (int b = ch; b < nact; b += 2) {
-            const float* U = Ug + (long long)s_act[b] * a.u_rstride;
-            uint32_t hi[K8], lo[K8];
+        if (cs < nact) {
+            const float* U = Ug + (long long)s_act[cs] * a.u_rstride;
+            const uint32_t col = C::UBASE + cs * C::PERB;
 #pragma unroll
-            for (int c = 0; c < K8; ++c) {
-                const float u = !valid ? 1.f : (c < k ? U[(long long)o * a.su_o + (long long)c * a.su_a] : 0.f);
-                hi[c] = __float_as_uint(u) & 0xffffe000u;
-                lo[c] = __float_as_uint(u - __uint_as_float(hi[c]));
-            }
-            const uint32_t col = C::UBASE + b * C::PERB;
+            for (int c0 = 0; c0 < K8; c0 += 8) {
+                uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int c = 0; c < K8; c += 8) {
-                tc::tmem_st8(lane_base + col + c, hi + c);
-                tc::tmem_st8(lane_base + col + K8 + c, lo + c);
+                for (int c = 0; c < 8; ++c) {
+                    const float u = !valid ? 1.f : (c0 + c < k ? U[(long long)o * a.su_o + (long long)(c0 + c) * a.su_a] : 0.f);
+                    hi[c] = __float_as_uint(u) & 0xffffe000u;
+                    lo[c] = __float_as_uint(u - __uint_as_float(hi[c]));
+                }
+                tc::tmem_st8(lane_base + col + c0, hi);
+                tc::tmem_st8(lane_base + col + K8 + c0, lo);
             }
         }
         tc::tmem_wait_st();
@@ -164,24 +176,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
     tc::tc_fence_after_sync();
 
     if (warp == 0) {
-        // ===== X producer: one bulk copy per step row (128 consecutive own indices = 512 bytes) =====
-        if (lane == 0) {
+        // ===== X producer: one bulk copy per step row (128 consecutive own indices = 512 bytes).  The whole warp runs
+        // the loop; the copies are issued from an elect.sync region (single thread, uniform registers) =====
+        {
             const uint32_t row_bytes = (uint32_t)min(TC_M, a.nown - o0) * 4u;
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c % TC_NXS;
                 if (c >= TC_NXS) tc::mbar_wait(&x_empty[s], (uint32_t)((c / TC_NXS - 1) & 1), errflag, 10);
                 const int t0 = t_begin + c * TC_TS;
                 const int cnt = min(TC_TS, t_end - t0);
-                tc::mbar_arrive_expect_tx(&x_full[s], (uint32_t)cnt * row_bytes);
-                float* dst = Xs + (size_t)s * TC_TS * TC_M;
-                const float* src = D + (long long)o0 + (long long)t0 * a.nown;
-                for (int j = 0; j < cnt; ++j) tc::bulk_g2s(dst + j * TC_M, src + (long long)j * a.nown, row_bytes, &x_full[s]);
+                if (tc::elect_one()) {
+                    tc::mbar_arrive_expect_tx(&x_full[s], (uint32_t)cnt * row_bytes);
+                    float* dst = Xs + (size_t)s * TC_TS * TC_M;
+                    const float* src = D + (long long)o0 + (long long)t0 * a.nown;
+                    for (int j = 0; j < cnt; ++j) tc::bulk_g2s(dst + j * TC_M, src + (long long)j * a.nown, row_bytes, &x_full[s]);
+                }
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread); descriptors are built once, the unrolled issue loops only add constants =====
-        if (lane == 0) {
+        // ===== MMA issuer: the whole warp runs the (warp-uniform) control flow, lane 0 issues; descriptors are built once,
+        // the unrolled issue loops only add constants =====
+        {
             constexpr uint32_t idP = tc::idesc_tf32(TC_M, TC_TS, 0);
             constexpr uint32_t idA1 = tc::idesc_tf32(TC_M, C::ACOLS, 0);  // Qhi * [Vhi ; Vlo] (or Qhi * Vhi when not stacked)
             constexpr uint32_t idA2 = tc::idesc_tf32(TC_M, N2, 0);
@@ -196,6 +212,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
                 const uint32_t d = tbase + (uint32_t)(u & 1) * 128;
                 const uint32_t uh = tbase + C::UBASE + b * C::PERB, ul = uh + K8;
                 const uint64_t bh = d1 + (uint64_t)((vb * C::V_BYTES) >> 4), bl = bh + (C::B1_BYTES >> 4);
+                if (tc::elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < K8 / 8; ++ks) {
                     tc::mma_tf32_ts(d, ul + ks * 8, bh + ks * KSTEP, idP, ks > 0);
@@ -203,6 +220,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
                     tc::mma_tf32_ts(d, uh + ks * 8, bh + ks * KSTEP, idP, 1);
                 }
                 tc::mma_commit(&p_full[u & 1]);
+                }
+                __syncwarp();
             };
             auto mma2 = [&](int u) {
                 const int vb = u % TC_NVB;
@@ -211,6 +230,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
                 const uint32_t d = tbase + C::ABASE + (uint32_t)(u & 1) * C::ACOLS;
                 const uint32_t qh = tbase + (uint32_t)(u & 1) * 128, ql = qh + 64;
                 const uint64_t bh = d2 + (uint64_t)((vb * C::V_BYTES) >> 4), bl = bh + (C::B2_BYTES >> 4);
+                if (tc::elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < TC_TS / 8; ++ks) tc::mma_tf32_ts(d, qh + ks * 8, bh + ks * KSTEP, idA1, ks > 0);
                 if (C::NST == 1) {
@@ -221,9 +241,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
                 for (int ks = 0; ks < TC_TS / 8; ++ks) tc::mma_tf32_ts(d, ql + ks * 8, bh + ks * KSTEP, idA2, 1);
                 tc::mma_commit(&v_empty[vb]);
                 tc::mma_commit(&a_full[u & 1]);
+                }
+                __syncwarp();
             };
             // unit u = c * nact + b; MMA#1 runs two units ahead of MMA#2
-            int b1 = 0;  // restart index of the next MMA#1
+            int b1 = 0;  // restart slot of the next MMA#1
             auto next_b = [&](int b) { return b + 1 == nact ? 0 : b + 1; };
             mma1(0, b1);
             b1 = next_b(b1);
@@ -240,100 +262,147 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
             }
         }
         __syncwarp();
-    } else if (warp < 4) {
-        // ===== V stagers: 4 x 4 blocks (4 steps x 4 columns) of the unit's V chunk, software-prefetched =====
+    } else if (warp < TC_QW0) {
+        // ===== V stagers (128 threads): cp.async the raw chunk two units ahead (16 bytes at a time along whichever index is
+        // contiguous in global memory), then split hi / lo into the two images.  Work item = half a 4 x 4 block. =====
+        constexpr int NS = TC_SWARPS * 32;
         const int sid = tid - 64;
-        constexpr int NBLK = 16 * (K8 / 4);
-        constexpr int NPT = (NBLK + 63) / 64;
-        float cur[NPT][16], nxt[NPT][16];
-        auto load = [&](int c, int b, float (&dst)[NPT][16]) {
+        const bool t_major = a.sv_t == 1;  // raw layout [column][step] (H-update: V = W) instead of [step][column]
+        const bool vec16 = t_major ? ((a.sv_a & 3) == 0 && (a.v_rstride & 3) == 0)
+                                   : (a.sv_a == 1 && (k & 3) == 0 && (a.sv_t & 3) == 0 && (a.v_rstride & 3) == 0);
+        auto issue_raw = [&](int c, int b, int stage) {
             const float* V = Vg + (long long)s_act[b] * a.v_rstride;
             const int t0 = t_begin + c * TC_TS;
-#pragma unroll
-            for (int q = 0; q < NPT; ++q) {
-                const int blk = sid + q * 64;
-                const int tb = blk & 15, ab = blk >> 4;
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int t = t0 + tb * 4 + i, col = ab * 4 + j;
-                        dst[q][i * 4 + j] =
-                            (blk < NBLK && t < t_end && col < k) ? __ldg(V + (long long)t * a.sv_t + (long long)col * a.sv_a) : 0.f;
+            float* dst = Raw + (size_t)stage * TC_TS * K8;
+            if (vec16 && t_major) {
+                for (int e = sid; e < K8 * (TC_TS / 4); e += NS) {
+                    const int col = e / (TC_TS / 4), t4 = (e % (TC_TS / 4)) * 4;
+                    const bool live = (t0 + t4 < t_end) && (col < k);
+                    tc::cp_async16_zfill(dst + col * TC_TS + t4, live ? V + (long long)(t0 + t4) + (long long)col * a.sv_a : V, live ? 16u : 0u);
+                }
+            } else if (vec16) {
+                for (int e = sid; e < TC_TS * (K8 / 4); e += NS) {
+                    const int tl = e / (K8 / 4), a4 = (e % (K8 / 4)) * 4;
+                    const bool live = (t0 + tl < t_end) && (a4 < k);
+                    tc::cp_async16_zfill(dst + tl * K8 + a4, live ? V + (long long)(t0 + tl) * a.sv_t + a4 : V, live ? 16u : 0u);
+                }
+            } else {
+                for (int e = sid; e < TC_TS * K8; e += NS) {
+                    int tl, col;
+                    if (t_major) {
+                        tl = e % TC_TS;
+                        col = e / TC_TS;
+                    } else {
+                        col = e % K8;
+                        tl = e / K8;
                     }
+                    const bool live = (t0 + tl < t_end) && (col < k);
+                    tc::cp_async4_zfill(dst + (t_major ? col * TC_TS + tl : tl * K8 + col),
+                                        live ? V + (long long)(t0 + tl) * a.sv_t + (long long)col * a.sv_a : V, live ? 4u : 0u);
+                }
             }
         };
-        load(0, 0, cur);
-        int cn = 0, bn = 0;  // (chunk, restart) of unit u + 1
-        for (int u = 0; u < total; ++u) {
-            if (++bn == nact) {
-                bn = 0;
-                ++cn;
+        int ci = 0, bi = 0;  // (chunk, restart slot) of the next unit to issue
+        auto advance = [&]() {
+            if (++bi == nact) {
+                bi = 0;
+                ++ci;
             }
-            if (u + 1 < total) load(cn, bn, nxt);
+        };
+        issue_raw(ci, bi, 0);
+        advance();
+        tc::cp_async_commit();
+        if (total > 1) {
+            issue_raw(ci, bi, 1);
+            advance();
+        }
+        tc::cp_async_commit();
+        for (int u = 0; u < total; ++u) {
+            if (u + 2 < total) {
+                issue_raw(ci, bi, (u + 2) % TC_NRAW);
+                advance();
+            }
+            tc::cp_async_commit();
+            tc::cp_async_wait<2>();           // this thread's copies of unit u have landed
+            tc::named_bar_sync(1, NS);        // ... and everybody else's
             const int vb = u % TC_NVB;
             if (u >= TC_NVB) tc::mbar_wait(&v_empty[vb], (uint32_t)((u / TC_NVB - 1) & 1), errflag, 30);
             unsigned char* base = Vs + (size_t)vb * C::V_BYTES;
+            const float* raw = Raw + (size_t)(u % TC_NRAW) * TC_TS * K8;
+            for (int it = sid; it < 2 * 16 * (K8 / 4); it += NS) {
+                const int hf = it & 1, tb = (it >> 1) & 15, ab = it >> 5;  // steps 4 tb + 2 hf + {0,1}, columns 4 ab + {0..3}
+                float v[2][4];
+                if (t_major) {
 #pragma unroll
-            for (int q = 0; q < NPT; ++q) {
-                const int blk = sid + q * 64;
-                if (blk < NBLK) {
-                    const int tb = blk & 15, ab = blk >> 4;
-                    float h[16], l[16];
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 w = *reinterpret_cast<const float2*>(raw + (ab * 4 + j) * TC_TS + tb * 4 + hf * 2);
+                        v[0][j] = w.x;
+                        v[1][j] = w.y;
+                    }
+                } else {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        h[e] = __uint_as_float(__float_as_uint(cur[q][e]) & 0xffffe000u);
-                        l[e] = cur[q][e] - h[e];
+                    for (int i = 0; i < 2; ++i) {
+                        const float4 w = *reinterpret_cast<const float4*>(raw + (tb * 4 + hf * 2 + i) * K8 + ab * 4);
+                        v[i][0] = w.x;
+                        v[i][1] = w.y;
+                        v[i][2] = w.z;
+                        v[i][3] = w.w;
+                    }
+                }
+                float h[2][4], l[2][4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        h[i][j] = __uint_as_float(__float_as_uint(v[i][j]) & 0xffffe000u);
+                        l[i][j] = v[i][j] - h[i][j];
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {  // MMA#1 image: row = step, 16 bytes = 4 columns
-                        const int t = tb * 4 + i;
-                        const uint32_t off = (t & 7) * 16 + (t >> 3) * C::SBO1 + ab * TC_LBO;
-                        *reinterpret_cast<float4*>(base + off) = make_float4(h[i * 4], h[i * 4 + 1], h[i * 4 + 2], h[i * 4 + 3]);
-                        *reinterpret_cast<float4*>(base + C::B1_BYTES + off) =
-                            make_float4(l[i * 4], l[i * 4 + 1], l[i * 4 + 2], l[i * 4 + 3]);
-                    }
+                for (int i = 0; i < 2; ++i) {  // MMA#1 image: row = step, 16 bytes = 4 columns
+                    const int t = tb * 4 + hf * 2 + i;
+                    const uint32_t off = (t & 7) * 16 + (t >> 3) * C::SBO1 + ab * TC_LBO;
+                    *reinterpret_cast<float4*>(base + off) = make_float4(h[i][0], h[i][1], h[i][2], h[i][3]);
+                    *reinterpret_cast<float4*>(base + C::B1_BYTES + off) = make_float4(l[i][0], l[i][1], l[i][2], l[i][3]);
+                }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {  // MMA#2 image: row = column a, 16 bytes = 4 steps
-                        const int col = ab * 4 + j;
-                        const uint32_t off = 2 * C::B1_BYTES + (col & 7) * 16 + (col >> 3) * C::SBO2 + tb * TC_LBO;
-                        *reinterpret_cast<float4*>(base + off) = make_float4(h[j], h[4 + j], h[8 + j], h[12 + j]);
-                        *reinterpret_cast<float4*>(base + C::B2_BYTES + off) = make_float4(l[j], l[4 + j], l[8 + j], l[12 + j]);
-                    }
+                for (int j = 0; j < 4; ++j) {  // MMA#2 image: row = column a, 16 bytes = 4 steps (this item: 2 of them)
+                    const int col = ab * 4 + j;
+                    const uint32_t off = 2 * C::B1_BYTES + (col & 7) * 16 + (col >> 3) * C::SBO2 + tb * TC_LBO + hf * 8;
+                    *reinterpret_cast<float2*>(base + off) = make_float2(h[0][j], h[1][j]);
+                    *reinterpret_cast<float2*>(base + C::B2_BYTES + off) = make_float2(l[0][j], l[1][j]);
                 }
             }
             tc::fence_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&v_full[vb]);
-#pragma unroll
-            for (int q = 0; q < NPT; ++q)
-#pragma unroll
-                for (int e = 0; e < 16; ++e) cur[q][e] = nxt[q][e];
         }
+        tc::cp_async_wait<0>();
         __syncwarp();
     } else {
-        // ===== quotient warps =====
-        const int lq = warp & 3, ch = (warp - 4) >> 2;
+        // ===== quotient warps: 128 lanes x 16 columns each =====
+        const int lq = warp & 3, cs = (warp - TC_QW0) >> 2;
         const int o_loc = lq * 32 + lane;
         const int o = o0 + o_loc;
         const bool valid = o < a.nown;
         const uint32_t lane_base = tbase + ((uint32_t)(lq * 32) << 16);
-        const int j0 = ch * 32;
+        const int j0 = cs * 16;
         float acc[RB][NC];
 #pragma unroll
         for (int b = 0; b < RB; ++b)
 #pragma unroll
             for (int c = 0; c < NC; ++c) acc[b][c] = 0.f;
-        // numerators of unit uu (restart slot bb, compile-time) -> registers, round-to-nearest adds
+        // numerators of unit uu -> registers of restart slot `target`, round-to-nearest adds
         auto drain = [&](int uu, int target) {
             tc::mbar_wait(&a_full[uu & 1], (uint32_t)((uu >> 1) & 1), errflag, 43);
             tc::tc_fence_after_sync();
-            const uint32_t col = lane_base + C::ABASE + (uint32_t)(uu & 1) * C::ACOLS + ch * NC;
+            const uint32_t col = lane_base + C::ABASE + (uint32_t)(uu & 1) * C::ACOLS + cs * NC;
             uint32_t v0[NC], v1[NC];
-#pragma unroll
-            for (int c = 0; c < NC; c += 8) {
-                tc::tmem_ld8(col + c, v0 + c);
-                if (C::NST == 2) tc::tmem_ld8(col + N2 + c, v1 + c);
+            if (NC == 4) {
+                tc::tmem_ld4(col, v0);
+                if (C::NST == 2) tc::tmem_ld4(col + N2, v1);
+            } else {
+                tc::tmem_ld8(col, v0);
+                if (C::NST == 2) tc::tmem_ld8(col + N2, v1);
             }
             tc::tmem_wait_ld();
 #pragma unroll
@@ -353,52 +422,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
             const int cnt = min(TC_TS, t_end - (t_begin + c * TC_TS));
             tc::mbar_wait(&x_full[s], (uint32_t)((c / TC_NXS) & 1), errflag, 40);
             const float* xs = Xs + (size_t)s * TC_TS * TC_M + (size_t)j0 * TC_M + o_loc;
+            for (int b = 0; b < nact; ++b, ++u) {
+                const uint32_t col = lane_base + (uint32_t)(u & 1) * 128 + j0;
+                tc::mbar_wait(&p_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 41);
+                tc::tc_fence_after_sync();
+                uint32_t p[16], lo[16];
+                tc::tmem_ld16(col, p);
+                tc::tmem_wait_ld();
+                if (cnt == TC_TS) {
 #pragma unroll
-            for (int b = 0; b < RB; ++b) {
-                if (b < nact) {
-                    const uint32_t col = lane_base + (uint32_t)(u & 1) * 128 + j0;
-                    tc::mbar_wait(&p_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 41);
-                    tc::tc_fence_after_sync();
-                    uint32_t p[32];
-                    tc::tmem_ld32(col, p);
-                    tc::tmem_wait_ld();
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        uint32_t lo[16];
-                        if (cnt == TC_TS) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const int jj = half * 16 + j;
-                                const float q = xs[jj * TC_M] * rcp_fast(__uint_as_float(p[jj]));
-                                const uint32_t h = __float_as_uint(q) & 0xffffe000u;
-                                lo[j] = __float_as_uint(q - __uint_as_float(h));
-                                p[jj] = h;
-                            }
-                        } else {  // last chunk of the slice: steps past the end contribute nothing
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const int jj = half * 16 + j;
-                                float q = xs[jj * TC_M] * rcp_fast(__uint_as_float(p[jj]));
-                                q = (j0 + jj < cnt) ? q : 0.f;
-                                const uint32_t h = __float_as_uint(q) & 0xffffe000u;
-                                lo[j] = __float_as_uint(q - __uint_as_float(h));
-                                p[jj] = h;
-                            }
-                        }
-                        tc::tmem_st16(col + 64 + half * 16, lo);
+                    for (int j = 0; j < 16; ++j) {
+                        const float q = xs[j * TC_M] * rcp_fast(__uint_as_float(p[j]));
+                        const uint32_t h = __float_as_uint(q) & 0xffffe000u;
+                        lo[j] = __float_as_uint(q - __uint_as_float(h));
+                        p[j] = h;
                     }
-                    tc::tmem_st32(col, p);
-                    tc::tmem_wait_st();
-                    tc::tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&q_full[u & 1]);
-                    // drain the numerators of the previous unit while the tensor pipe works on this one
-                    if (b > 0)
-                        drain(u - 1, b - 1);
-                    else if (u > 0)
-                        drain(u - 1, nact - 1);
-                    ++u;
+                } else {  // last chunk of the slice: steps past the end contribute nothing
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float q = xs[j * TC_M] * rcp_fast(__uint_as_float(p[j]));
+                        q = (j0 + j < cnt) ? q : 0.f;
+                        const uint32_t h = __float_as_uint(q) & 0xffffe000u;
+                        lo[j] = __float_as_uint(q - __uint_as_float(h));
+                        p[j] = h;
+                    }
                 }
+                tc::tmem_st16(col, p);
+                tc::tmem_st16(col + 64, lo);
+                tc::tmem_wait_st();
+                tc::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&q_full[u & 1]);
+                // drain the numerators of the previous unit while the tensor pipe works on this one
+                if (u > 0) drain(u - 1, b > 0 ? b - 1 : nact - 1);
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&x_empty[s]);
@@ -414,7 +470,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
                     const float* den = static_cast<const float*>(a.den) + (long long)r * 32;
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
-                        const int col = ch * NC + c;
+                        const int col = cs * NC + c;
                         if (col < k) {
                             const long long idx = (long long)o * a.su_o + (long long)col * a.su_a;
                             U[idx] = (U[idx] * acc[b][c]) / den[col];
@@ -424,7 +480,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
                     float* dst = static_cast<float*>(a.partial) + (((long long)slice * a.R + r) * a.nown + o) * a.ktmpl;
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
-                        const int col = ch * NC + c;
+                        const int col = cs * NC + c;
                         if (col < a.ktmpl) dst[col] = acc[b][c];
                     }
                 }
