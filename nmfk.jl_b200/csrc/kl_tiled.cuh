@@ -610,9 +610,9 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     const int nblkW = (n + ownper - 1) / ownper;  // W-update: own = rows
     constexpr int TCH = TiledCfg<TX>::TCH;
     auto slices = [&](int nblk, int nred) {
-        const long long target = (use_tc ? 3ll : 4ll) * sms;
+        const long long target = (use_tc ? 3ll * tc_pass_ctas_per_sm(k) : 4ll) * sms;
         long long S = (target + (long long)nblk * units - 1) / ((long long)nblk * units);
-        const long long smax = std::max(1, nred / ((use_tc ? 64 : TCH) * 8));
+        const long long smax = std::max(1, nred / ((use_tc ? tc_pass_chunk(k) : TCH) * 8));
         if (S > smax) S = smax;
         if (S < 1) S = 1;
         return (int)S;

@@ -27,6 +27,8 @@ struct TiledPassArgs {
 // S x nblocks x ceil(R / tc_pass_group(k)).
 bool tc_pass_supported(const TiledPassArgs& a);
 int tc_pass_group(int k);  // restarts that share one X tile inside a CTA
+int tc_pass_ctas_per_sm(int k);
+int tc_pass_chunk(int k);  // steps per chunk (slices hold whole chunks)
 cudaError_t launch_tc_pass(const TiledPassArgs& a, int* d_errflag, cudaStream_t s);
 
 }  // namespace nmfk

@@ -31,31 +31,40 @@
 namespace nmfk {
 namespace {
 
-constexpr int TC_M = 128, TC_TS = 64;
-constexpr int TC_QWARPS = 16;                       // quotient warps: lane quarter = warp % 4, 16 columns each
-constexpr int TC_SWARPS = 4;                        // V stager warps
-constexpr int TC_QW0 = 2 + TC_SWARPS;               // first quotient warp
-constexpr int TC_THREADS = (TC_QW0 + TC_QWARPS) * 32;
+constexpr int TC_M = 128;
 constexpr int TC_NXS = 3, TC_NVB = 3, TC_NRAW = 4;
 constexpr uint32_t TC_LBO = 128;
 
-template <int K8, int N2>
+// K8 / N2: k rounded up to the K granularity of MMA#1 (8) / the N granularity of MMA#2 (16).
+// WIDE = true : one CTA per SM, chunks of 64 steps, 16 quotient + 4 stager warps, 512 tensor-memory columns (k > 16).
+// WIDE = false: TWO CTAs per SM, chunks of 32 steps, 8 quotient + 2 stager warps, 256 columns each (k <= 16): the two
+//               CTAs run out of phase, so one divides (MUFU-bound) while the other waits on its tensor-pipe round trip.
+template <int K8, int N2, bool WIDE>
 struct TcCfg {
+    static constexpr int TS = WIDE ? 64 : 32;                         // steps per chunk
+    static constexpr int QW = TS / 4;                                 // quotient warps: lane quarter = warp % 4, 16 columns each
+    static constexpr int SW = WIDE ? 4 : 2;                           // V stager warps
+    static constexpr int QW0 = 2 + SW;                                // first quotient warp
+    static constexpr int THREADS = (QW0 + QW) * 32;
+    static constexpr int TCOLS = WIDE ? 512 : 256;                    // tensor-memory columns of the CTA
+    static constexpr int NCS = QW / 4;                                // column groups of quotient warps
     static constexpr int NST = N2 == 16 ? 2 : 1;                      // MMA#2: Qhi * [Vhi ; Vlo] stacked along N
     static constexpr int ACOLS = NST * N2;                            // columns of one per-unit numerator buffer
-    static constexpr int ABASE = 256, UBASE = 256 + 2 * ACOLS;        // tensor-memory columns
+    static constexpr int PQ = 2 * TS;                                 // one P/Q buffer: P -> Qhi | Qlo
+    static constexpr int ABASE = 2 * PQ, UBASE = ABASE + 2 * ACOLS;   // tensor-memory columns
     static constexpr int PERB = 2 * K8;                               // U hi | U lo per restart
-    static constexpr int NCQ = N2 / 4;                                // numerator columns per quotient thread
-    static constexpr int RBT = (512 - UBASE) / PERB;
+    static constexpr int NCQ = N2 / NCS;                              // numerator columns per quotient thread
+    static constexpr int RBT = (TCOLS - UBASE) / PERB;
     static constexpr int RBR = 16 / NCQ;                              // 16 accumulator registers per quotient thread
-    static constexpr int RB = RBT < RBR ? RBT : RBR;                  // restarts per CTA (they share the X tiles)
+    static constexpr int RB0 = RBT < RBR ? RBT : RBR;
+    static constexpr int RB = RB0 < NCS ? RB0 : NCS;                  // restarts per CTA (they share the X tiles)
     static constexpr uint32_t SBO1 = (K8 / 4) * 128;                  // MMA#1 B: rows = steps, K extent = K8
-    static constexpr uint32_t SBO2 = (TC_TS / 4) * 128;               // MMA#2 B: rows = columns a, K extent = TS
-    static constexpr uint32_t B1_BYTES = TC_TS * K8 * 4;
-    static constexpr uint32_t B2_BYTES = N2 * TC_TS * 4;
+    static constexpr uint32_t SBO2 = (TS / 4) * 128;                  // MMA#2 B: rows = columns a, K extent = TS
+    static constexpr uint32_t B1_BYTES = TS * K8 * 4;
+    static constexpr uint32_t B2_BYTES = N2 * TS * 4;
     static constexpr uint32_t V_BYTES = 2 * B1_BYTES + 2 * B2_BYTES;  // B1 hi | B1 lo | B2 hi | B2 lo
-    static constexpr uint32_t X_BYTES = TC_TS * TC_M * 4;
-    static constexpr uint32_t RAW_BYTES = TC_TS * K8 * 4;             // un-split V chunk [step][column]
+    static constexpr uint32_t X_BYTES = TS * TC_M * 4;
+    static constexpr uint32_t RAW_BYTES = TS * K8 * 4;             // un-split V chunk [step][column]
     static constexpr size_t SMEM =
         (size_t)TC_NXS * X_BYTES + (size_t)TC_NVB * V_BYTES + (size_t)TC_NRAW * RAW_BYTES + 32 * 8 + 64;
     static_assert(RB >= 1 && RB <= 4, "restart group");
@@ -67,9 +76,10 @@ __device__ __forceinline__ float rcp_fast(float p) {
     return r;
 }
 
-template <int K8, int N2>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassArgs a, int* errflag) {
-    using C = TcCfg<K8, N2>;
+template <int K8, int N2, bool WIDE>
+__global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)) tc_pass_kernel(const TiledPassArgs a, int* errflag) {
+    using C = TcCfg<K8, N2, WIDE>;
+    constexpr int TC_TS = C::TS, TC_QWARPS = C::QW, TC_SWARPS = C::SW, TC_QW0 = C::QW0, TC_THREADS = C::THREADS;
     constexpr int RB = C::RB;
     constexpr int NC = C::NCQ;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -114,7 +124,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
     if (nact == 0 || nchunks <= 0) return;
     const int total = nchunks * nact;
 
-    if (warp == 0) tc::tmem_alloc<512>(tmem_slot);
+    if (warp == 0) tc::tmem_alloc<C::TCOLS>(tmem_slot);
     if (tid == 32) {
         for (int i = 0; i < TC_NXS; ++i) {
             tc::mbar_init(&x_full[i], 1);
@@ -209,7 +219,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
                 const int vb = u % TC_NVB;
                 tc::mbar_wait(&v_full[vb], (uint32_t)((u / TC_NVB) & 1), errflag, 20);
                 tc::tc_fence_after_sync();
-                const uint32_t d = tbase + (uint32_t)(u & 1) * 128;
+                const uint32_t d = tbase + (uint32_t)(u & 1) * C::PQ;
                 const uint32_t uh = tbase + C::UBASE + b * C::PERB, ul = uh + K8;
                 const uint64_t bh = d1 + (uint64_t)((vb * C::V_BYTES) >> 4), bl = bh + (C::B1_BYTES >> 4);
                 if (tc::elect_one()) {
@@ -228,7 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
                 tc::mbar_wait(&q_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 21);
                 tc::tc_fence_after_sync();
                 const uint32_t d = tbase + C::ABASE + (uint32_t)(u & 1) * C::ACOLS;
-                const uint32_t qh = tbase + (uint32_t)(u & 1) * 128, ql = qh + 64;
+                const uint32_t qh = tbase + (uint32_t)(u & 1) * C::PQ, ql = qh + TC_TS;
                 const uint64_t bh = d2 + (uint64_t)((vb * C::V_BYTES) >> 4), bl = bh + (C::B2_BYTES >> 4);
                 if (tc::elect_one()) {
 #pragma unroll
@@ -329,8 +339,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
             if (u >= TC_NVB) tc::mbar_wait(&v_empty[vb], (uint32_t)((u / TC_NVB - 1) & 1), errflag, 30);
             unsigned char* base = Vs + (size_t)vb * C::V_BYTES;
             const float* raw = Raw + (size_t)(u % TC_NRAW) * TC_TS * K8;
-            for (int it = sid; it < 2 * 16 * (K8 / 4); it += NS) {
-                const int hf = it & 1, tb = (it >> 1) & 15, ab = it >> 5;  // steps 4 tb + 2 hf + {0,1}, columns 4 ab + {0..3}
+            for (int it = sid; it < 2 * (TC_TS / 4) * (K8 / 4); it += NS) {
+                const int hf = it & 1, tb = (it >> 1) % (TC_TS / 4), ab = (it >> 1) / (TC_TS / 4);  // steps 4 tb + 2 hf + {0,1}, columns 4 ab + {0..3}
                 float v[2][4];
                 if (t_major) {
 #pragma unroll
@@ -397,6 +407,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
             tc::tc_fence_after_sync();
             const uint32_t col = lane_base + C::ABASE + (uint32_t)(uu & 1) * C::ACOLS + cs * NC;
             uint32_t v0[NC], v1[NC];
+            static_assert(NC == 4 || NC == 8, "numerator columns per quotient thread");
             if (NC == 4) {
                 tc::tmem_ld4(col, v0);
                 if (C::NST == 2) tc::tmem_ld4(col + N2, v1);
@@ -423,7 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
             tc::mbar_wait(&x_full[s], (uint32_t)((c / TC_NXS) & 1), errflag, 40);
             const float* xs = Xs + (size_t)s * TC_TS * TC_M + (size_t)j0 * TC_M + o_loc;
             for (int b = 0; b < nact; ++b, ++u) {
-                const uint32_t col = lane_base + (uint32_t)(u & 1) * 128 + j0;
+                const uint32_t col = lane_base + (uint32_t)(u & 1) * C::PQ + j0;
                 tc::mbar_wait(&p_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 41);
                 tc::tc_fence_after_sync();
                 uint32_t p[16], lo[16];
@@ -448,7 +459,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
                     }
                 }
                 tc::tmem_st16(col, p);
-                tc::tmem_st16(col + 64, lo);
+                tc::tmem_st16(col + TC_TS, lo);
                 tc::tmem_wait_st();
                 tc::tc_fence_before_sync();
                 __syncwarp();
@@ -490,29 +501,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TiledPassA
     }
     tc::tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc<512>(tbase);
+    if (warp == 0) tc::tmem_dealloc<C::TCOLS>(tbase);
 }
 
-template <int K8, int N2>
+template <int K8, int N2, bool WIDE>
 cudaError_t launch_tc(const TiledPassArgs& a, int* d_errflag, cudaStream_t s) {
-    using C = TcCfg<K8, N2>;
+    using C = TcCfg<K8, N2, WIDE>;
     const int ngroups = (a.R + C::RB - 1) / C::RB;
     const long long grid = (long long)a.S * a.nblocks * ngroups;
     if (grid > 2147483647ll) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(tc_pass_kernel<K8, N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(tc_pass_kernel<K8, N2, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) return e;
-    tc_pass_kernel<K8, N2><<<(unsigned)grid, TC_THREADS, C::SMEM, s>>>(a, d_errflag);
+    tc_pass_kernel<K8, N2, WIDE><<<(unsigned)grid, C::THREADS, C::SMEM, s>>>(a, d_errflag);
     return cudaGetLastError();
 }
 
 }  // namespace
 
 int tc_pass_group(int k) {
-    if (k <= 8) return TcCfg<8, 16>::RB;
-    if (k <= 16) return TcCfg<16, 16>::RB;
-    if (k <= 24) return TcCfg<24, 32>::RB;
-    return TcCfg<32, 32>::RB;
+    if (k <= 8) return TcCfg<8, 16, true>::RB;
+    if (k <= 16) return TcCfg<16, 16, true>::RB;
+    if (k <= 24) return TcCfg<24, 32, true>::RB;
+    return TcCfg<32, 32, true>::RB;
 }
+// The two-CTAs-per-SM configuration (WIDE = false, chunks of 32 steps) measured SLOWER than the wide one on C3
+// (3083 vs 3489 restart-iterations/s: the per-unit hand-offs are paid twice as often), so every k uses WIDE.
+int tc_pass_ctas_per_sm(int) { return 1; }
+int tc_pass_chunk(int) { return 64; }
 
 // bulk copies need 16-byte aligned rows of 128 own indices: nown % 4 == 0
 bool tc_pass_supported(const TiledPassArgs& a) {
@@ -520,10 +535,10 @@ bool tc_pass_supported(const TiledPassArgs& a) {
 }
 
 cudaError_t launch_tc_pass(const TiledPassArgs& a, int* d_errflag, cudaStream_t s) {
-    if (a.k <= 8) return launch_tc<8, 16>(a, d_errflag, s);
-    if (a.k <= 16) return launch_tc<16, 16>(a, d_errflag, s);
-    if (a.k <= 24) return launch_tc<24, 32>(a, d_errflag, s);
-    return launch_tc<32, 32>(a, d_errflag, s);
+    if (a.k <= 8) return launch_tc<8, 16, true>(a, d_errflag, s);
+    if (a.k <= 16) return launch_tc<16, 16, true>(a, d_errflag, s);
+    if (a.k <= 24) return launch_tc<24, 32, true>(a, d_errflag, s);
+    return launch_tc<32, 32, true>(a, d_errflag, s);
 }
 
 }  // namespace nmfk

@@ -193,22 +193,33 @@ __global__ void __launch_bounds__(128) umma_timing_kernel(const float* __restric
     tc::tc_fence_before_sync();
     __syncthreads();
     uint32_t phase = 0;
+    // issued from an elect.sync region of warp 0 (no waterfall loops), unrolled by 8
     auto timed = [&](int which, int nmma, int N, bool ss, bool alt) {
         long long t0 = 0;
-        if (tid == 0) {
+        if (warp == 0) {
             tc::tc_fence_after_sync();
             const uint32_t id = tc::idesc_tf32(M, N, 0);
+            const uint64_t da = tc::smem_desc(tc::smem_u32(As), LBO, SBO_K16), db1 = tc::smem_desc(tc::smem_u32(B1), LBO, SBO_K16);
+            const uint64_t db2 = tc::smem_desc(tc::smem_u32(B2), LBO, SBO_K64);
             t0 = clock64();
-            for (int i = 0; i < nmma; ++i) {
-                const uint32_t d = tbase + ((alt && (i & 1)) ? 64 : 0);
-                if (ss)
-                    tc::mma_tf32_ss(d, tc::smem_desc(tc::smem_u32(As), LBO, SBO_K16), tc::smem_desc(tc::smem_u32(B1), LBO, SBO_K16), id, i > 1);
-                else if (N == 64)
-                    tc::mma_tf32_ts(d, tbase + C_U, tc::smem_desc(tc::smem_u32(B1), LBO, SBO_K16), id, i > 1);
-                else
-                    tc::mma_tf32_ts(d, tbase + C_QH + (i & 7) * 8, tc::smem_desc(tc::smem_u32(B2) + (i & 7) * 2 * LBO, LBO, SBO_K64), id, i > 1);
+            if (tc::elect_one()) {
+                for (int i0 = 0; i0 < nmma; i0 += 8) {
+#pragma unroll
+                    for (int ii = 0; ii < 8; ++ii) {
+                        if (i0 + ii < nmma) {
+                            const uint32_t d = tbase + ((alt && (ii & 1)) ? 64 : 0);
+                            if (ss)
+                                tc::mma_tf32_ss(d, da, db1, id, 1);
+                            else if (N == 64)
+                                tc::mma_tf32_ts(d, tbase + C_U, db1, id, 1);
+                            else
+                                tc::mma_tf32_ts(d, tbase + C_QH + ii * 8, db2 + ii * 16, id, 1);
+                        }
+                    }
+                }
+                tc::mma_commit(&bar[0]);
             }
-            tc::mma_commit(&bar[0]);
+            __syncwarp();
         }
         tc::mbar_wait(&bar[0], phase, errflag, 2);
         phase ^= 1;

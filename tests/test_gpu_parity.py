@@ -368,3 +368,73 @@ def test_rowsharded_two_gpus_torchrun():
                        timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ROWSHARD OK" in r.stdout
+
+
+# ---------------------------------------------------------------------------------------------
+# Float32 tiled engine on the 5th-generation tensor cores (kl_tiled_tc.cu): tcgen05.mma kind::tf32 with the
+# 3-term split, tensor-memory operands, per-unit accumulators drained in FP32.  engine=2 takes this path for
+# Float32 data without NaN whose row and column counts are multiples of 4; engine=4 forces the scalar-FMA pass.
+# ---------------------------------------------------------------------------------------------
+def test_umma_building_blocks_selftest(ctx):
+    """tcgen05.mma with A/B in shared memory, A in tensor memory, and the 2-term split of the A operand."""
+    import ctypes as C
+    rng = np.random.default_rng(7)
+    U = (rng.integers(0, 256, (128, 16)) / 64.0).astype(np.float32)  # tf32-exact inputs
+    V = (rng.integers(0, 256, (64, 16)) / 64.0).astype(np.float32)
+    Pss, Pts = np.zeros((128, 64), np.float32), np.zeros((128, 64), np.float32)
+    Aa, Ab = np.zeros((128, 16), np.float32), np.zeros((128, 16), np.float32)
+    err = C.c_int32(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    nb._lib.check(ctx._lib.nmfk_umma_selftest(ctx._h, p(U), p(V), 7, p(Pss), p(Pts), p(Aa), p(Ab), C.byref(err)), ctx._h)
+    P = U.astype(np.float64) @ V.astype(np.float64).T
+    assert err.value == 0
+    assert np.array_equal(Pss.astype(np.float64), P) and np.array_equal(Pts.astype(np.float64), P)
+    assert relerr(Aa, (0.5 * P) @ V.astype(np.float64)) < 5e-6
+
+
+@pytest.mark.parametrize("n,m,k,niter", [(1024, 256, 16, 20), (1000, 200, 10, 22), (640, 1204, 24, 12), (512, 384, 32, 12),
+                                         (256, 128, 3, 25), (3108, 332, 7, 21), (128, 64, 1, 12)])
+def test_tc_tiled_trace_parity_f32(ctx, n, m, k, niter):
+    """Per-iteration W, H of the tcgen05 path against the Float64 oracle: <= 1e-4 relative (BASELINE north_star)."""
+    X = synth.mixture(n, m, 3, seed=17, dtype=np.float32)
+    W0, H0 = synth.philox_inits(23, 1, n, k, m, dtype=np.float32)
+    Wt, Ht, ob = nb.trace(X, k, W0[0], H0[0], niter, ctx=ctx, engine=2)
+    Wr, Hr, obr = oracle_trace(X, k, W0[0], H0[0], niter)
+    for t in range(niter):
+        assert relerr(Wt[t], Wr[t]) < RTOL32, ("W", t)
+        assert relerr(Ht[t], Hr[t]) < RTOL32, ("H", t)
+    assert np.allclose(ob, obr, rtol=2e-3, atol=1e-12 + 1e-5 * obr.max())
+
+
+@pytest.mark.parametrize("n,m,k,R", [(2048, 512, 16, 9), (20000, 1000, 24, 5), (1000, 5000, 8, 6)])
+def test_tc_tiled_restart_groups_match_scalar_pass(ctx, n, m, k, R):
+    """Several restarts per CTA (ragged last group), sliced reductions and edge tiles: the tcgen05 pass and the
+    scalar-FMA pass give the same factors after a fixed number of iterations."""
+    X = synth.mixture(n, m, 4, seed=9, dtype=np.float32)
+    ctx.set_X(X)
+    res = {}
+    for eng in (4, 2):
+        b = ctx.batch(k, R)
+        b.init_random(77)
+        ctx.solve([b], nb.default_params(engine=eng, maxiter=8, normalize=0))
+        res[eng] = b.get()
+        b.close()
+    assert relerr(res[2]["W"], res[4]["W"]) < 2e-5 and relerr(res[2]["H"], res[4]["H"]) < 2e-5
+    assert np.allclose(res[2]["obj_norm"], res[4]["obj_norm"], rtol=1e-4)
+
+
+def test_tc_tiled_frozen_restarts_and_stop_rule(ctx):
+    """Restarts that stop early are frozen inside a restart group; iteration counts / stop reasons equal the
+    scalar pass with the reference stop rule."""
+    X = synth.mixture(512, 128, 3, seed=4, dtype=np.float32)
+    ctx.set_X(X)
+    res = {}
+    for eng in (4, 2):
+        b = ctx.batch(3, 7)
+        b.init_random(5)
+        ctx.solve([b], nb.default_params(engine=eng, maxiter=400))
+        res[eng] = b.get()
+        b.close()
+    assert np.array_equal(res[2]["stop_reason"], res[4]["stop_reason"])
+    assert np.max(np.abs(res[2]["iters"].astype(int) - res[4]["iters"].astype(int))) <= 10  # one check period
+    assert np.allclose(res[2]["obj_norm"], res[4]["obj_norm"], rtol=5e-3)
