@@ -22,6 +22,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 #include <vector>
 
@@ -706,6 +707,14 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
             NMFK_TRY(cudaGetLastError());
             ++*launches;
         }
+        // NMFK_TC_TRACE=<file>: clock64 stamps of CTA 0 of the first tcgen05 H-update (tools/tc_trace.py reads them)
+        long long* d_trace = nullptr;
+        const char* trace_path = use_tc ? getenv("NMFK_TC_TRACE") : nullptr;
+        if (trace_path != nullptr) {
+            NMFK_TRY(cudaMalloc(&d_trace, 3 * 64 * 8 * sizeof(long long)));
+            NMFK_TRY(cudaMemsetAsync(d_trace, 0, 3 * 64 * 8 * sizeof(long long), s));
+            ph.trace = d_trace;
+        }
         bool need_guard = true;
         while (true) {
             if (need_guard) {
@@ -726,6 +735,18 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
                 NMFK_TRY(cudaGetLastError());
                 NMFK_TRY((dispatch_tiled_pass<TX, TC>(ph, red, s, use_tc, h_active + 1)));
                 *launches += 2 + (SH > 1 || sharded);
+                if (d_trace != nullptr) {
+                    std::vector<long long> ht(3 * 64 * 8);
+                    NMFK_TRY(cudaMemcpyAsync(ht.data(), d_trace, ht.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
+                    NMFK_TRY(cudaStreamSynchronize(s));
+                    if (FILE* f = fopen(trace_path, "wb")) {
+                        fwrite(ht.data(), sizeof(long long), ht.size(), f);
+                        fclose(f);
+                    }
+                    cudaFree(d_trace);
+                    d_trace = nullptr;
+                    ph.trace = nullptr;
+                }
                 if (sharded) {
                     // colsum(W) and W' * (X ./ (W*H)) over this rank's rows -> sums over all rows, then the update
                     NMFK_TRY(sh->allreduce(sh->comm, den, (size_t)R * 32 + redsz, sizeof(TC) == 8 ? 1 : 0, s));

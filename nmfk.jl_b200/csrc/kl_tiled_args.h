@@ -19,6 +19,7 @@ struct TiledPassArgs {
     int ldimp;
     int has_nan, first_iter;
     double lambda;
+    long long* trace;   // debug: clock64 stamps of CTA 0 ([role][unit < 64][8]); nullptr in production
     int ktmpl;          // column stride of `partial` (the template K of the combine kernel)
 };
 

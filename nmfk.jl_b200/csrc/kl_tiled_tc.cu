@@ -32,7 +32,7 @@ namespace nmfk {
 namespace {
 
 constexpr int TC_M = 128;
-constexpr int TC_NXS = 3, TC_NVB = 3, TC_NRAW = 4;
+constexpr int TC_NVB = 3, TC_NRAW = 4;
 constexpr uint32_t TC_LBO = 128;
 
 // K8 / N2: k rounded up to the K granularity of MMA#1 (8) / the N granularity of MMA#2 (16).
@@ -42,6 +42,8 @@ constexpr uint32_t TC_LBO = 128;
 template <int K8, int N2, bool WIDE>
 struct TcCfg {
     static constexpr int TS = WIDE ? 64 : 32;                         // steps per chunk
+    static constexpr int NXS = 3;                                     // X tile stages
+    static constexpr int RPAD = (WIDE && K8 > 24) ? 0 : 4;            // raw V chunk padding (shared memory budget at K8 = 32)
     static constexpr int QW = TS / 4;                                 // quotient warps: lane quarter = warp % 4, 16 columns each
     static constexpr int SW = WIDE ? 4 : 2;                           // V stager warps
     static constexpr int QW0 = 2 + SW;                                // first quotient warp
@@ -64,10 +66,13 @@ struct TcCfg {
     static constexpr uint32_t B2_BYTES = N2 * TS * 4;
     static constexpr uint32_t V_BYTES = 2 * B1_BYTES + 2 * B2_BYTES;  // B1 hi | B1 lo | B2 hi | B2 lo
     static constexpr uint32_t X_BYTES = TS * TC_M * 4;
-    static constexpr uint32_t RAW_BYTES = TS * K8 * 4;             // un-split V chunk [step][column]
+    static constexpr int RAWP_T = TS + RPAD;                          // raw V chunk [column][step], padded pitch (floats)
+    static constexpr int RAWP_A = K8 + RPAD;                          // raw V chunk [step][column], padded pitch
+    static constexpr uint32_t RAW_BYTES = (K8 * TS + RPAD * (K8 > TS ? K8 : TS)) * 4;
     static constexpr size_t SMEM =
-        (size_t)TC_NXS * X_BYTES + (size_t)TC_NVB * V_BYTES + (size_t)TC_NRAW * RAW_BYTES + 32 * 8 + 64;
+        (size_t)NXS * X_BYTES + (size_t)TC_NVB * V_BYTES + (size_t)TC_NRAW * RAW_BYTES + 32 * 8 + 64;
     static_assert(RB >= 1 && RB <= 4, "restart group");
+    static_assert(SMEM <= 232448, "shared memory budget of one CTA");
 };
 
 __device__ __forceinline__ float rcp_fast(float p) {
@@ -79,13 +84,14 @@ __device__ __forceinline__ float rcp_fast(float p) {
 template <int K8, int N2, bool WIDE>
 __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)) tc_pass_kernel(const TiledPassArgs a, int* errflag) {
     using C = TcCfg<K8, N2, WIDE>;
+    constexpr int TC_NXS = C::NXS;
     constexpr int TC_TS = C::TS, TC_QWARPS = C::QW, TC_SWARPS = C::SW, TC_QW0 = C::QW0, TC_THREADS = C::THREADS;
     constexpr int RB = C::RB;
     constexpr int NC = C::NCQ;
     extern __shared__ __align__(1024) unsigned char smem[];
     float* Xs = reinterpret_cast<float*>(smem);                         // [NXS][TS][M]
     unsigned char* Vs = smem + (size_t)TC_NXS * C::X_BYTES;              // [NVB][V_BYTES]
-    float* Raw = reinterpret_cast<float*>(Vs + (size_t)TC_NVB * C::V_BYTES);  // [NRAW][TS][K8]
+    float* Raw = reinterpret_cast<float*>(Vs + (size_t)TC_NVB * C::V_BYTES);  // [NRAW][RAW_BYTES]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(Raw) + (size_t)TC_NRAW * C::RAW_BYTES);
     uint64_t* x_full = bars;                 // [NXS]  X tile landed (bulk-copy transaction count)
     uint64_t* x_empty = x_full + TC_NXS;     // [NXS]  quotient warps are done with the tile
@@ -98,6 +104,11 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
     int* s_act = reinterpret_cast<int*>(tmem_slot + 1);  // [RB] active restarts of the group, then their count
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    long long* const trc = (a.trace != nullptr && blockIdx.x == 0) ? a.trace : nullptr;
+#define TC_STAMP(role, unit, ev)                                                                    \
+    do {                                                                                            \
+        if (trc != nullptr && (unit) < 64 && lane == 0) trc[((role) * 64 + (unit)) * 8 + (ev)] = clock64(); \
+    } while (0)
     const int ngroups = (a.R + RB - 1) / RB;
     const int g = blockIdx.x % ngroups;
     const int rest = blockIdx.x / ngroups;
@@ -217,8 +228,10 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             constexpr uint64_t KSTEP = (2 * TC_LBO) >> 4;                                // one K-step = two 16-byte chunks
             auto mma1 = [&](int u, int b) {
                 const int vb = u % TC_NVB;
+                TC_STAMP(1, u, 3);
                 tc::mbar_wait(&v_full[vb], (uint32_t)((u / TC_NVB) & 1), errflag, 20);
                 tc::tc_fence_after_sync();
+                TC_STAMP(1, u, 4);
                 const uint32_t d = tbase + (uint32_t)(u & 1) * C::PQ;
                 const uint32_t uh = tbase + C::UBASE + b * C::PERB, ul = uh + K8;
                 const uint64_t bh = d1 + (uint64_t)((vb * C::V_BYTES) >> 4), bl = bh + (C::B1_BYTES >> 4);
@@ -232,11 +245,14 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                 tc::mma_commit(&p_full[u & 1]);
                 }
                 __syncwarp();
+                TC_STAMP(1, u, 5);
             };
             auto mma2 = [&](int u) {
                 const int vb = u % TC_NVB;
+                TC_STAMP(1, u, 0);
                 tc::mbar_wait(&q_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 21);
                 tc::tc_fence_after_sync();
+                TC_STAMP(1, u, 1);
                 const uint32_t d = tbase + C::ABASE + (uint32_t)(u & 1) * C::ACOLS;
                 const uint32_t qh = tbase + (uint32_t)(u & 1) * C::PQ, ql = qh + TC_TS;
                 const uint64_t bh = d2 + (uint64_t)((vb * C::V_BYTES) >> 4), bl = bh + (C::B2_BYTES >> 4);
@@ -253,6 +269,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                 tc::mma_commit(&a_full[u & 1]);
                 }
                 __syncwarp();
+                TC_STAMP(1, u, 2);
             };
             // unit u = c * nact + b; MMA#1 runs two units ahead of MMA#2
             int b1 = 0;  // restart slot of the next MMA#1
@@ -280,21 +297,22 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
         const bool t_major = a.sv_t == 1;  // raw layout [column][step] (H-update: V = W) instead of [step][column]
         const bool vec16 = t_major ? ((a.sv_a & 3) == 0 && (a.v_rstride & 3) == 0)
                                    : (a.sv_a == 1 && (k & 3) == 0 && (a.sv_t & 3) == 0 && (a.v_rstride & 3) == 0);
+        constexpr int RAWF = C::RAW_BYTES / 4, PT = C::RAWP_T, PA = C::RAWP_A;
         auto issue_raw = [&](int c, int b, int stage) {
             const float* V = Vg + (long long)s_act[b] * a.v_rstride;
             const int t0 = t_begin + c * TC_TS;
-            float* dst = Raw + (size_t)stage * TC_TS * K8;
+            float* dst = Raw + (size_t)stage * RAWF;
             if (vec16 && t_major) {
                 for (int e = sid; e < K8 * (TC_TS / 4); e += NS) {
                     const int col = e / (TC_TS / 4), t4 = (e % (TC_TS / 4)) * 4;
                     const bool live = (t0 + t4 < t_end) && (col < k);
-                    tc::cp_async16_zfill(dst + col * TC_TS + t4, live ? V + (long long)(t0 + t4) + (long long)col * a.sv_a : V, live ? 16u : 0u);
+                    tc::cp_async16_zfill(dst + col * PT + t4, live ? V + (long long)(t0 + t4) + (long long)col * a.sv_a : V, live ? 16u : 0u);
                 }
             } else if (vec16) {
                 for (int e = sid; e < TC_TS * (K8 / 4); e += NS) {
                     const int tl = e / (K8 / 4), a4 = (e % (K8 / 4)) * 4;
                     const bool live = (t0 + tl < t_end) && (a4 < k);
-                    tc::cp_async16_zfill(dst + tl * K8 + a4, live ? V + (long long)(t0 + tl) * a.sv_t + a4 : V, live ? 16u : 0u);
+                    tc::cp_async16_zfill(dst + tl * PA + a4, live ? V + (long long)(t0 + tl) * a.sv_t + a4 : V, live ? 16u : 0u);
                 }
             } else {
                 for (int e = sid; e < TC_TS * K8; e += NS) {
@@ -307,7 +325,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                         tl = e / K8;
                     }
                     const bool live = (t0 + tl < t_end) && (col < k);
-                    tc::cp_async4_zfill(dst + (t_major ? col * TC_TS + tl : tl * K8 + col),
+                    tc::cp_async4_zfill(dst + (t_major ? col * PT + tl : tl * PA + col),
                                         live ? V + (long long)(t0 + tl) * a.sv_t + (long long)col * a.sv_a : V, live ? 4u : 0u);
                 }
             }
@@ -327,64 +345,90 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             advance();
         }
         tc::cp_async_commit();
+        constexpr int NAB = K8 / 4, NTB = TC_TS / 4;
+        constexpr int ITA = TC_TS * NAB / NS, ITB = K8 * NTB / NS;  // items per thread and pass
+        static_assert(ITA * NS == TC_TS * NAB && ITB * NS == K8 * NTB && ITA >= 1, "stager work split");
         for (int u = 0; u < total; ++u) {
-            if (u + 2 < total) {
-                issue_raw(ci, bi, (u + 2) % TC_NRAW);
-                advance();
-            }
-            tc::cp_async_commit();
-            tc::cp_async_wait<2>();           // this thread's copies of unit u have landed
+            tc::cp_async_wait<1>();           // this thread's copies of unit u have landed (unit u + 1 may be in flight)
             tc::named_bar_sync(1, NS);        // ... and everybody else's
+            if (warp == 2) TC_STAMP(2, u, 1);
             const int vb = u % TC_NVB;
             if (u >= TC_NVB) tc::mbar_wait(&v_empty[vb], (uint32_t)((u / TC_NVB - 1) & 1), errflag, 30);
+            if (warp == 2) TC_STAMP(2, u, 2);
             unsigned char* base = Vs + (size_t)vb * C::V_BYTES;
-            const float* raw = Raw + (size_t)(u % TC_NRAW) * TC_TS * K8;
-            for (int it = sid; it < 2 * (TC_TS / 4) * (K8 / 4); it += NS) {
-                const int hf = it & 1, tb = (it >> 1) % (TC_TS / 4), ab = (it >> 1) / (TC_TS / 4);  // steps 4 tb + 2 hf + {0,1}, columns 4 ab + {0..3}
-                float v[2][4];
-                if (t_major) {
+            const float* raw = Raw + (size_t)(u % TC_NRAW) * RAWF;
+            // Two passes with shared-memory-conflict-free lane mappings (a warp touches 8 consecutive 16-byte rows of
+            // 4 different core matrices = 512 contiguous bytes per store); all loads of a pass are issued up front.
+            // pass A -> MMA#1 images: item = (step t, 4 columns 4 ab ..): row = step, 16 bytes = 4 columns
+            {
+                float v[ITA][4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 w = *reinterpret_cast<const float2*>(raw + (ab * 4 + j) * TC_TS + tb * 4 + hf * 2);
-                        v[0][j] = w.x;
-                        v[1][j] = w.y;
-                    }
-                } else {
+                for (int q = 0; q < ITA; ++q) {
+                    const int it = sid + q * NS;
+                    const int t = (it & 7) + 8 * (it / (8 * NAB)), ab = (it >> 3) % NAB;
+                    if (t_major) {
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const float4 w = *reinterpret_cast<const float4*>(raw + (tb * 4 + hf * 2 + i) * K8 + ab * 4);
-                        v[i][0] = w.x;
-                        v[i][1] = w.y;
-                        v[i][2] = w.z;
-                        v[i][3] = w.w;
+                        for (int j = 0; j < 4; ++j) v[q][j] = raw[(ab * 4 + j) * PT + t];
+                    } else {
+                        const float4 w = *reinterpret_cast<const float4*>(raw + t * PA + ab * 4);
+                        v[q][0] = w.x, v[q][1] = w.y, v[q][2] = w.z, v[q][3] = w.w;
                     }
                 }
-                float h[2][4], l[2][4];
 #pragma unroll
-                for (int i = 0; i < 2; ++i)
+                for (int q = 0; q < ITA; ++q) {
+                    const int it = sid + q * NS;
+                    const int t = (it & 7) + 8 * (it / (8 * NAB)), ab = (it >> 3) % NAB;
+                    float h[4], l[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        h[i][j] = __uint_as_float(__float_as_uint(v[i][j]) & 0xffffe000u);
-                        l[i][j] = v[i][j] - h[i][j];
+                        h[j] = __uint_as_float(__float_as_uint(v[q][j]) & 0xffffe000u);
+                        l[j] = v[q][j] - h[j];
                     }
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {  // MMA#1 image: row = step, 16 bytes = 4 columns
-                    const int t = tb * 4 + hf * 2 + i;
                     const uint32_t off = (t & 7) * 16 + (t >> 3) * C::SBO1 + ab * TC_LBO;
-                    *reinterpret_cast<float4*>(base + off) = make_float4(h[i][0], h[i][1], h[i][2], h[i][3]);
-                    *reinterpret_cast<float4*>(base + C::B1_BYTES + off) = make_float4(l[i][0], l[i][1], l[i][2], l[i][3]);
+                    *reinterpret_cast<float4*>(base + off) = make_float4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<float4*>(base + C::B1_BYTES + off) = make_float4(l[0], l[1], l[2], l[3]);
+                }
+            }
+            // pass B -> MMA#2 images: item = (column, 4 steps 4 tb ..): row = column, 16 bytes = 4 steps
+            {
+                float v[ITB][4];
+#pragma unroll
+                for (int q = 0; q < ITB; ++q) {
+                    const int it = sid + q * NS;
+                    const int col = (it & 7) + 8 * (it / (8 * NTB)), tb = (it >> 3) % NTB;
+                    if (t_major) {
+                        const float4 w = *reinterpret_cast<const float4*>(raw + col * PT + tb * 4);
+                        v[q][0] = w.x, v[q][1] = w.y, v[q][2] = w.z, v[q][3] = w.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[q][i] = raw[(tb * 4 + i) * PA + col];
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {  // MMA#2 image: row = column a, 16 bytes = 4 steps (this item: 2 of them)
-                    const int col = ab * 4 + j;
-                    const uint32_t off = 2 * C::B1_BYTES + (col & 7) * 16 + (col >> 3) * C::SBO2 + tb * TC_LBO + hf * 8;
-                    *reinterpret_cast<float2*>(base + off) = make_float2(h[0][j], h[1][j]);
-                    *reinterpret_cast<float2*>(base + C::B2_BYTES + off) = make_float2(l[0][j], l[1][j]);
+                for (int q = 0; q < ITB; ++q) {
+                    const int it = sid + q * NS;
+                    const int col = (it & 7) + 8 * (it / (8 * NTB)), tb = (it >> 3) % NTB;
+                    float h[4], l[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        h[i] = __uint_as_float(__float_as_uint(v[q][i]) & 0xffffe000u);
+                        l[i] = v[q][i] - h[i];
+                    }
+                    const uint32_t off = 2 * C::B1_BYTES + (col & 7) * 16 + (col >> 3) * C::SBO2 + tb * TC_LBO;
+                    *reinterpret_cast<float4*>(base + off) = make_float4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<float4*>(base + C::B2_BYTES + off) = make_float4(l[0], l[1], l[2], l[3]);
                 }
             }
             tc::fence_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&v_full[vb]);
+            if (warp == 2) TC_STAMP(2, u, 3);
+            if (u + 2 < total) {
+                issue_raw(ci, bi, (u + 2) % TC_NRAW);
+                advance();
+            }
+            tc::cp_async_commit();
+            if (warp == 2) TC_STAMP(2, u, 0);
         }
         tc::cp_async_wait<0>();
         __syncwarp();
@@ -401,12 +445,12 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
         for (int b = 0; b < RB; ++b)
 #pragma unroll
             for (int c = 0; c < NC; ++c) acc[b][c] = 0.f;
-        // numerators of unit uu -> registers of restart slot `target`, round-to-nearest adds
-        auto drain = [&](int uu, int target) {
-            tc::mbar_wait(&a_full[uu & 1], (uint32_t)((uu >> 1) & 1), errflag, 43);
-            tc::tc_fence_after_sync();
+        // numerators of unit uu -> registers of restart slot `target`, round-to-nearest adds.  No barrier of its own in the
+        // steady state: the tcgen05.commit behind p_full(u) also covers MMA#2(u-2), issued earlier by the same thread,
+        // so the numerators of unit u-2 are complete when P(u) is (their buffer is reused by MMA#2(u), after q_full(u)).
+        uint32_t v0[NC], v1[NC];
+        auto drain_load = [&](int uu) {
             const uint32_t col = lane_base + C::ABASE + (uint32_t)(uu & 1) * C::ACOLS + cs * NC;
-            uint32_t v0[NC], v1[NC];
             static_assert(NC == 4 || NC == 8, "numerator columns per quotient thread");
             if (NC == 4) {
                 tc::tmem_ld4(col, v0);
@@ -415,7 +459,8 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                 tc::tmem_ld8(col, v0);
                 if (C::NST == 2) tc::tmem_ld8(col + N2, v1);
             }
-            tc::tmem_wait_ld();
+        };
+        auto drain_add = [&](int target) {
 #pragma unroll
             for (int bb = 0; bb < RB; ++bb)
                 if (bb == target) {
@@ -427,6 +472,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                     }
                 }
         };
+        int bm1 = 0, bm2 = 0;  // restart slots of units u-1 and u-2
         int u = 0;
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % TC_NXS;
@@ -435,12 +481,19 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             const float* xs = Xs + (size_t)s * TC_TS * TC_M + (size_t)j0 * TC_M + o_loc;
             for (int b = 0; b < nact; ++b, ++u) {
                 const uint32_t col = lane_base + (uint32_t)(u & 1) * C::PQ + j0;
+                if (warp == TC_QW0) TC_STAMP(0, u, 0);
                 tc::mbar_wait(&p_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 41);
                 tc::tc_fence_after_sync();
+                if (warp == TC_QW0) TC_STAMP(0, u, 1);
                 uint32_t p[16], lo[16];
                 tc::tmem_ld16(col, p);
+                if (u >= 2) drain_load(u - 2);
                 tc::tmem_wait_ld();
+                if (u >= 2) drain_add(bm2);
+                if (warp == TC_QW0) TC_STAMP(0, u, 2);
                 if (cnt == TC_TS) {
+                    // (one MUFU.RCP per PAIR of quotients, r = 1/(p0 p1), was measured slower: this loop is bound by
+                    // instruction issue, not by the MUFU unit)
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float q = xs[j * TC_M] * rcp_fast(__uint_as_float(p[j]));
@@ -458,19 +511,29 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                         p[j] = h;
                     }
                 }
+                if (warp == TC_QW0) TC_STAMP(0, u, 3);
                 tc::tmem_st16(col, p);
                 tc::tmem_st16(col + TC_TS, lo);
                 tc::tmem_wait_st();
                 tc::tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&q_full[u & 1]);
-                // drain the numerators of the previous unit while the tensor pipe works on this one
-                if (u > 0) drain(u - 1, b > 0 ? b - 1 : nact - 1);
+                if (warp == TC_QW0) TC_STAMP(0, u, 4);
+                if (warp == TC_QW0) TC_STAMP(0, u, 5);
+                bm2 = bm1;
+                bm1 = b;
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&x_empty[s]);
         }
-        drain(total - 1, nact - 1);
+        // the last two units: wait for their own MMA#2
+        for (int uu = max(0, total - 2); uu < total; ++uu) {
+            tc::mbar_wait(&a_full[uu & 1], (uint32_t)((uu >> 1) & 1), errflag, 43);
+            tc::tc_fence_after_sync();
+            drain_load(uu);
+            tc::tmem_wait_ld();
+            drain_add(uu == total - 1 ? bm1 : bm2);
+        }
         // numerators -> factor update (or the slice's partial sums): this thread's NC columns of every restart
 #pragma unroll
         for (int b = 0; b < RB; ++b) {
