@@ -637,7 +637,36 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     const size_t psz = std::max((size_t)((SH > 1 || sharded) ? (size_t)SH * R * m * kt : 0),
                                 (size_t)(SW > 1 ? (size_t)SW * R * n * kt : 0));
     const size_t redsz = sharded ? (size_t)R * m * kt : 0;
-    if (sharded && a.normalize == 2) return cudaErrorNotSupported;  // column sums of W would need another exchange
+    if (sharded && a.normalize == 2) return cudaErrorNotSupported;
+    // Float32 objective on the tensor cores: D = X, U = W, V = H (the W-update orientation), P = W H by MMA#1 and
+    // (x - p)^2 by the quotient warps; partial sums per block of 128 rows like tiled_objective_kernel
+    auto obj_args = [&](int restore, int sel) {
+        TiledPassArgs po{};
+        po.D = a.X;
+        po.U = a.W;
+        po.V = a.H;
+        po.st = a.st;
+        po.u_rstride = (long long)n * k;
+        po.v_rstride = (long long)k * m;
+        po.su_o = 1;
+        po.su_a = n;
+        po.sv_t = k;
+        po.sv_a = 1;
+        po.nown = n;
+        po.nred = m;
+        po.k = k;
+        po.R = R;
+        po.S = 1;
+        po.nblocks = nblkObj;
+        po.lambda = a.lambda;
+        po.ktmpl = kt;
+        po.obj_partials = objp;
+        po.obj_weight = a.weight;
+        po.obj_restore = restore;
+        po.obj_sel = sel;
+        return po;
+    };
+  // column sums of W would need another exchange
 
     NMFK_TRY(cudaMalloc(&den, ((size_t)R * 32 + redsz) * sizeof(TC)));
     if (sharded) {
@@ -768,9 +797,13 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
                 ++*launches;
             }
             if (it % a.check_every == 0) {
-                dim3 g(nblkObj, R);
-                tiled_objective_kernel<TX, TC><<<g, 128, (size_t)k * 128 * sizeof(TC), s>>>(
-                    (const TX*)a.X, n, m, k, (const TC*)a.W, (const TC*)a.H, a.st, (TC)a.lambda, 0, 1, a.weight, objp);
+                if (use_tc) {
+                    NMFK_TRY(launch_tc_objective(obj_args(0, 0), h_active + 1, s));
+                } else {
+                    dim3 g(nblkObj, R);
+                    tiled_objective_kernel<TX, TC><<<g, 128, (size_t)k * 128 * sizeof(TC), s>>>(
+                        (const TX*)a.X, n, m, k, (const TC*)a.W, (const TC*)a.H, a.st, (TC)a.lambda, 0, 1, a.weight, objp);
+                }
                 NMFK_TRY(cudaGetLastError());
                 if (sharded) {  // the objective is a sum over all rows
                     tiled_objsum_kernel<<<(R + 127) / 128, 128, 0, s>>>(objp, nblkObj, R, obj2);
@@ -804,9 +837,13 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     }
     {
         // post-run objective on the restored X + normalisation for restarts that stopped in this call
-        dim3 g(nblkObj, R);
-        tiled_objective_kernel<TX, TC><<<g, 128, (size_t)k * 128 * sizeof(TC), s>>>(
-            (const TX*)a.X, n, m, k, (const TC*)a.W, (const TC*)a.H, a.st, (TC)a.lambda, 1, 0, a.weight, objp);
+        if (use_tc) {
+            NMFK_TRY(launch_tc_objective(obj_args(1, 1), h_active + 1, s));
+        } else {
+            dim3 g(nblkObj, R);
+            tiled_objective_kernel<TX, TC><<<g, 128, (size_t)k * 128 * sizeof(TC), s>>>(
+                (const TX*)a.X, n, m, k, (const TC*)a.W, (const TC*)a.H, a.st, (TC)a.lambda, 1, 0, a.weight, objp);
+        }
         NMFK_TRY(cudaGetLastError());
         if (sharded) {
             tiled_objsum_kernel<<<(R + 127) / 128, 128, 0, s>>>(objp, nblkObj, R, obj2);

@@ -19,6 +19,11 @@ struct TiledPassArgs {
     int ldimp;
     int has_nan, first_iter;
     double lambda;
+    // objective mode (tc_objective): sum over non-NaN entries of (x - U V^T)^2 per restart and block of 128 own indices
+    double* obj_partials;  // [(r * nblocks + block) * 2 + {0: weighted, 1: plain}]
+    double obj_weight;
+    int obj_restore;       // 1: substituted zeros (x == lambda) count as 0 (final objective on the restored X)
+    int obj_sel;           // 0: running restarts (stop == 0); 1: restarts that stopped and are not finished (done == 0)
     long long* trace;   // debug: clock64 stamps of CTA 0 ([role][unit < 64][8]); nullptr in production
     int ktmpl;          // column stride of `partial` (the template K of the combine kernel)
 };
@@ -31,5 +36,7 @@ int tc_pass_group(int k);  // restarts that share one X tile inside a CTA
 int tc_pass_ctas_per_sm(int k);
 int tc_pass_chunk(int k);  // steps per chunk (slices hold whole chunks)
 cudaError_t launch_tc_pass(const TiledPassArgs& a, int* d_errflag, cudaStream_t s);
+// Float32 objective sums on the same machinery (MMA#1 only): a = the W-update arguments (D = X, U = W, V = H), S = 1
+cudaError_t launch_tc_objective(const TiledPassArgs& a, int* d_errflag, cudaStream_t s);
 
 }  // namespace nmfk

@@ -81,7 +81,9 @@ __device__ __forceinline__ float rcp_fast(float p) {
     return r;
 }
 
-template <int K8, int N2, bool WIDE>
+// OBJ = true: objective mode.  Only MMA#1 runs (P = U V^T); the quotient warps accumulate (x - p)^2 instead of dividing,
+// nothing is written back to the factors: replaces tiled_objective_kernel (NMFkMultiplicative.jl:74,125) for Float32.
+template <int K8, int N2, bool WIDE, bool OBJ>
 __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)) tc_pass_kernel(const TiledPassArgs a, int* errflag) {
     using C = TcCfg<K8, N2, WIDE>;
     constexpr int TC_NXS = C::NXS;
@@ -126,7 +128,10 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
         int nact = 0;
         for (int b = 0; b < RB; ++b) {
             const int r = g * RB + b;
-            if (r < a.R && a.st[r].stop == 0) s_act[nact++] = r;  // finished restarts are frozen
+            if (r >= a.R) continue;
+            const bool stopped = a.st[r].stop != 0;
+            const bool take = (OBJ && a.obj_sel == 1) ? (stopped && a.st[r].done == 0) : !stopped;  // finished restarts are frozen
+            if (take) s_act[nact++] = r;
         }
         s_act[RB] = nact;
     }
@@ -243,6 +248,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                     tc::mma_tf32_ts(d, uh + ks * 8, bh + ks * KSTEP, idP, 1);
                 }
                 tc::mma_commit(&p_full[u & 1]);
+                if (OBJ) tc::mma_commit(&v_empty[vb]);  // MMA#1 is the only reader of the V images
                 }
                 __syncwarp();
                 TC_STAMP(1, u, 5);
@@ -281,7 +287,12 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                 b1 = next_b(b1);
             }
             for (int u = 0; u < total; ++u) {
-                mma2(u);
+                if (OBJ) {  // no MMA#2: the P buffer is free once the quotient warps have read it
+                    tc::mbar_wait(&q_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 22);
+                    tc::tc_fence_after_sync();
+                } else {
+                    mma2(u);
+                }
                 if (u + 2 < total) {
                     mma1(u + 2, b1);
                     b1 = next_b(b1);
@@ -390,7 +401,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                 }
             }
             // pass B -> MMA#2 images: item = (column, 4 steps 4 tb ..): row = column, 16 bytes = 4 steps
-            {
+            if (!OBJ) {
                 float v[ITB][4];
 #pragma unroll
                 for (int q = 0; q < ITB; ++q) {
@@ -440,6 +451,65 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
         const bool valid = o < a.nown;
         const uint32_t lane_base = tbase + ((uint32_t)(lq * 32) << 16);
         const int j0 = cs * 16;
+        if constexpr (OBJ) {
+            // ----- objective mode: sum over this thread's (own index, 16 steps) of (x - p)^2, per restart slot -----
+            double sacc[RB];
+#pragma unroll
+            for (int b = 0; b < RB; ++b) sacc[b] = 0.0;
+            const float lambda = (float)a.lambda;
+            const bool restore = a.obj_restore != 0;
+            int u = 0;
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % TC_NXS;
+                const int cnt = min(TC_TS, t_end - (t_begin + c * TC_TS));
+                tc::mbar_wait(&x_full[s], (uint32_t)((c / TC_NXS) & 1), errflag, 40);
+                const float* xs = Xs + (size_t)s * TC_TS * TC_M + (size_t)j0 * TC_M + o_loc;
+                for (int b = 0; b < nact; ++b, ++u) {
+                    const uint32_t col = lane_base + (uint32_t)(u & 1) * C::PQ + j0;
+                    tc::mbar_wait(&p_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 41);
+                    tc::tc_fence_after_sync();
+                    uint32_t p[16];
+                    tc::tmem_ld16(col, p);
+                    tc::tmem_wait_ld();
+                    tc::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&q_full[u & 1]);  // P is in registers: the buffer is free
+                    float su = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float x = xs[j * TC_M];
+                        if (restore && x == lambda) x = 0.f;
+                        float e = x - __uint_as_float(p[j]);
+                        e = (valid && j0 + j < cnt) ? e : 0.f;
+                        su = fmaf(e, e, su);
+                    }
+#pragma unroll
+                    for (int bb = 0; bb < RB; ++bb)
+                        if (bb == b) sacc[bb] += (double)su;
+                }
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&x_empty[s]);
+            }
+            // fixed-order reduction: lanes (shuffle tree), then the 16 quotient warps in warp order
+            double* red = reinterpret_cast<double*>(Xs);  // the X stages are idle now: [RB][QWARPS]
+            __syncwarp();
+            tc::named_bar_sync(2, TC_QWARPS * 32);  // every quotient warp is past its last X tile
+#pragma unroll
+            for (int b = 0; b < RB; ++b) {
+                double v = sacc[b];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                if (lane == 0) red[b * TC_QWARPS + (warp - TC_QW0)] = v;
+            }
+            tc::named_bar_sync(2, TC_QWARPS * 32);
+            if (warp == TC_QW0 && lane < nact) {
+                double t = 0.0;
+                for (int w = 0; w < TC_QWARPS; ++w) t += red[lane * TC_QWARPS + w];
+                double* dst = a.obj_partials + ((long long)s_act[lane] * a.nblocks + ob) * 2;
+                dst[0] = t * a.obj_weight * a.obj_weight;
+                dst[1] = t;
+            }
+        } else {
         float acc[RB][NC];
 #pragma unroll
         for (int b = 0; b < RB; ++b)
@@ -560,6 +630,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                 }
             }
         }
+        }
         __syncwarp();
     }
     tc::tc_fence_before_sync();
@@ -567,15 +638,15 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
     if (warp == 0) tc::tmem_dealloc<C::TCOLS>(tbase);
 }
 
-template <int K8, int N2, bool WIDE>
+template <int K8, int N2, bool WIDE, bool OBJ>
 cudaError_t launch_tc(const TiledPassArgs& a, int* d_errflag, cudaStream_t s) {
     using C = TcCfg<K8, N2, WIDE>;
     const int ngroups = (a.R + C::RB - 1) / C::RB;
     const long long grid = (long long)a.S * a.nblocks * ngroups;
     if (grid > 2147483647ll) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(tc_pass_kernel<K8, N2, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(tc_pass_kernel<K8, N2, WIDE, OBJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) return e;
-    tc_pass_kernel<K8, N2, WIDE><<<(unsigned)grid, C::THREADS, C::SMEM, s>>>(a, d_errflag);
+    tc_pass_kernel<K8, N2, WIDE, OBJ><<<(unsigned)grid, C::THREADS, C::SMEM, s>>>(a, d_errflag);
     return cudaGetLastError();
 }
 
@@ -598,10 +669,17 @@ bool tc_pass_supported(const TiledPassArgs& a) {
 }
 
 cudaError_t launch_tc_pass(const TiledPassArgs& a, int* d_errflag, cudaStream_t s) {
-    if (a.k <= 8) return launch_tc<8, 16, true>(a, d_errflag, s);
-    if (a.k <= 16) return launch_tc<16, 16, true>(a, d_errflag, s);
-    if (a.k <= 24) return launch_tc<24, 32, true>(a, d_errflag, s);
-    return launch_tc<32, 32, true>(a, d_errflag, s);
+    if (a.k <= 8) return launch_tc<8, 16, true, false>(a, d_errflag, s);
+    if (a.k <= 16) return launch_tc<16, 16, true, false>(a, d_errflag, s);
+    if (a.k <= 24) return launch_tc<24, 32, true, false>(a, d_errflag, s);
+    return launch_tc<32, 32, true, false>(a, d_errflag, s);
+}
+
+cudaError_t launch_tc_objective(const TiledPassArgs& a, int* d_errflag, cudaStream_t s) {
+    if (a.k <= 8) return launch_tc<8, 16, true, true>(a, d_errflag, s);
+    if (a.k <= 16) return launch_tc<16, 16, true, true>(a, d_errflag, s);
+    if (a.k <= 24) return launch_tc<24, 32, true, true>(a, d_errflag, s);
+    return launch_tc<32, 32, true, true>(a, d_errflag, s);
 }
 
 }  // namespace nmfk
