@@ -50,7 +50,26 @@ with nb.Context(local) as ctx2:
     o2 = nbdist.solve_rowsharded(ctx2, X[r0:r1], k, R, rank=rank, world=world, n_global=n, unique_id=nbdist.exchange_unique_id(rank),
                                  seed0=33, params=params)
 assert np.array_equal(o2["iters"], out["iters"]) and rel(o2["H"], out["H"]) < 1e-12
+# Float32: every rank runs the tcgen05 pass kernel on its rows (n_local % 4 == 0); numerators all-reduced in Float32
+n32, m32, k32, R32 = 2048 * world, 256, 16, 5
+X32 = synth.mixture(n32, m32, 4, seed=11, dtype=np.float32)
+W32, H32 = synth.philox_inits(44, R32, n32, k32, m32, dtype=np.float32)
+q0, q1 = nbdist.row_block(n32, rank, world)
+p32 = nb.default_params(maxiter=30)
+with nb.Context(local) as ctx3:
+    o32 = nbdist.solve_rowsharded(ctx3, X32[q0:q1], k32, R32, rank=rank, world=world, n_global=n32,
+                                  unique_id=nbdist.exchange_unique_id(rank), Winit_local=W32[:, q0:q1, :], Hinit=H32, params=p32)
+with nb.Context(local) as ctx4:
+    ctx4.set_X(X32)
+    b = ctx4.batch(k32, R32)
+    b.set_init(W32, H32)
+    ctx4.solve([b], nb.default_params(maxiter=30, engine=2))
+    r32 = b.get()
+    b.close()
+e32H, e32W = rel(o32["H"], r32["H"].astype(np.float64)), rel(o32["W_local"], r32["W"][:, q0:q1, :].astype(np.float64))
+assert np.array_equal(o32["iters"], r32["iters"]) and e32H < 1e-4 and e32W < 1e-4, (e32H, e32W)
 td.barrier()
 if rank == 0:
+    print("ROWSHARD F32 (tcgen05) OK relerr H=%.2e W=%.2e solve_ms=%.2f" % (e32H, e32W, o32["solve_ms"]))
     print("ROWSHARD OK world=%d iters=%s relerr H=%.2e W=%.2e obj=%.2e solve_ms=%.2f" % (world, out["iters"].tolist(), eH, eW, eo, out["solve_ms"]))
 td.destroy_process_group()
