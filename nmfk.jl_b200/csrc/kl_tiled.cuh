@@ -640,6 +640,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     if (sharded && a.normalize == 2) return cudaErrorNotSupported;
     // Float32 objective on the tensor cores: D = X, U = W, V = H (the W-update orientation), P = W H by MMA#1 and
     // (x - p)^2 by the quotient warps; partial sums per block of 128 rows like tiled_objective_kernel
+    const int wait_hint = getenv("NMFK_TC_WAIT_HINT_NS") ? atoi(getenv("NMFK_TC_WAIT_HINT_NS")) : 0;  // experiment knob
     auto obj_args = [&](int restore, int sel) {
         TiledPassArgs po{};
         po.D = a.X;
@@ -664,6 +665,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
         po.obj_weight = a.weight;
         po.obj_restore = restore;
         po.obj_sel = sel;
+        po.wait_hint_ns = wait_hint;
         return po;
     };
   // column sums of W would need another exchange
@@ -712,6 +714,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
         ph.has_nan = a.has_nan;
         ph.lambda = a.lambda;
         ph.ktmpl = kt;
+        ph.wait_hint_ns = wait_hint;
         pw = ph;
         pw.D = a.X;
         pw.U = a.W;

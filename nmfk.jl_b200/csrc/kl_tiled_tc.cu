@@ -53,7 +53,8 @@ struct TcCfg {
     static constexpr int NST = N2 == 16 ? 2 : 1;                      // MMA#2: Qhi * [Vhi ; Vlo] stacked along N
     static constexpr int ACOLS = NST * N2;                            // columns of one per-unit numerator buffer
     static constexpr int PQ = 2 * TS;                                 // one P/Q buffer: P -> Qhi | Qlo
-    static constexpr int ABASE = 2 * PQ, UBASE = ABASE + 2 * ACOLS;   // tensor-memory columns
+    static constexpr int NAB3 = 3;                                    // per-unit numerator buffers (drained 3 units later)
+    static constexpr int ABASE = 2 * PQ, UBASE = ABASE + NAB3 * ACOLS;  // tensor-memory columns
     static constexpr int PERB = 2 * K8;                               // U hi | U lo per restart
     static constexpr int NCQ = N2 / NCS;                              // numerator columns per quotient thread
     static constexpr int RBT = (TCOLS - UBASE) / PERB;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
     int* s_act = reinterpret_cast<int*>(tmem_slot + 1);  // [RB] active restarts of the group, then their count
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t hint = (uint32_t)a.wait_hint_ns;
     long long* const trc = (a.trace != nullptr && blockIdx.x == 0) ? a.trace : nullptr;
 #define TC_STAMP(role, unit, ev)                                                                    \
     do {                                                                                            \
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             const uint32_t row_bytes = (uint32_t)min(TC_M, a.nown - o0) * 4u;
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c % TC_NXS;
-                if (c >= TC_NXS) tc::mbar_wait(&x_empty[s], (uint32_t)((c / TC_NXS - 1) & 1), errflag, 10);
+                if (c >= TC_NXS) tc::mbar_wait_h(hint, &x_empty[s], (uint32_t)((c / TC_NXS - 1) & 1), errflag, 10);
                 const int t0 = t_begin + c * TC_TS;
                 const int cnt = min(TC_TS, t_end - t0);
                 if (tc::elect_one()) {
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             auto mma1 = [&](int u, int b) {
                 const int vb = u % TC_NVB;
                 TC_STAMP(1, u, 3);
-                tc::mbar_wait(&v_full[vb], (uint32_t)((u / TC_NVB) & 1), errflag, 20);
+                tc::mbar_wait_h(hint, &v_full[vb], (uint32_t)((u / TC_NVB) & 1), errflag, 20);
                 tc::tc_fence_after_sync();
                 TC_STAMP(1, u, 4);
                 const uint32_t d = tbase + (uint32_t)(u & 1) * C::PQ;
@@ -256,10 +258,10 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             auto mma2 = [&](int u) {
                 const int vb = u % TC_NVB;
                 TC_STAMP(1, u, 0);
-                tc::mbar_wait(&q_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 21);
+                tc::mbar_wait_h(hint, &q_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 21);
                 tc::tc_fence_after_sync();
                 TC_STAMP(1, u, 1);
-                const uint32_t d = tbase + C::ABASE + (uint32_t)(u & 1) * C::ACOLS;
+                const uint32_t d = tbase + C::ABASE + (uint32_t)(u % C::NAB3) * C::ACOLS;
                 const uint32_t qh = tbase + (uint32_t)(u & 1) * C::PQ, ql = qh + TC_TS;
                 const uint64_t bh = d2 + (uint64_t)((vb * C::V_BYTES) >> 4), bl = bh + (C::B2_BYTES >> 4);
                 if (tc::elect_one()) {
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             }
             for (int u = 0; u < total; ++u) {
                 if (OBJ) {  // no MMA#2: the P buffer is free once the quotient warps have read it
-                    tc::mbar_wait(&q_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 22);
+                    tc::mbar_wait_h(hint, &q_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 22);
                     tc::tc_fence_after_sync();
                 } else {
                     mma2(u);
@@ -364,7 +366,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             tc::named_bar_sync(1, NS);        // ... and everybody else's
             if (warp == 2) TC_STAMP(2, u, 1);
             const int vb = u % TC_NVB;
-            if (u >= TC_NVB) tc::mbar_wait(&v_empty[vb], (uint32_t)((u / TC_NVB - 1) & 1), errflag, 30);
+            if (u >= TC_NVB) tc::mbar_wait_h(hint, &v_empty[vb], (uint32_t)((u / TC_NVB - 1) & 1), errflag, 30);
             if (warp == 2) TC_STAMP(2, u, 2);
             unsigned char* base = Vs + (size_t)vb * C::V_BYTES;
             const float* raw = Raw + (size_t)(u % TC_NRAW) * RAWF;
@@ -462,11 +464,11 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c % TC_NXS;
                 const int cnt = min(TC_TS, t_end - (t_begin + c * TC_TS));
-                tc::mbar_wait(&x_full[s], (uint32_t)((c / TC_NXS) & 1), errflag, 40);
+                tc::mbar_wait_h(hint, &x_full[s], (uint32_t)((c / TC_NXS) & 1), errflag, 40);
                 const float* xs = Xs + (size_t)s * TC_TS * TC_M + (size_t)j0 * TC_M + o_loc;
                 for (int b = 0; b < nact; ++b, ++u) {
                     const uint32_t col = lane_base + (uint32_t)(u & 1) * C::PQ + j0;
-                    tc::mbar_wait(&p_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 41);
+                    tc::mbar_wait_h(hint, &p_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 41);
                     tc::tc_fence_after_sync();
                     uint32_t p[16];
                     tc::tmem_ld16(col, p);
@@ -516,11 +518,12 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
 #pragma unroll
             for (int c = 0; c < NC; ++c) acc[b][c] = 0.f;
         // numerators of unit uu -> registers of restart slot `target`, round-to-nearest adds.  No barrier of its own in the
-        // steady state: the tcgen05.commit behind p_full(u) also covers MMA#2(u-2), issued earlier by the same thread,
-        // so the numerators of unit u-2 are complete when P(u) is (their buffer is reused by MMA#2(u), after q_full(u)).
+        // steady state: the tcgen05.commit behind p_full(u-1) also covers MMA#2(u-3), issued earlier by the same thread,
+        // so once P(u-1) has been seen the numerators of unit u-3 are complete; their tensor-memory load is issued at
+        // the end of unit u-1 and overlaps the wait for P(u).  Buffer (u-3) % 3 is rewritten by MMA#2(u), after q_full(u).
         uint32_t v0[NC], v1[NC];
         auto drain_load = [&](int uu) {
-            const uint32_t col = lane_base + C::ABASE + (uint32_t)(uu & 1) * C::ACOLS + cs * NC;
+            const uint32_t col = lane_base + C::ABASE + (uint32_t)(uu % C::NAB3) * C::ACOLS + cs * NC;
             static_assert(NC == 4 || NC == 8, "numerator columns per quotient thread");
             if (NC == 4) {
                 tc::tmem_ld4(col, v0);
@@ -542,24 +545,23 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                     }
                 }
         };
-        int bm1 = 0, bm2 = 0;  // restart slots of units u-1 and u-2
+        int bm1 = 0, bm2 = 0, bm3 = 0;  // restart slots of units u-1, u-2, u-3
         int u = 0;
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % TC_NXS;
             const int cnt = min(TC_TS, t_end - (t_begin + c * TC_TS));
-            tc::mbar_wait(&x_full[s], (uint32_t)((c / TC_NXS) & 1), errflag, 40);
+            tc::mbar_wait_h(hint, &x_full[s], (uint32_t)((c / TC_NXS) & 1), errflag, 40);
             const float* xs = Xs + (size_t)s * TC_TS * TC_M + (size_t)j0 * TC_M + o_loc;
             for (int b = 0; b < nact; ++b, ++u) {
                 const uint32_t col = lane_base + (uint32_t)(u & 1) * C::PQ + j0;
                 if (warp == TC_QW0) TC_STAMP(0, u, 0);
-                tc::mbar_wait(&p_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 41);
+                tc::mbar_wait_h(hint, &p_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 41);
                 tc::tc_fence_after_sync();
                 if (warp == TC_QW0) TC_STAMP(0, u, 1);
                 uint32_t p[16], lo[16];
                 tc::tmem_ld16(col, p);
-                if (u >= 2) drain_load(u - 2);
-                tc::tmem_wait_ld();
-                if (u >= 2) drain_add(bm2);
+                tc::tmem_wait_ld();  // also covers the numerators of unit u-3 requested at the end of unit u-1
+                if (u >= 3) drain_add(bm3);
                 if (warp == TC_QW0) TC_STAMP(0, u, 2);
                 if (cnt == TC_TS) {
                     // (one MUFU.RCP per PAIR of quotients, r = 1/(p0 p1), was measured slower: this loop is bound by
@@ -589,17 +591,21 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&q_full[u & 1]);
                 if (warp == TC_QW0) TC_STAMP(0, u, 4);
+                if (u >= 2) drain_load(u - 2);  // complete since P(u) was seen; consumed in the next unit
                 if (warp == TC_QW0) TC_STAMP(0, u, 5);
+                bm3 = bm2;
                 bm2 = bm1;
                 bm1 = b;
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&x_empty[s]);
         }
-        // the last two units: wait for their own MMA#2
+        // tail: the load of unit total-3 is in flight; the last two units wait for the commit behind the last MMA#2
+        tc::tmem_wait_ld();
+        if (total >= 3) drain_add(bm3);
+        tc::mbar_wait_h(hint, &a_full[(total - 1) & 1], (uint32_t)(((total - 1) >> 1) & 1), errflag, 43);
+        tc::tc_fence_after_sync();
         for (int uu = max(0, total - 2); uu < total; ++uu) {
-            tc::mbar_wait(&a_full[uu & 1], (uint32_t)((uu >> 1) & 1), errflag, 43);
-            tc::tc_fence_after_sync();
             drain_load(uu);
             tc::tmem_wait_ld();
             drain_add(uu == total - 1 ? bm1 : bm2);

@@ -60,6 +60,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
     __trap();
 }
 
+// same with an explicit suspend-time hint (ns) when hint_ns != 0
+__device__ __forceinline__ void mbar_wait_h(uint32_t hint_ns, uint64_t* bar, uint32_t parity, int* errflag, int where) {
+    if (hint_ns == 0) return mbar_wait(bar, parity, errflag, where);
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+            : "memory");
+        if (ok) return;
+    }
+    if (errflag) atomicExch(errflag, where);
+    __threadfence_system();
+    __trap();
+}
+
 // ---- proxies / fences -----------------------------------------------------------------------
 // generic-proxy st.shared -> visible to the async proxy (tcgen05.mma / bulk copies reading smem)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
