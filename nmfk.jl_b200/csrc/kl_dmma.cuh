@@ -218,7 +218,10 @@ __device__ __forceinline__ int dmma_sigma(int c) { return c < 4 ? c : (c ^ 1); }
 // NT (1 or 2) consecutive 8-own x 8-step tiles, instruction streams interleaved.  For tile j:
 // vp1 + j*8*pitch -> V[t0+sigma(g)][q]; vp2a/vp2b -> V[t0+sigma(2q)][g], V[t0+sigma(2q+1)][g];
 // x[j][0..1] = this lane's X values at those two steps.  Tile j accumulates into set (SET0 + j) % SETS.
-template <int K, bool EXACT, int NT, int SET0>
+// MODE 0: fast reciprocal, no range check (the caller tests the accumulators for NaN and redoes the item);
+// MODE 1: IEEE divisions, steps beyond the end masked; MODE 2: fast reciprocal with a warp-uniform range
+// check that falls back to IEEE divisions (tiled engine: an item cannot be redone once its V chunks are gone).
+template <int K, int MODE, int NT, int SET0>
 __device__ __forceinline__ void dmma_tiles(DmmaRegs<K>& R, const double (&x)[NT][2], const double* __restrict__ vp1,
                                            const double* __restrict__ vp2a, const double* __restrict__ vp2b, int g,
                                            const bool (&in)[NT][2], bool hi_ok) {
@@ -259,9 +262,18 @@ __device__ __forceinline__ void dmma_tiles(DmmaRegs<K>& R, const double (&x)[NT]
         for (int j = 0; j < NT; ++j) dmma884(p[j], R.ua[kc], vp1[j * TS + kc * 4]);
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-        if constexpr (EXACT) {
+        if constexpr (MODE == 1) {
             qv[j][0] = in[j][0] ? div_cold<double>(x[j][0], p[j][0]) : 0.0;  // steps beyond the end contribute nothing
             qv[j][1] = in[j][1] ? div_cold<double>(x[j][1], p[j][1]) : 0.0;
+        } else if constexpr (MODE == 2) {
+            qv[j][0] = div_fast(x[j][0], p[j][0]);
+            qv[j][1] = div_fast(x[j][1], p[j][1]);
+            const bool ok = p[j][0] > 1e-290 && p[j][0] < 1e290 && p[j][1] > 1e-290 && p[j][1] < 1e290 &&
+                            x[j][0] < 1e290 && x[j][1] < 1e290;  // false for NaN operands too
+            if (__any_sync(0xffffffffu, !ok)) {
+                qv[j][0] = div_cold<double>(x[j][0], p[j][0]);
+                qv[j][1] = div_cold<double>(x[j][1], p[j][1]);
+            }
         } else {
             qv[j][0] = div_fast(x[j][0], p[j][0]);
             qv[j][1] = div_fast(x[j][1], p[j][1]);
@@ -390,7 +402,7 @@ __device__ __forceinline__ void dmma_half_update(const double* __restrict__ D, i
                 if (tile < te) {  // warp-uniform
                     double x[1][2];
                     take(u, tile, x[0]);
-                    dmma_tiles<K, false, 1, 0>(R, x, vp1, vp2a, vp2b, g, inall, hi_ok);
+                    dmma_tiles<K, 0, 1, 0>(R, x, vp1, vp2a, vp2b, g, inall, hi_ok);
                     xp += 8;
                     vp1 += 8 * pitch;
                     vp2a += 8 * pitch;
@@ -412,7 +424,7 @@ __device__ __forceinline__ void dmma_half_update(const double* __restrict__ D, i
                 const double* vt = V + (size_t)tile * (8 * pitch);
                 const double xx[1][2] = {{x0, x1}};
                 const bool in1[1][2] = {{ta < nred, tb2 < nred}};
-                dmma_tiles<K, true, 1, 0>(R, xx, vt + off1, vt + off2a, vt + off2b, g, in1, hi_ok);
+                dmma_tiles<K, 1, 1, 0>(R, xx, vt + off1, vt + off2a, vt + off2b, g, in1, hi_ok);
             }
             R.finish();
         }

@@ -555,11 +555,18 @@ cudaError_t dispatch_tiled_combine(const TiledPassArgs& a, void* red, cudaStream
     NMFK_DISPATCH_K(launch_tiled_combine_k, TX, TC, kt, a, red, s)
 }
 // use_tc: Float32 without NaN -> the tcgen05 kernel of kl_tiled_tc.cu (a.nblocks counts 128-index tiles)
+// use_td: Float64 without NaN, k >= 4 -> the DMMA kernel of kl_tiled_dmma.cu (a.nblocks counts 128-index blocks, a.D is
+// the step-contiguous copy of the data)
 template <typename TX, typename TC>
-cudaError_t dispatch_tiled_pass(const TiledPassArgs& a, void* red, cudaStream_t s, bool use_tc, int* errflag) {
+cudaError_t dispatch_tiled_pass(const TiledPassArgs& a, void* red, cudaStream_t s, bool use_tc, int* errflag, bool use_td = false) {
     const int kt = resident_template_k(a.k);
     if (use_tc) {
         cudaError_t e = launch_tc_pass(a, errflag, s);
+        if (e != cudaSuccess || a.partial == nullptr) return e;
+        return dispatch_tiled_combine<TX, TC>(a, red, s);
+    }
+    if (use_td) {
+        cudaError_t e = launch_tiled_dmma_pass(a, s);
         if (e != cudaSuccess || a.partial == nullptr) return e;
         return dispatch_tiled_combine<TX, TC>(a, red, s);
     }
@@ -605,15 +612,17 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
         probe.D = a.X;
         use_tc = use_tc && tc_pass_supported(probe);
     }
-    const int ownper = use_tc ? 128 : kTiledThreads;
+    // Float64 without NaN, k >= 4: both half-updates run on the FP64 tensor pipe (kl_tiled_dmma.cu)
+    const bool use_td = std::is_same<TX, double>::value && std::is_same<TC, double>::value && a.tiled_tc && !a.has_nan && k >= 4;
+    const int ownper = use_tc ? 128 : (use_td ? tiled_dmma_own() : kTiledThreads);
     const int units = use_tc ? (R + tc_pass_group(k) - 1) / tc_pass_group(k) : R;  // CTAs per own block and slice
     const int nblkH = (m + ownper - 1) / ownper;  // H-update: own = columns
     const int nblkW = (n + ownper - 1) / ownper;  // W-update: own = rows
     constexpr int TCH = TiledCfg<TX>::TCH;
     auto slices = [&](int nblk, int nred) {
-        const long long target = (use_tc ? 3ll * tc_pass_ctas_per_sm(k) : 4ll) * sms;
+        const long long target = (use_tc ? 3ll * tc_pass_ctas_per_sm(k) : (use_td ? 3ll : 4ll)) * sms;
         long long S = (target + (long long)nblk * units - 1) / ((long long)nblk * units);
-        const long long smax = std::max(1, nred / ((use_tc ? tc_pass_chunk(k) : TCH) * 8));
+        const long long smax = std::max(1, nred / ((use_tc ? tc_pass_chunk(k) : (use_td ? tiled_dmma_chunk() : TCH)) * 8));
         if (S > smax) S = smax;
         if (S < 1) S = 1;
         return (int)S;
@@ -690,7 +699,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     if (any_running) {
         // restarts of one batch advance in lockstep
         TiledPassArgs ph{}, pw{};
-        ph.D = a.Xt;
+        ph.D = use_td ? a.X : a.Xt;  // the DMMA kernel reads the STEP-contiguous copy, the others the OWN-contiguous one
         ph.U = a.H;
         ph.V = a.W;
         ph.den = den;
@@ -716,7 +725,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
         ph.ktmpl = kt;
         ph.wait_hint_ns = wait_hint;
         pw = ph;
-        pw.D = a.X;
+        pw.D = use_td ? a.Xt : a.X;
         pw.U = a.W;
         pw.V = a.H;
         pw.partial = SW > 1 ? partial : nullptr;
@@ -765,7 +774,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
             if (!a.Hfixed) {
                 tiled_sums_kernel<TC><<<dim3(k, R), 256, 0, s>>>(a.W, (long long)n * k, 1, n, n, a.st, den);
                 NMFK_TRY(cudaGetLastError());
-                NMFK_TRY((dispatch_tiled_pass<TX, TC>(ph, red, s, use_tc, h_active + 1)));
+                NMFK_TRY((dispatch_tiled_pass<TX, TC>(ph, red, s, use_tc, h_active + 1, use_td)));
                 *launches += 2 + (SH > 1 || sharded);
                 if (d_trace != nullptr) {
                     std::vector<long long> ht(3 * 64 * 8);
@@ -789,7 +798,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
             if (!a.Wfixed) {
                 tiled_sums_kernel<TC><<<dim3(k, R), 256, 0, s>>>(a.H, (long long)k * m, k, 1, m, a.st, den);
                 NMFK_TRY(cudaGetLastError());
-                NMFK_TRY((dispatch_tiled_pass<TX, TC>(pw, nullptr, s, use_tc, h_active + 1)));
+                NMFK_TRY((dispatch_tiled_pass<TX, TC>(pw, nullptr, s, use_tc, h_active + 1, use_td)));
                 *launches += 2 + (SW > 1);
             }
             if (a.has_nan) {

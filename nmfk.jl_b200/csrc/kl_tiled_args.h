@@ -40,4 +40,11 @@ cudaError_t launch_tc_pass(const TiledPassArgs& a, int* d_errflag, cudaStream_t 
 // Float32 objective sums on the same machinery (MMA#1 only): a = the W-update arguments (D = X, U = W, V = H), S = 1
 cudaError_t launch_tc_objective(const TiledPassArgs& a, int* d_errflag, cudaStream_t s);
 
+// Float64 half-update on the FP64 tensor pipe (kl_tiled_dmma.cu): DMMA fragment formulation of the resident engine with
+// the other factor streamed through shared memory.  a.D = STEP-contiguous data (H-update: X, W-update: X^T),
+// nblocks = ceil(nown / tiled_dmma_own()), 4 <= k <= 32, no NaN.
+int tiled_dmma_own();
+int tiled_dmma_chunk();
+cudaError_t launch_tiled_dmma_pass(const TiledPassArgs& a, cudaStream_t s);
+
 }  // namespace nmfk
