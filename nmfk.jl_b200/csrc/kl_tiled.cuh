@@ -652,7 +652,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     const int wait_hint = getenv("NMFK_TC_WAIT_HINT_NS") ? atoi(getenv("NMFK_TC_WAIT_HINT_NS")) : 0;  // experiment knob
     auto obj_args = [&](int restore, int sel) {
         TiledPassArgs po{};
-        po.D = a.X;
+        po.D = use_td ? a.Xt : a.X;  // the DMMA kernel reads the step-contiguous copy
         po.U = a.W;
         po.V = a.H;
         po.st = a.st;
@@ -811,6 +811,8 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
             if (it % a.check_every == 0) {
                 if (use_tc) {
                     NMFK_TRY(launch_tc_objective(obj_args(0, 0), h_active + 1, s));
+                } else if (use_td) {
+                    NMFK_TRY(launch_tiled_dmma_objective(obj_args(0, 0), s));
                 } else {
                     dim3 g(nblkObj, R);
                     tiled_objective_kernel<TX, TC><<<g, 128, (size_t)k * 128 * sizeof(TC), s>>>(
@@ -851,6 +853,8 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
         // post-run objective on the restored X + normalisation for restarts that stopped in this call
         if (use_tc) {
             NMFK_TRY(launch_tc_objective(obj_args(1, 1), h_active + 1, s));
+        } else if (use_td) {
+            NMFK_TRY(launch_tiled_dmma_objective(obj_args(1, 1), s));
         } else {
             dim3 g(nblkObj, R);
             tiled_objective_kernel<TX, TC><<<g, 128, (size_t)k * 128 * sizeof(TC), s>>>(

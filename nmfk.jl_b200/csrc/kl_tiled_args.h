@@ -46,5 +46,6 @@ cudaError_t launch_tc_objective(const TiledPassArgs& a, int* d_errflag, cudaStre
 int tiled_dmma_own();
 int tiled_dmma_chunk();
 cudaError_t launch_tiled_dmma_pass(const TiledPassArgs& a, cudaStream_t s);
+cudaError_t launch_tiled_dmma_objective(const TiledPassArgs& a, cudaStream_t s);
 
 }  // namespace nmfk

@@ -27,7 +27,28 @@ constexpr int TD_OWN = TD_WARPS * 8;   // own indices per CTA
 constexpr int TD_TCH = 64;             // steps per staged chunk (8 tiles)
 constexpr int TD_ST = 3;               // cp.async stages
 
+// P = U V^T for one tile (the first product of dmma_tiles): p[e] = value at (own g, step sigma(2q+e))
 template <int K>
+__device__ __forceinline__ void dmma_p_tile(const DmmaRegs<K>& R, const double* __restrict__ vp1, const double* __restrict__ vp2a,
+                                            const double* __restrict__ vp2b, int g, double (&p)[2]) {
+    using C = DmmaCfg<K>;
+    p[0] = p[1] = 0.0;
+    if constexpr (C::NSP > 0) {
+        const double* vpsa = vp2a + (C::C0 - g);
+        const double* vpsb = vp2b + (C::C0 - g);
+#pragma unroll
+        for (int i = 0; i < C::NSP; ++i) {
+            p[0] = fma(R.us[i], vpsa[C::KD - C::C0 + i], p[0]);
+            p[1] = fma(R.us[i], vpsb[C::KD - C::C0 + i], p[1]);
+        }
+    }
+#pragma unroll
+    for (int kc = 0; kc < C::KCD; ++kc) dmma884(p, R.ua[kc], vp1[kc * 4]);
+}
+
+// OBJ = true: objective mode (NMFkMultiplicative.jl:74,125): only P = U V^T, the lanes accumulate (x - p)^2; nothing is
+// written to the factors.  a = the W-update arguments with S = 1; partial sums per block of 128 rows.
+template <int K, bool OBJ>
 __global__ void __launch_bounds__(TD_THREADS, 1) tiled_dmma_pass_kernel(const TiledPassArgs a) {
     using C = DmmaCfg<K>;
     constexpr int pitch = C::pitch;
@@ -42,8 +63,15 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tiled_dmma_pass_kernel(const Ti
     const int rest = blockIdx.x / a.R;
     const int ob = rest % a.nblocks;
     const int slice = rest / a.nblocks;
-    if (a.st[r].stop != 0) return;  // finished restarts are frozen
+    {
+        const bool stopped = a.st[r].stop != 0;
+        const bool take = (OBJ && a.obj_sel == 1) ? (stopped && a.st[r].done == 0) : !stopped;  // finished restarts are frozen
+        if (!take) return;
+    }
     const int k = a.k, nown = a.nown, nred = a.nred;
+    double ssum = 0.0;
+    const double lambda = a.lambda;
+    const bool restore = OBJ && a.obj_restore != 0;
 
     const double* D = static_cast<const double*>(a.D);  // element (o, t) at D[t + o * nred]
     double* U = static_cast<double*>(a.U) + (long long)r * a.u_rstride;
@@ -146,13 +174,42 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tiled_dmma_pass_kernel(const Ti
                 else if (tile + PF < te)
                     xq[u] = load_tail(xp + PF * 8, tile + PF);
                 const double* vt = vb + (size_t)u * 8 * pitch;
-                dmma_tiles<K, 2, 1, 0>(R, x, vt + off1, vt + off2a, vt + off2b, g, inall, hi_ok);
+                if constexpr (OBJ) {
+                    double p[2];
+                    dmma_p_tile<K>(R, vt + off1, vt + off2a, vt + off2b, g, p);
+                    double x0 = x[0][0], x1 = x[0][1];
+                    if (restore) {
+                        x0 = (x0 == lambda) ? 0.0 : x0;
+                        x1 = (x1 == lambda) ? 0.0 : x1;
+                    }
+                    const double e0 = (rvalid && tile * 8 + sa < nred) ? x0 - p[0] : 0.0;
+                    const double e1 = (rvalid && tile * 8 + sb < nred) ? x1 - p[1] : 0.0;
+                    ssum = fma(e0, e0, ssum);
+                    ssum = fma(e1, e1, ssum);
+                } else {
+                    dmma_tiles<K, 2, 1, 0>(R, x, vt + off1, vt + off2a, vt + off2b, g, inall, hi_ok);
+                }
                 xp += 8;
                 ++tile;
             }
         }
     }
     cp_async_wait<0>();
+    if constexpr (OBJ) {
+        // fixed-order reduction: lanes (shuffle tree), then the 16 warps in warp order
+        __shared__ double red[TD_WARPS];
+        ssum = warp_sum(ssum);
+        if (lane == 0) red[warp] = ssum;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < TD_WARPS; ++w) t += red[w];
+            double* dst = a.obj_partials + ((long long)r * a.nblocks + ob) * 2;
+            dst[0] = t * a.obj_weight * a.obj_weight;
+            dst[1] = t;
+        }
+        return;
+    }
     R.finish();
     if (!rvalid) return;
     if (a.partial == nullptr) {
@@ -175,15 +232,35 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tiled_dmma_pass_kernel(const Ti
     }
 }
 
-template <int K>
+template <int K, bool OBJ>
 cudaError_t launch_td(const TiledPassArgs& a, cudaStream_t s) {
     const size_t smem = (size_t)TD_ST * TD_TCH * DmmaCfg<K>::pitch * sizeof(double);
     const long long grid = (long long)a.S * a.nblocks * a.R;
     if (grid > 2147483647ll) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(tiled_dmma_pass_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tiled_dmma_pass_kernel<K, OBJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tiled_dmma_pass_kernel<K><<<(unsigned)grid, TD_THREADS, smem, s>>>(a);
+    tiled_dmma_pass_kernel<K, OBJ><<<(unsigned)grid, TD_THREADS, smem, s>>>(a);
     return cudaGetLastError();
+}
+
+template <bool OBJ>
+cudaError_t dispatch_td(const TiledPassArgs& a, cudaStream_t s) {
+    switch (a.ktmpl) {
+        case 4: return launch_td<4, OBJ>(a, s);
+        case 5: return launch_td<5, OBJ>(a, s);
+        case 6: return launch_td<6, OBJ>(a, s);
+        case 7: return launch_td<7, OBJ>(a, s);
+        case 8: return launch_td<8, OBJ>(a, s);
+        case 9: return launch_td<9, OBJ>(a, s);
+        case 10: return launch_td<10, OBJ>(a, s);
+        case 11: return launch_td<11, OBJ>(a, s);
+        case 12: return launch_td<12, OBJ>(a, s);
+        case 16: return launch_td<16, OBJ>(a, s);
+        case 20: return launch_td<20, OBJ>(a, s);
+        case 24: return launch_td<24, OBJ>(a, s);
+        case 32: return launch_td<32, OBJ>(a, s);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 }  // namespace
@@ -193,23 +270,8 @@ int tiled_dmma_chunk() { return TD_TCH; }
 
 // a.k in 4..32 (smaller k are all-DFMA in the resident formulation and stay on the scalar pass); K = the template K of
 // the combine kernel (resident_template_k), a.nblocks = ceil(nown / 128), a.D step-contiguous
-cudaError_t launch_tiled_dmma_pass(const TiledPassArgs& a, cudaStream_t s) {
-    switch (a.ktmpl) {
-        case 4: return launch_td<4>(a, s);
-        case 5: return launch_td<5>(a, s);
-        case 6: return launch_td<6>(a, s);
-        case 7: return launch_td<7>(a, s);
-        case 8: return launch_td<8>(a, s);
-        case 9: return launch_td<9>(a, s);
-        case 10: return launch_td<10>(a, s);
-        case 11: return launch_td<11>(a, s);
-        case 12: return launch_td<12>(a, s);
-        case 16: return launch_td<16>(a, s);
-        case 20: return launch_td<20>(a, s);
-        case 24: return launch_td<24>(a, s);
-        case 32: return launch_td<32>(a, s);
-        default: return cudaErrorInvalidValue;
-    }
-}
+cudaError_t launch_tiled_dmma_pass(const TiledPassArgs& a, cudaStream_t s) { return dispatch_td<false>(a, s); }
+// objective sums: a = the W-update arguments (D = X^T step-contiguous, U = W, V = H), S = 1
+cudaError_t launch_tiled_dmma_objective(const TiledPassArgs& a, cudaStream_t s) { return dispatch_td<true>(a, s); }
 
 }  // namespace nmfk
