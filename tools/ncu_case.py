@@ -26,6 +26,13 @@ with nb.Context(0) as ctx:
         b.init_random(1)
         ctx.solve([b], nb.default_params(maxiter=2, engine=2))
         print("tc tiled ms=%.3f" % ctx.last_solve_ms)
+    elif mode == "td":  # DMMA Float64 tiled pass: td n m k R
+        n, m, k, R = (int(v) for v in sys.argv[2:6])
+        ctx.set_X(synth.mixture(n, m, 8, seed=3))
+        b = ctx.batch(k, R)
+        b.init_random(1)
+        ctx.solve([b], nb.default_params(maxiter=2, engine=2))
+        print("dmma tiled ms=%.3f" % ctx.last_solve_ms)
     else:
         ctx.set_X(synth.mixture(20000, 1000, 8, seed=3))
         b = ctx.batch(16, 16)
