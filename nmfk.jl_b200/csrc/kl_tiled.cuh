@@ -841,7 +841,13 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
                 c.tol = a.tol;
                 c.tolOF = a.tolOF;
                 c.eps_clamp = a.eps_clamp;
-                tiled_check_kernel<TC><<<R, 256, (size_t)(m + k) * sizeof(int), s>>>(c);
+                {
+                    // canonical co-clustering labels of the m columns live in shared memory (m <= ~58000)
+                    const size_t csm = (size_t)(m + k) * sizeof(int);
+                    if (csm > 48 * 1024)
+                        NMFK_TRY(cudaFuncSetAttribute(tiled_check_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+                    tiled_check_kernel<TC><<<R, 256, csm, s>>>(c);
+                }
                 NMFK_TRY(cudaGetLastError());
                 *launches += 2;
                 need_guard = true;

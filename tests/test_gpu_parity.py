@@ -438,3 +438,30 @@ def test_tc_tiled_frozen_restarts_and_stop_rule(ctx):
     assert np.array_equal(res[2]["stop_reason"], res[4]["stop_reason"])
     assert np.max(np.abs(res[2]["iters"].astype(int) - res[4]["iters"].astype(int))) <= 10  # one check period
     assert np.allclose(res[2]["obj_norm"], res[4]["obj_norm"], rtol=5e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# Float64 tiled engine on the FP64 tensor pipe (kl_tiled_dmma.cu): engine=2 takes this path for Float64 data
+# without NaN and 4 <= k <= 32; engine=4 forces the scalar-FMA pass.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,m,k,R", [(20000, 600, 32, 3), (1001, 5001, 5, 4), (3000, 257, 13, 5), (130, 30000, 8, 2)])
+def test_tiled_dmma_matches_scalar_pass(ctx, n, m, k, R):
+    """Sliced reductions, odd sizes (unaligned X tiles), padded k, edge blocks: DMMA pass + DMMA objective against the
+    scalar-FMA pass after a fixed number of iterations, and against the oracle for the first restart."""
+    X = synth.mixture(n, m, 4, seed=21)
+    W0, H0 = synth.philox_inits(91, R, n, k, m)
+    ctx.set_X(X)
+    res = {}
+    for eng in (4, 2):
+        b = ctx.batch(k, R)
+        b.set_init(W0, H0)
+        ctx.solve([b], nb.default_params(engine=eng, maxiter=12, normalize=0))
+        res[eng] = b.get()
+        b.close()
+    assert relerr(res[2]["W"], res[4]["W"]) < 1e-10 and relerr(res[2]["H"], res[4]["H"]) < 1e-10
+    assert np.allclose(res[2]["obj_norm"], res[4]["obj_norm"], rtol=1e-10)
+    assert np.allclose(res[2]["obj_ssq"], res[4]["obj_ssq"], rtol=1e-10)
+    if n * m <= 6e6:
+        Xc = np.array(X, dtype=np.float64, order="F", copy=True)
+        W, H, _ = o.nmf_multiplicative(Xc, k, Winit=W0[0].copy(), Hinit=H0[0].copy(), maxiter=12)
+        assert relerr(res[2]["W"][0], W) < RTOL64 and relerr(res[2]["H"][0], H) < RTOL64
