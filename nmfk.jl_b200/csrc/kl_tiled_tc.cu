@@ -518,9 +518,8 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
 #pragma unroll
             for (int c = 0; c < NC; ++c) acc[b][c] = 0.f;
         // numerators of unit uu -> registers of restart slot `target`, round-to-nearest adds.  No barrier of its own in the
-        // steady state: the tcgen05.commit behind p_full(u-1) also covers MMA#2(u-3), issued earlier by the same thread,
-        // so once P(u-1) has been seen the numerators of unit u-3 are complete; their tensor-memory load is issued at
-        // the end of unit u-1 and overlaps the wait for P(u).  Buffer (u-3) % 3 is rewritten by MMA#2(u), after q_full(u).
+        // steady state: the tcgen05.commit behind p_full(u) also covers MMA#2(u-2), issued earlier by the same thread,
+        // so once P(u) has been seen the numerators of unit u-2 are complete.
         uint32_t v0[NC], v1[NC];
         auto drain_load = [&](int uu) {
             const uint32_t col = lane_base + C::ABASE + (uint32_t)(uu % C::NAB3) * C::ACOLS + cs * NC;
@@ -545,7 +544,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                     }
                 }
         };
-        int bm1 = 0, bm2 = 0, bm3 = 0;  // restart slots of units u-1, u-2, u-3
+        int bm1 = 0, bm2 = 0;  // restart slots of units u-1, u-2
         int u = 0;
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % TC_NXS;
@@ -560,8 +559,11 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                 if (warp == TC_QW0) TC_STAMP(0, u, 1);
                 uint32_t p[16], lo[16];
                 tc::tmem_ld16(col, p);
-                tc::tmem_wait_ld();  // also covers the numerators of unit u-3 requested at the end of unit u-1
-                if (u >= 3) drain_add(bm3);
+                tc::tmem_wait_ld();
+                // the numerators of unit u-2 (complete: the commit behind p_full(u) covers MMA#2(u-2)) are fetched while
+                // this unit is divided: the tensor pipe is quiet then (MMA#2(u) waits for q_full(u)), and a tensor-memory
+                // load issued while MMAs run was measured ~300 clk slower
+                if (u >= 2) drain_load(u - 2);
                 if (warp == TC_QW0) TC_STAMP(0, u, 2);
                 if (cnt == TC_TS) {
                     // (one MUFU.RCP per PAIR of quotients, r = 1/(p0 p1), was measured slower: this loop is bound by
@@ -583,6 +585,10 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                         p[j] = h;
                     }
                 }
+                if (u >= 2) {
+                    tc::tmem_wait_ld();
+                    drain_add(bm2);
+                }
                 if (warp == TC_QW0) TC_STAMP(0, u, 3);
                 tc::tmem_st16(col, p);
                 tc::tmem_st16(col + TC_TS, lo);
@@ -591,18 +597,14 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&q_full[u & 1]);
                 if (warp == TC_QW0) TC_STAMP(0, u, 4);
-                if (u >= 2) drain_load(u - 2);  // complete since P(u) was seen; consumed in the next unit
                 if (warp == TC_QW0) TC_STAMP(0, u, 5);
-                bm3 = bm2;
                 bm2 = bm1;
                 bm1 = b;
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&x_empty[s]);
         }
-        // tail: the load of unit total-3 is in flight; the last two units wait for the commit behind the last MMA#2
-        tc::tmem_wait_ld();
-        if (total >= 3) drain_add(bm3);
+        // tail: the last two units wait for the commit behind the last MMA#2
         tc::mbar_wait_h(hint, &a_full[(total - 1) & 1], (uint32_t)(((total - 1) >> 1) & 1), errflag, 43);
         tc::tc_fence_after_sync();
         for (int uu = max(0, total - 2); uu < total; ++uu) {
