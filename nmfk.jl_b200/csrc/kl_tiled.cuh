@@ -329,7 +329,23 @@ struct TiledCheckArgs {
     int maxbad, stopconv;
     double tol, tolOF, eps_clamp;
     int* active_count;
+    int w_clamped;           // 1: W was clamped by tiled_clampW_kernel (tall matrices: n*k elements per restart)
 };
+
+// W = max(W, eps()) of :100 for every restart that goes on (running and objective >= tol: a restart that stops on the
+// tolerance keeps its unclamped factors, :75-78), spread over the whole GPU: one CTA per restart is 22 ms at n = 500 000.
+// obj2[2r] is the SAME objective sum the check kernel reads, so the two kernels take the same decision.
+template <typename TC>
+__global__ void __launch_bounds__(256) tiled_clampW_kernel(TC* __restrict__ Wst, long long nk, const UnitState* st,
+                                                            const double* __restrict__ obj2, double tol, TC epsc) {
+    const int r = blockIdx.y;
+    if (st[r].stop != 0 || obj2[2 * r] < tol) return;
+    TC* W = Wst + (long long)r * nk;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nk; e += (long long)gridDim.x * blockDim.x) {
+        const TC v = W[e];
+        W[e] = (v != v) ? v : (v < epsc ? epsc : v);
+    }
+}
 
 // the every-10th-iteration block of NMFmultiplicative (:73-116) for one restart per CTA
 template <typename TC>
@@ -385,10 +401,11 @@ __global__ void __launch_bounds__(256) tiled_check_kernel(const TiledCheckArgs a
         return;
     }
     const TC epsc = (TC)a.eps_clamp;
-    for (long long e = tid; e < (long long)n * k; e += NT) {
-        const TC v = W[e];
-        W[e] = (v != v) ? v : (v < epsc ? epsc : v);
-    }
+    if (!a.w_clamped)
+        for (long long e = tid; e < (long long)n * k; e += NT) {
+            const TC v = W[e];
+            W[e] = (v != v) ? v : (v < epsc ? epsc : v);
+        }
     for (long long e = tid; e < (long long)k * m; e += NT) {
         const TC v = H[e];
         H[e] = (v != v) ? v : (v < epsc ? epsc : v);
@@ -680,10 +697,8 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
   // column sums of W would need another exchange
 
     NMFK_TRY(cudaMalloc(&den, ((size_t)R * 32 + redsz) * sizeof(TC)));
-    if (sharded) {
-        red = den + (size_t)R * 32;
-        NMFK_TRY(cudaMalloc(&obj2, (size_t)R * 2 * sizeof(double)));
-    }
+    if (sharded) red = den + (size_t)R * 32;
+    NMFK_TRY(cudaMalloc(&obj2, (size_t)R * 2 * sizeof(double)));
     if (psz) NMFK_TRY(cudaMalloc(&partial, psz * sizeof(TC)));
     NMFK_TRY(cudaMalloc(&objp, (size_t)R * nblkObj * 2 * sizeof(double)));
     NMFK_TRY(cudaMalloc(&d_active, sizeof(int)));
@@ -819,10 +834,17 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
                         (const TX*)a.X, n, m, k, (const TC*)a.W, (const TC*)a.H, a.st, (TC)a.lambda, 0, 1, a.weight, objp);
                 }
                 NMFK_TRY(cudaGetLastError());
-                if (sharded) {  // the objective is a sum over all rows
-                    tiled_objsum_kernel<<<(R + 127) / 128, 128, 0, s>>>(objp, nblkObj, R, obj2);
+                // per-restart objective sums in block order (and, row-sharded, over all ranks)
+                tiled_objsum_kernel<<<(R + 127) / 128, 128, 0, s>>>(objp, nblkObj, R, obj2);
+                NMFK_TRY(cudaGetLastError());
+                ++*launches;
+                if (sharded) NMFK_TRY(sh->allreduce(sh->comm, obj2, (size_t)R * 2, 1, s));
+                const bool wide_clamp = (long long)n * k >= (1ll << 18) && !a.Wfixed;
+                if (wide_clamp) {
+                    const long long nk = (long long)n * k;
+                    dim3 g((unsigned)std::min<long long>((nk + 2047) / 2048, 4096), R);
+                    tiled_clampW_kernel<TC><<<g, 256, 0, s>>>((TC*)a.W, nk, a.st, obj2, a.tol, (TC)a.eps_clamp);
                     NMFK_TRY(cudaGetLastError());
-                    NMFK_TRY(sh->allreduce(sh->comm, obj2, (size_t)R * 2, 1, s));
                     ++*launches;
                 }
                 TiledCheckArgs c{};
@@ -830,11 +852,12 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
                 c.H = a.H;
                 c.st = a.st;
                 c.canon = a.canon;
-                c.partials = sharded ? obj2 : objp;
+                c.partials = obj2;
                 c.n = n;
                 c.m = m;
                 c.k = k;
-                c.nblk = sharded ? 1 : nblkObj;
+                c.nblk = 1;
+                c.w_clamped = wide_clamp ? 1 : 0;
                 c.it = it;
                 c.maxbad = a.maxbad;
                 c.stopconv = a.stopconv;
