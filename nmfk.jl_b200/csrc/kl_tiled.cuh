@@ -666,7 +666,9 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     if (sharded && a.normalize == 2) return cudaErrorNotSupported;
     // Float32 objective on the tensor cores: D = X, U = W, V = H (the W-update orientation), P = W H by MMA#1 and
     // (x - p)^2 by the quotient warps; partial sums per block of 128 rows like tiled_objective_kernel
-    const int wait_hint = getenv("NMFK_TC_WAIT_HINT_NS") ? atoi(getenv("NMFK_TC_WAIT_HINT_NS")) : 0;  // experiment knob
+    // nanosleep between barrier polls of the roles that run ahead of the critical path: low 16 bits = X producer,
+    // high 16 bits = V stagers (NMFK_TC_WAIT_HINT_NS overrides; 64 / 32 ns measured best or equal on C3, C3 k=32, C5)
+    const int wait_hint = getenv("NMFK_TC_WAIT_HINT_NS") ? atoi(getenv("NMFK_TC_WAIT_HINT_NS")) : ((32 << 16) | 64);
     auto obj_args = [&](int restore, int sel) {
         TiledPassArgs po{};
         po.D = use_td ? a.Xt : a.X;  // the DMMA kernel reads the step-contiguous copy

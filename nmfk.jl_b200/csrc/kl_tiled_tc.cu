@@ -210,7 +210,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             const uint32_t row_bytes = (uint32_t)min(TC_M, a.nown - o0) * 4u;
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c % TC_NXS;
-                if (c >= TC_NXS) tc::mbar_wait_h(hint, &x_empty[s], (uint32_t)((c / TC_NXS - 1) & 1), errflag, 10);
+                if (c >= TC_NXS) tc::mbar_wait_relaxed(&x_empty[s], (uint32_t)((c / TC_NXS - 1) & 1), hint & 0xffffu, errflag, 10);
                 const int t0 = t_begin + c * TC_TS;
                 const int cnt = min(TC_TS, t_end - t0);
                 if (tc::elect_one()) {
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             auto mma1 = [&](int u, int b) {
                 const int vb = u % TC_NVB;
                 TC_STAMP(1, u, 3);
-                tc::mbar_wait_h(hint, &v_full[vb], (uint32_t)((u / TC_NVB) & 1), errflag, 20);
+                tc::mbar_wait_h(0u, &v_full[vb], (uint32_t)((u / TC_NVB) & 1), errflag, 20);
                 tc::tc_fence_after_sync();
                 TC_STAMP(1, u, 4);
                 const uint32_t d = tbase + (uint32_t)(u & 1) * C::PQ;
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             auto mma2 = [&](int u) {
                 const int vb = u % TC_NVB;
                 TC_STAMP(1, u, 0);
-                tc::mbar_wait_h(hint, &q_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 21);
+                tc::mbar_wait_h(0u, &q_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 21);
                 tc::tc_fence_after_sync();
                 TC_STAMP(1, u, 1);
                 const uint32_t d = tbase + C::ABASE + (uint32_t)(u % C::NAB3) * C::ACOLS;
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             }
             for (int u = 0; u < total; ++u) {
                 if (OBJ) {  // no MMA#2: the P buffer is free once the quotient warps have read it
-                    tc::mbar_wait_h(hint, &q_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 22);
+                    tc::mbar_wait_h(0u, &q_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 22);
                     tc::tc_fence_after_sync();
                 } else {
                     mma2(u);
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             tc::named_bar_sync(1, NS);        // ... and everybody else's
             if (warp == 2) TC_STAMP(2, u, 1);
             const int vb = u % TC_NVB;
-            if (u >= TC_NVB) tc::mbar_wait_h(hint, &v_empty[vb], (uint32_t)((u / TC_NVB - 1) & 1), errflag, 30);
+            if (u >= TC_NVB) tc::mbar_wait_relaxed(&v_empty[vb], (uint32_t)((u / TC_NVB - 1) & 1), hint >> 16, errflag, 30);
             if (warp == 2) TC_STAMP(2, u, 2);
             unsigned char* base = Vs + (size_t)vb * C::V_BYTES;
             const float* raw = Raw + (size_t)(u % TC_NRAW) * RAWF;
@@ -464,11 +464,11 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c % TC_NXS;
                 const int cnt = min(TC_TS, t_end - (t_begin + c * TC_TS));
-                tc::mbar_wait_h(hint, &x_full[s], (uint32_t)((c / TC_NXS) & 1), errflag, 40);
+                tc::mbar_wait_h(0u, &x_full[s], (uint32_t)((c / TC_NXS) & 1), errflag, 40);
                 const float* xs = Xs + (size_t)s * TC_TS * TC_M + (size_t)j0 * TC_M + o_loc;
                 for (int b = 0; b < nact; ++b, ++u) {
                     const uint32_t col = lane_base + (uint32_t)(u & 1) * C::PQ + j0;
-                    tc::mbar_wait_h(hint, &p_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 41);
+                    tc::mbar_wait_h(0u, &p_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 41);
                     tc::tc_fence_after_sync();
                     uint32_t p[16];
                     tc::tmem_ld16(col, p);
@@ -549,12 +549,12 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % TC_NXS;
             const int cnt = min(TC_TS, t_end - (t_begin + c * TC_TS));
-            tc::mbar_wait_h(hint, &x_full[s], (uint32_t)((c / TC_NXS) & 1), errflag, 40);
+            tc::mbar_wait_h(0u, &x_full[s], (uint32_t)((c / TC_NXS) & 1), errflag, 40);
             const float* xs = Xs + (size_t)s * TC_TS * TC_M + (size_t)j0 * TC_M + o_loc;
             for (int b = 0; b < nact; ++b, ++u) {
                 const uint32_t col = lane_base + (uint32_t)(u & 1) * C::PQ + j0;
                 if (warp == TC_QW0) TC_STAMP(0, u, 0);
-                tc::mbar_wait_h(hint, &p_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 41);
+                tc::mbar_wait_h(0u, &p_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 41);
                 tc::tc_fence_after_sync();
                 if (warp == TC_QW0) TC_STAMP(0, u, 1);
                 uint32_t p[16], lo[16];
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             if (lane == 0) tc::mbar_arrive(&x_empty[s]);
         }
         // tail: the last two units wait for the commit behind the last MMA#2
-        tc::mbar_wait_h(hint, &a_full[(total - 1) & 1], (uint32_t)(((total - 1) >> 1) & 1), errflag, 43);
+        tc::mbar_wait_h(0u, &a_full[(total - 1) & 1], (uint32_t)(((total - 1) >> 1) & 1), errflag, 43);
         tc::tc_fence_after_sync();
         for (int uu = max(0, total - 2); uu < total; ++uu) {
             drain_load(uu);

@@ -77,6 +77,18 @@ __device__ __forceinline__ void mbar_wait_h(uint32_t hint_ns, uint64_t* bar, uin
     __trap();
 }
 
+// wait of a role that runs AHEAD of the critical path (X producer, V stagers): sleep between polls so that the
+// polling does not take issue slots from the quotient warps of the same scheduler
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned sleep_ns, int* errflag, int where) {
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        if (mbar_try_wait(bar, parity)) return;
+        if (sleep_ns) __nanosleep(sleep_ns);
+    }
+    if (errflag) atomicExch(errflag, where);
+    __threadfence_system();
+    __trap();
+}
+
 // ---- proxies / fences -----------------------------------------------------------------------
 // generic-proxy st.shared -> visible to the async proxy (tcgen05.mma / bulk copies reading smem)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

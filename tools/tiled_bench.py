@@ -37,11 +37,13 @@ def main():
                              bf16_mma_sync=max(ctx.measure_peak(12) for _ in range(2)))
                 print(json.dumps(dict(peaks_tflops=peaks)), flush=True)
             ctx.set_X(X)
-            for engine_iters in (3, iters):  # the first run is the warm-up
+            ms = None
+            for engine_iters in (10, iters, iters):  # warm-up (with one check: loads every kernel), then best of two
                 b = ctx.batch(k, R)
                 b.init_random(2015)
-                ctx.solve([b], nb.default_params(maxiter=engine_iters, engine=2))
-                ms = ctx.last_solve_ms
+                ctx.solve([b], nb.default_params(maxiter=engine_iters, engine=int(os.environ.get("NMFK_BENCH_ENGINE", "2"))))
+                if engine_iters == iters and (ms is None or ctx.last_solve_ms < ms):
+                    ms = ctx.last_solve_ms
                 out = b.get(factors=False)
                 b.close()
             tot = int(out["iters"].sum())
