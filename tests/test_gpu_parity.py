@@ -465,3 +465,18 @@ def test_tiled_dmma_matches_scalar_pass(ctx, n, m, k, R):
         Xc = np.array(X, dtype=np.float64, order="F", copy=True)
         W, H, _ = o.nmf_multiplicative(Xc, k, Winit=W0[0].copy(), Hinit=H0[0].copy(), maxiter=12)
         assert relerr(res[2]["W"][0], W) < RTOL64 and relerr(res[2]["H"][0], H) < RTOL64
+
+
+def test_execute_through_tensor_tiled_engines_same_decisions(ctx):
+    """execute(X, ks, nNMF) with the tiled engine forced (engine=2: tcgen05 for Float32, DMMA for Float64) against the
+    scalar-FMA tiled pass (engine=4) on a 3-source mixture: same kopt, same robustness ranking, fits equal to rounding."""
+    for dt, tol in ((np.float32, 2e-3), (np.float64, 1e-6)):
+        X = synth.mixture(1200, 400, 3, seed=31, dtype=dt)
+        out = {}
+        for eng in (4, 2):
+            W, H, fit, rob, aic, kopt = nb.execute(X, range(2, 6), 8, seed=77, ctx=ctx, engine=eng, maxiter=400)
+            out[eng] = (fit, rob, kopt)
+        assert out[2][2] == out[4][2] == 3, (out[2][2], out[4][2])
+        r2, r4 = np.asarray(out[2][1][1:5], dtype=float), np.asarray(out[4][1][1:5], dtype=float)
+        assert np.array_equal(r2 > 0.5, r4 > 0.5)
+        assert np.allclose(np.asarray(out[2][0][1:5], dtype=float), np.asarray(out[4][0][1:5], dtype=float), rtol=tol, atol=tol)
