@@ -76,6 +76,12 @@ struct TcCfg {
     static_assert(SMEM <= 232448, "shared memory budget of one CTA");
 };
 
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+
 __device__ __forceinline__ float rcp_fast(float p) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
@@ -567,13 +573,20 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                 if (warp == TC_QW0) TC_STAMP(0, u, 2);
                 if (cnt == TC_TS) {
                     // (one MUFU.RCP per PAIR of quotients, r = 1/(p0 p1), was measured slower: this loop is bound by
-                    // instruction issue, not by the MUFU unit)
+                    // instruction issue, not by the MUFU unit.)  Packed FP32x2 arithmetic of sm_100 (FMUL2 / FADD2) for the
+                    // quotient and the low part: 8 instead of 10 issue slots per pair of elements.
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float q = xs[j * TC_M] * rcp_fast(__uint_as_float(p[j]));
-                        const uint32_t h = __float_as_uint(q) & 0xffffe000u;
-                        lo[j] = __float_as_uint(q - __uint_as_float(h));
-                        p[j] = h;
+                    for (int j = 0; j < 16; j += 2) {
+                        const float r0 = rcp_fast(__uint_as_float(p[j])), r1 = rcp_fast(__uint_as_float(p[j + 1]));
+                        const unsigned long long x2 = pack2(xs[j * TC_M], xs[(j + 1) * TC_M]), r2 = pack2(r0, r1);
+                        unsigned long long q2, l2;
+                        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(q2) : "l"(x2), "l"(r2));
+                        const unsigned long long h2 = q2 & 0xffffe000ffffe000ull;
+                        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(l2) : "l"(q2), "l"(h2));
+                        p[j] = (uint32_t)h2;
+                        p[j + 1] = (uint32_t)(h2 >> 32);
+                        lo[j] = (uint32_t)l2;
+                        lo[j + 1] = (uint32_t)(l2 >> 32);
                     }
                 } else {  // last chunk of the slice: steps past the end contribute nothing
 #pragma unroll
