@@ -53,7 +53,7 @@ struct TcCfg {
     static constexpr int NST = N2 == 16 ? 2 : 1;                      // MMA#2: Qhi * [Vhi ; Vlo] stacked along N
     static constexpr int ACOLS = NST * N2;                            // columns of one per-unit numerator buffer
     static constexpr int PQ = 2 * TS;                                 // one P/Q buffer: P -> Qhi | Qlo
-    static constexpr int NAB3 = 3;                                    // per-unit numerator buffers (drained 3 units later)
+    static constexpr int NAB3 = 2;                                    // per-unit numerator buffers (one per quotient group)
     static constexpr int ABASE = 2 * PQ, UBASE = ABASE + NAB3 * ACOLS;  // tensor-memory columns
     static constexpr int PERB = 2 * K8;                               // U hi | U lo per restart
     static constexpr int NCQ = N2 / NCS;                              // numerator columns per quotient thread
@@ -96,7 +96,6 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
     constexpr int TC_NXS = C::NXS;
     constexpr int TC_TS = C::TS, TC_QWARPS = C::QW, TC_SWARPS = C::SW, TC_QW0 = C::QW0, TC_THREADS = C::THREADS;
     constexpr int RB = C::RB;
-    constexpr int NC = C::NCQ;
     extern __shared__ __align__(1024) unsigned char smem[];
     float* Xs = reinterpret_cast<float*>(smem);                         // [NXS][TS][M]
     unsigned char* Vs = smem + (size_t)TC_NXS * C::X_BYTES;              // [NVB][V_BYTES]
@@ -110,7 +109,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
     uint64_t* q_full = p_full + 2;           // [2]    Q written (and the numerator buffer of unit u-2 drained)
     uint64_t* a_full = q_full + 2;           // [2]    MMA#2 done: the unit's numerators readable
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
-    int* s_act = reinterpret_cast<int*>(tmem_slot + 1);  // [RB] active restarts of the group, then their count
+    int* s_act = reinterpret_cast<int*>(tmem_slot + 1);  // [RB] restart of every unit slot, then the number of real ones
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t hint = (uint32_t)a.wait_hint_ns;
@@ -142,10 +141,14 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             if (take) s_act[nact++] = r;
         }
         s_act[RB] = nact;
+        // pass mode: the two quotient groups alternate units, so a chunk holds an EVEN number of units; an odd group of
+        // restarts (ragged last group, frozen restarts) gets a shadow unit that recomputes its first restart and is dropped
+        if (!OBJ && (nact & 1)) s_act[nact] = s_act[0];
     }
     __syncthreads();
-    const int nact = s_act[RB];
-    if (nact == 0 || nchunks <= 0) return;
+    const int nreal = s_act[RB];
+    const int nact = OBJ ? nreal : nreal + (nreal & 1);
+    if (nreal == 0 || nchunks <= 0) return;
     const int total = nchunks * nact;
 
     if (warp == 0) tc::tmem_alloc<C::TCOLS>(tmem_slot);
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
         }
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&p_full[i], 1);
-            tc::mbar_init(&q_full[i], TC_QWARPS);
+            tc::mbar_init(&q_full[i], OBJ ? TC_QWARPS : TC_QWARPS / 2);
             tc::mbar_init(&a_full[i], 1);
         }
         tc::mbar_fence_init();
@@ -518,135 +521,145 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                 dst[1] = t;
             }
         } else {
-        float acc[RB][NC];
+        // Two GROUPS of 8 warps (4 lane quarters x 2 column halves of 32) alternate units: group 0 takes the even units
+        // (P/Q and numerator buffers 0), group 1 the odd ones (buffers 1).  While one group divides, the other waits for
+        // its P tile / loads / stores: the division stage no longer runs in lockstep over the whole CTA.
+        const int grp = cs >> 1, hh = cs & 1;
+        const int jh = hh * 32;                     // this thread's 32 columns of a unit
+        constexpr int NC2 = N2 / 2;                 // numerator columns per thread
+        constexpr int SL = (RB + 1) / 2;            // restart slots a group accumulates (slot b -> group b % 2, index b / 2)
+        float acc[SL][NC2];
 #pragma unroll
-        for (int b = 0; b < RB; ++b)
+        for (int i = 0; i < SL; ++i)
 #pragma unroll
-            for (int c = 0; c < NC; ++c) acc[b][c] = 0.f;
-        // numerators of unit uu -> registers of restart slot `target`, round-to-nearest adds.  No barrier of its own in the
-        // steady state: the tcgen05.commit behind p_full(u) also covers MMA#2(u-2), issued earlier by the same thread,
-        // so once P(u) has been seen the numerators of unit u-2 are complete.
-        uint32_t v0[NC], v1[NC];
-        auto drain_load = [&](int uu) {
-            const uint32_t col = lane_base + C::ABASE + (uint32_t)(uu % C::NAB3) * C::ACOLS + cs * NC;
-            static_assert(NC == 4 || NC == 8, "numerator columns per quotient thread");
-            if (NC == 4) {
-                tc::tmem_ld4(col, v0);
-                if (C::NST == 2) tc::tmem_ld4(col + N2, v1);
-            } else {
-                tc::tmem_ld8(col, v0);
-                if (C::NST == 2) tc::tmem_ld8(col + N2, v1);
-            }
-        };
-        auto drain_add = [&](int target) {
+            for (int c = 0; c < NC2; ++c) acc[i][c] = 0.f;
+        // numerators of a unit -> registers, round-to-nearest adds.  No barrier of its own in the steady state: the
+        // tcgen05.commit behind p_full(u) also covers MMA#2(u-2), issued earlier by the same thread, so once P(u) has been
+        // seen the numerators of this group's previous unit u-2 are complete; they are fetched while unit u is divided
+        // (the tensor pipe is quieter then: a tensor-memory load issued while MMAs run was measured ~300 clk slower).
+        // The 16 numerator values of a thread (NST = 2: 8 columns of Qhi*Vhi+Qlo*Vhi and the same 8 of Qhi*Vlo; NST = 1:
+        // 16 columns) are fetched in two parts of 8, one per 16-column round of the division, to keep registers down.
+        static_assert(NC2 * C::NST == 16, "numerator values per quotient thread");
+        uint32_t v[8];
+        const uint32_t acol = lane_base + C::ABASE + (uint32_t)grp * C::ACOLS + hh * NC2;
+        auto drain_load = [&](int part) { tc::tmem_ld8(acol + part * (C::NST == 2 ? N2 : 8), v); };
+        auto drain_add = [&](int slot, int part) {
 #pragma unroll
-            for (int bb = 0; bb < RB; ++bb)
-                if (bb == target) {
+            for (int i = 0; i < SL; ++i)
+                if (i == slot) {
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) {
-                        float v = __uint_as_float(v0[c]);
-                        if (C::NST == 2) v += __uint_as_float(v1[c]);
-                        acc[bb][c] += v;
+                    for (int c = 0; c < 8; ++c) {
+                        if (C::NST == 2) {
+                            acc[i][c] += __uint_as_float(v[c]);
+                        } else {
+#pragma unroll
+                            for (int pp = 0; pp < 2; ++pp)
+                                if (pp == part) acc[i][pp * 8 + c] += __uint_as_float(v[c]);
+                        }
                     }
                 }
         };
-        int bm1 = 0, bm2 = 0;  // restart slots of units u-1, u-2
-        int u = 0;
+        int prev_slot = -1;  // restart slot index (b / 2) of this group's previous unit, -1: none yet
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % TC_NXS;
             const int cnt = min(TC_TS, t_end - (t_begin + c * TC_TS));
             tc::mbar_wait_h(0u, &x_full[s], (uint32_t)((c / TC_NXS) & 1), errflag, 40);
-            const float* xs = Xs + (size_t)s * TC_TS * TC_M + (size_t)j0 * TC_M + o_loc;
-            for (int b = 0; b < nact; ++b, ++u) {
-                const uint32_t col = lane_base + (uint32_t)(u & 1) * C::PQ + j0;
+            const float* xs = Xs + (size_t)s * TC_TS * TC_M + (size_t)jh * TC_M + o_loc;
+            for (int b = grp; b < nact; b += 2) {
+                const int u = c * nact + b;  // u % 2 == grp (nact is even)
+                const uint32_t col = lane_base + (uint32_t)grp * C::PQ + jh;
                 if (warp == TC_QW0) TC_STAMP(0, u, 0);
-                tc::mbar_wait_h(0u, &p_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 41);
+                tc::mbar_wait_h(0u, &p_full[grp], (uint32_t)((u >> 1) & 1), errflag, 41);
                 tc::tc_fence_after_sync();
                 if (warp == TC_QW0) TC_STAMP(0, u, 1);
-                uint32_t p[16], lo[16];
-                tc::tmem_ld16(col, p);
-                tc::tmem_wait_ld();
-                // the numerators of unit u-2 (complete: the commit behind p_full(u) covers MMA#2(u-2)) are fetched while
-                // this unit is divided: the tensor pipe is quiet then (MMA#2(u) waits for q_full(u)), and a tensor-memory
-                // load issued while MMAs run was measured ~300 clk slower
-                if (u >= 2) drain_load(u - 2);
-                if (warp == TC_QW0) TC_STAMP(0, u, 2);
-                if (cnt == TC_TS) {
-                    // (one MUFU.RCP per PAIR of quotients, r = 1/(p0 p1), was measured slower: this loop is bound by
-                    // instruction issue, not by the MUFU unit.)  Packed FP32x2 arithmetic of sm_100 (FMUL2 / FADD2) for the
-                    // quotient and the low part: 8 instead of 10 issue slots per pair of elements.
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        const float r0 = rcp_fast(__uint_as_float(p[j])), r1 = rcp_fast(__uint_as_float(p[j + 1]));
-                        const unsigned long long x2 = pack2(xs[j * TC_M], xs[(j + 1) * TC_M]), r2 = pack2(r0, r1);
-                        unsigned long long q2, l2;
-                        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(q2) : "l"(x2), "l"(r2));
-                        const unsigned long long h2 = q2 & 0xffffe000ffffe000ull;
-                        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(l2) : "l"(q2), "l"(h2));
-                        p[j] = (uint32_t)h2;
-                        p[j + 1] = (uint32_t)(h2 >> 32);
-                        lo[j] = (uint32_t)l2;
-                        lo[j + 1] = (uint32_t)(l2 >> 32);
-                    }
-                } else {  // last chunk of the slice: steps past the end contribute nothing
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float q = xs[j * TC_M] * rcp_fast(__uint_as_float(p[j]));
-                        q = (j0 + j < cnt) ? q : 0.f;
-                        const uint32_t h = __float_as_uint(q) & 0xffffe000u;
-                        lo[j] = __float_as_uint(q - __uint_as_float(h));
-                        p[j] = h;
-                    }
-                }
-                if (u >= 2) {
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t p[16], lo[16];
+                    tc::tmem_ld16(col + half * 16, p);
                     tc::tmem_wait_ld();
-                    drain_add(bm2);
+                    if (prev_slot >= 0) drain_load(half);
+                    if (half == 0 && warp == TC_QW0) TC_STAMP(0, u, 2);
+                    const float* xh = xs + half * 16 * TC_M;
+                    if (cnt == TC_TS) {
+                        // (one MUFU.RCP per PAIR of quotients, r = 1/(p0 p1), was measured slower: this loop is bound by
+                        // instruction issue, not by the MUFU unit.)  Packed FP32x2 arithmetic of sm_100 (FMUL2 / FADD2) for
+                        // the quotient and the low part: 8 instead of 10 issue slots per pair of elements.
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            const float r0 = rcp_fast(__uint_as_float(p[j])), r1 = rcp_fast(__uint_as_float(p[j + 1]));
+                            const unsigned long long x2 = pack2(xh[j * TC_M], xh[(j + 1) * TC_M]), r2 = pack2(r0, r1);
+                            unsigned long long q2, l2;
+                            asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(q2) : "l"(x2), "l"(r2));
+                            const unsigned long long h2 = q2 & 0xffffe000ffffe000ull;
+                            asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(l2) : "l"(q2), "l"(h2));
+                            p[j] = (uint32_t)h2;
+                            p[j + 1] = (uint32_t)(h2 >> 32);
+                            lo[j] = (uint32_t)l2;
+                            lo[j + 1] = (uint32_t)(l2 >> 32);
+                        }
+                    } else {  // last chunk of the slice: steps past the end contribute nothing
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float q = xh[j * TC_M] * rcp_fast(__uint_as_float(p[j]));
+                            q = (jh + half * 16 + j < cnt) ? q : 0.f;
+                            const uint32_t h = __float_as_uint(q) & 0xffffe000u;
+                            lo[j] = __float_as_uint(q - __uint_as_float(h));
+                            p[j] = h;
+                        }
+                    }
+                    if (prev_slot >= 0) {
+                        tc::tmem_wait_ld();
+                        drain_add(prev_slot, half);
+                    }
+                    tc::tmem_st16(col + half * 16, p);
+                    tc::tmem_st16(col + TC_TS + half * 16, lo);
                 }
                 if (warp == TC_QW0) TC_STAMP(0, u, 3);
-                tc::tmem_st16(col, p);
-                tc::tmem_st16(col + TC_TS, lo);
                 tc::tmem_wait_st();
                 tc::tc_fence_before_sync();
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&q_full[u & 1]);
+                if (lane == 0) tc::mbar_arrive(&q_full[grp]);
                 if (warp == TC_QW0) TC_STAMP(0, u, 4);
-                if (warp == TC_QW0) TC_STAMP(0, u, 5);
-                bm2 = bm1;
-                bm1 = b;
+                prev_slot = b >> 1;
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&x_empty[s]);
         }
-        // tail: the last two units wait for the commit behind the last MMA#2
-        tc::mbar_wait_h(0u, &a_full[(total - 1) & 1], (uint32_t)(((total - 1) >> 1) & 1), errflag, 43);
-        tc::tc_fence_after_sync();
-        for (int uu = max(0, total - 2); uu < total; ++uu) {
-            drain_load(uu);
-            tc::tmem_wait_ld();
-            drain_add(uu == total - 1 ? bm1 : bm2);
-        }
-        // numerators -> factor update (or the slice's partial sums): this thread's NC columns of every restart
+        // tail: this group's last unit waits for the commit behind its own MMA#2
+        {
+            const int ulast = (nchunks - 1) * nact + (nact - 2 + grp);
+            tc::mbar_wait_h(0u, &a_full[grp], (uint32_t)((ulast >> 1) & 1), errflag, 43);
+            tc::tc_fence_after_sync();
 #pragma unroll
-        for (int b = 0; b < RB; ++b) {
-            if (b < nact && valid) {
+            for (int part = 0; part < 2; ++part) {
+                drain_load(part);
+                tc::tmem_wait_ld();
+                drain_add(prev_slot, part);
+            }
+        }
+        // numerators -> factor update (or the slice's partial sums): this thread's NC2 columns of this group's restarts
+#pragma unroll
+        for (int i = 0; i < SL; ++i) {
+            const int b = 2 * i + grp;
+            if (b < nreal && valid) {
                 const int r = s_act[b];
                 if (a.partial == nullptr) {
                     float* U = Ug + (long long)r * a.u_rstride;
                     const float* den = static_cast<const float*>(a.den) + (long long)r * 32;
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) {
-                        const int col = cs * NC + c;
+                    for (int c = 0; c < NC2; ++c) {
+                        const int col = hh * NC2 + c;
                         if (col < k) {
                             const long long idx = (long long)o * a.su_o + (long long)col * a.su_a;
-                            U[idx] = (U[idx] * acc[b][c]) / den[col];
+                            U[idx] = (U[idx] * acc[i][c]) / den[col];
                         }
                     }
                 } else {
                     float* dst = static_cast<float*>(a.partial) + (((long long)slice * a.R + r) * a.nown + o) * a.ktmpl;
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) {
-                        const int col = cs * NC + c;
-                        if (col < a.ktmpl) dst[col] = acc[b][c];
+                    for (int c = 0; c < NC2; ++c) {
+                        const int col = hh * NC2 + c;
+                        if (col < a.ktmpl) dst[col] = acc[i][c];
                     }
                 }
             }
