@@ -32,7 +32,7 @@ namespace nmfk {
 namespace {
 
 constexpr int TC_M = 128;
-constexpr int TC_NVB = 3, TC_NRAW = 4;
+constexpr int TC_NRAW = 4;
 constexpr uint32_t TC_LBO = 128;
 
 // K8 / N2: k rounded up to the K granularity of MMA#1 (8) / the N granularity of MMA#2 (16).
@@ -43,6 +43,7 @@ template <int K8, int N2, bool WIDE>
 struct TcCfg {
     static constexpr int TS = WIDE ? 64 : 32;                         // steps per chunk
     static constexpr int NXS = 3;                                     // X tile stages
+    static constexpr int NVB = K8 <= 16 ? 4 : 3;                      // V image buffers (shared memory budget for k > 16)
     static constexpr int RPAD = (WIDE && K8 > 24) ? 0 : 4;            // raw V chunk padding (shared memory budget at K8 = 32)
     static constexpr int QW = TS / 4;                                 // quotient warps: lane quarter = warp % 4, 16 columns each
     static constexpr int SW = WIDE ? 4 : 2;                           // V stager warps
@@ -53,8 +54,13 @@ struct TcCfg {
     static constexpr int NST = N2 == 16 ? 2 : 1;                      // MMA#2: Qhi * [Vhi ; Vlo] stacked along N
     static constexpr int ACOLS = NST * N2;                            // columns of one per-unit numerator buffer
     static constexpr int PQ = 2 * TS;                                 // one P/Q buffer: P -> Qhi | Qlo
+    // P/Q buffers.  With two, MMA#1(u) can only be issued after MMA#2(u-2) (same buffer), i.e. after the quotient group of
+    // unit u has finished its previous unit.  A third buffer lets MMA#1 run three units ahead.  Tensor memory has room
+    // for it with RB = 4 restarts per CTA only when k <= 8 (C3 shape at k = 8: 6494 against 5982 restart-iterations/s);
+    // at k = 16 it would leave RB = 2 and measured 5030-5100 against 5460 with two buffers and RB = 4.
+    static constexpr int NPQ = K8 <= 8 ? 3 : 2;
     static constexpr int NAB3 = 2;                                    // per-unit numerator buffers (one per quotient group)
-    static constexpr int ABASE = 2 * PQ, UBASE = ABASE + NAB3 * ACOLS;  // tensor-memory columns
+    static constexpr int ABASE = NPQ * PQ, UBASE = ABASE + NAB3 * ACOLS;  // tensor-memory columns
     static constexpr int PERB = 2 * K8;                               // U hi | U lo per restart
     static constexpr int NCQ = N2 / NCS;                              // numerator columns per quotient thread
     static constexpr int RBT = (TCOLS - UBASE) / PERB;
@@ -71,7 +77,7 @@ struct TcCfg {
     static constexpr int RAWP_A = K8 + RPAD;                          // raw V chunk [step][column], padded pitch
     static constexpr uint32_t RAW_BYTES = (K8 * TS + RPAD * (K8 > TS ? K8 : TS)) * 4;
     static constexpr size_t SMEM =
-        (size_t)NXS * X_BYTES + (size_t)TC_NVB * V_BYTES + (size_t)TC_NRAW * RAW_BYTES + 32 * 8 + 64;
+        (size_t)NXS * X_BYTES + (size_t)NVB * V_BYTES + (size_t)TC_NRAW * RAW_BYTES + 32 * 8 + 64;
     static_assert(RB >= 1 && RB <= 4, "restart group");
     static_assert(SMEM <= 232448, "shared memory budget of one CTA");
 };
@@ -93,7 +99,7 @@ __device__ __forceinline__ float rcp_fast(float p) {
 template <int K8, int N2, bool WIDE, bool OBJ>
 __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)) tc_pass_kernel(const TiledPassArgs a, int* errflag) {
     using C = TcCfg<K8, N2, WIDE>;
-    constexpr int TC_NXS = C::NXS;
+    constexpr int TC_NXS = C::NXS, TC_NVB = C::NVB;
     constexpr int TC_TS = C::TS, TC_QWARPS = C::QW, TC_SWARPS = C::SW, TC_QW0 = C::QW0, TC_THREADS = C::THREADS;
     constexpr int RB = C::RB;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -105,9 +111,9 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
     uint64_t* x_empty = x_full + TC_NXS;     // [NXS]  quotient warps are done with the tile
     uint64_t* v_full = x_empty + TC_NXS;     // [NVB]  V images staged
     uint64_t* v_empty = v_full + TC_NVB;     // [NVB]  MMA#1 and MMA#2 of the unit have read them
-    uint64_t* p_full = v_empty + TC_NVB;     // [2]    MMA#1 done: P readable
-    uint64_t* q_full = p_full + 2;           // [2]    Q written (and the numerator buffer of unit u-2 drained)
-    uint64_t* a_full = q_full + 2;           // [2]    MMA#2 done: the unit's numerators readable
+    uint64_t* p_full = v_empty + TC_NVB;     // [NPQ]  MMA#1 done: P readable
+    uint64_t* q_full = p_full + C::NPQ;      // [NPQ]  Q written (and the numerator buffer of unit u-2 drained)
+    uint64_t* a_full = q_full + C::NPQ;      // [2]    MMA#2 done: the unit's numerators readable
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
     int* s_act = reinterpret_cast<int*>(tmem_slot + 1);  // [RB] restart of every unit slot, then the number of real ones
 
@@ -161,11 +167,11 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             tc::mbar_init(&v_full[i], TC_SWARPS);
             tc::mbar_init(&v_empty[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < C::NPQ; ++i) {
             tc::mbar_init(&p_full[i], 1);
             tc::mbar_init(&q_full[i], OBJ ? TC_QWARPS : TC_QWARPS / 2);
-            tc::mbar_init(&a_full[i], 1);
         }
+        for (int i = 0; i < 2; ++i) tc::mbar_init(&a_full[i], 1);
         tc::mbar_fence_init();
     }
     // padding rows / columns of the V images stay zero for the whole kernel; so do the own indices past the
@@ -248,7 +254,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                 tc::mbar_wait_h(0u, &v_full[vb], (uint32_t)((u / TC_NVB) & 1), errflag, 20);
                 tc::tc_fence_after_sync();
                 TC_STAMP(1, u, 4);
-                const uint32_t d = tbase + (uint32_t)(u & 1) * C::PQ;
+                const uint32_t d = tbase + (uint32_t)(u % C::NPQ) * C::PQ;
                 const uint32_t uh = tbase + C::UBASE + b * C::PERB, ul = uh + K8;
                 const uint64_t bh = d1 + (uint64_t)((vb * C::V_BYTES) >> 4), bl = bh + (C::B1_BYTES >> 4);
                 if (tc::elect_one()) {
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                     tc::mma_tf32_ts(d, uh + ks * 8, bl + ks * KSTEP, idP, 1);
                     tc::mma_tf32_ts(d, uh + ks * 8, bh + ks * KSTEP, idP, 1);
                 }
-                tc::mma_commit(&p_full[u & 1]);
+                tc::mma_commit(&p_full[u % C::NPQ]);
                 if (OBJ) tc::mma_commit(&v_empty[vb]);  // MMA#1 is the only reader of the V images
                 }
                 __syncwarp();
@@ -267,11 +273,11 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             auto mma2 = [&](int u) {
                 const int vb = u % TC_NVB;
                 TC_STAMP(1, u, 0);
-                tc::mbar_wait_h(0u, &q_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 21);
+                tc::mbar_wait_h(0u, &q_full[u % C::NPQ], (uint32_t)((u / C::NPQ) & 1), errflag, 21);
                 tc::tc_fence_after_sync();
                 TC_STAMP(1, u, 1);
                 const uint32_t d = tbase + C::ABASE + (uint32_t)(u % C::NAB3) * C::ACOLS;
-                const uint32_t qh = tbase + (uint32_t)(u & 1) * C::PQ, ql = qh + TC_TS;
+                const uint32_t qh = tbase + (uint32_t)(u % C::NPQ) * C::PQ, ql = qh + TC_TS;
                 const uint64_t bh = d2 + (uint64_t)((vb * C::V_BYTES) >> 4), bl = bh + (C::B2_BYTES >> 4);
                 if (tc::elect_one()) {
 #pragma unroll
@@ -288,24 +294,22 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                 __syncwarp();
                 TC_STAMP(1, u, 2);
             };
-            // unit u = c * nact + b; MMA#1 runs two units ahead of MMA#2
+            // unit u = c * nact + b; MMA#1 runs NPQ units ahead of MMA#2
             int b1 = 0;  // restart slot of the next MMA#1
             auto next_b = [&](int b) { return b + 1 == nact ? 0 : b + 1; };
-            mma1(0, b1);
-            b1 = next_b(b1);
-            if (total > 1) {
-                mma1(1, b1);
+            for (int u0 = 0; u0 < C::NPQ && u0 < total; ++u0) {
+                mma1(u0, b1);
                 b1 = next_b(b1);
             }
             for (int u = 0; u < total; ++u) {
                 if (OBJ) {  // no MMA#2: the P buffer is free once the quotient warps have read it
-                    tc::mbar_wait_h(0u, &q_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 22);
+                    tc::mbar_wait_h(0u, &q_full[u % C::NPQ], (uint32_t)((u / C::NPQ) & 1), errflag, 22);
                     tc::tc_fence_after_sync();
                 } else {
                     mma2(u);
                 }
-                if (u + 2 < total) {
-                    mma1(u + 2, b1);
+                if (u + C::NPQ < total) {
+                    mma1(u + C::NPQ, b1);
                     b1 = next_b(b1);
                 }
             }
@@ -476,15 +480,15 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                 tc::mbar_wait_h(0u, &x_full[s], (uint32_t)((c / TC_NXS) & 1), errflag, 40);
                 const float* xs = Xs + (size_t)s * TC_TS * TC_M + (size_t)j0 * TC_M + o_loc;
                 for (int b = 0; b < nact; ++b, ++u) {
-                    const uint32_t col = lane_base + (uint32_t)(u & 1) * C::PQ + j0;
-                    tc::mbar_wait_h(0u, &p_full[u & 1], (uint32_t)((u >> 1) & 1), errflag, 41);
+                    const uint32_t col = lane_base + (uint32_t)(u % C::NPQ) * C::PQ + j0;
+                    tc::mbar_wait_h(0u, &p_full[u % C::NPQ], (uint32_t)((u / C::NPQ) & 1), errflag, 41);
                     tc::tc_fence_after_sync();
                     uint32_t p[16];
                     tc::tmem_ld16(col, p);
                     tc::tmem_wait_ld();
                     tc::tc_fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&q_full[u & 1]);  // P is in registers: the buffer is free
+                    if (lane == 0) tc::mbar_arrive(&q_full[u % C::NPQ]);  // P is in registers: the buffer is free
                     float su = 0.f;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
@@ -533,10 +537,9 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
         for (int i = 0; i < SL; ++i)
 #pragma unroll
             for (int c = 0; c < NC2; ++c) acc[i][c] = 0.f;
-        // numerators of a unit -> registers, round-to-nearest adds.  No barrier of its own in the steady state: the
-        // tcgen05.commit behind p_full(u) also covers MMA#2(u-2), issued earlier by the same thread, so once P(u) has been
-        // seen the numerators of this group's previous unit u-2 are complete; they are fetched while unit u is divided
-        // (the tensor pipe is quieter then: a tensor-memory load issued while MMAs run was measured ~300 clk slower).
+        // numerators of a unit -> registers, round-to-nearest adds.  A group drains its previous unit u-2 while it divides
+        // unit u (the tensor pipe is quieter then: a tensor-memory load issued while MMAs run was measured ~300 clk
+        // slower); the a_full wait that precedes it has normally completed long before.
         // The 16 numerator values of a thread (NST = 2: 8 columns of Qhi*Vhi+Qlo*Vhi and the same 8 of Qhi*Vlo; NST = 1:
         // 16 columns) are fetched in two parts of 8, one per 16-column round of the division, to keep registers down.
         static_assert(NC2 * C::NST == 16, "numerator values per quotient thread");
@@ -567,9 +570,13 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             const float* xs = Xs + (size_t)s * TC_TS * TC_M + (size_t)jh * TC_M + o_loc;
             for (int b = grp; b < nact; b += 2) {
                 const int u = c * nact + b;  // u % 2 == grp (nact is even)
-                const uint32_t col = lane_base + (uint32_t)grp * C::PQ + jh;
+                const int pq = u % C::NPQ;
+                const uint32_t col = lane_base + (uint32_t)pq * C::PQ + jh;
                 if (warp == TC_QW0) TC_STAMP(0, u, 0);
-                tc::mbar_wait_h(0u, &p_full[grp], (uint32_t)((u >> 1) & 1), errflag, 41);
+                tc::mbar_wait_h(0u, &p_full[pq], (uint32_t)((u / C::NPQ) & 1), errflag, 41);
+                // the numerators of this group's previous unit u-2: wait for the commit behind MMA#2(u-2) (with three P/Q
+                // buffers the commit behind p_full(u) only covers MMA#2(u-3)); it has normally completed long ago
+                if (prev_slot >= 0) tc::mbar_wait_h(0u, &a_full[grp], (uint32_t)((((u - 2) >> 1)) & 1), errflag, 44);
                 tc::tc_fence_after_sync();
                 if (warp == TC_QW0) TC_STAMP(0, u, 1);
 #pragma unroll 1
@@ -618,7 +625,7 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                 tc::tmem_wait_st();
                 tc::tc_fence_before_sync();
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&q_full[grp]);
+                if (lane == 0) tc::mbar_arrive(&q_full[pq]);
                 if (warp == TC_QW0) TC_STAMP(0, u, 4);
                 prev_slot = b >> 1;
             }

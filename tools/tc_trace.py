@@ -21,13 +21,12 @@ with nb.Context(0) as ctx:
 t = np.fromfile("/tmp/tc_trace.bin", dtype=np.int64).reshape(3, 64, 8)
 t0 = t[t > 0].min()
 q, mm, st = t[0], t[1], t[2]
-print("unit | quotient: pwait  ld  compute  st+arrive  drain | total || mma: qwait mma2-issue vwait mma1-issue || stager: cpwait vempty convert")
-for u in range(8, 40):
-    if q[u, 0] == 0:
+print("unit | quotient group 0 (even units): pwait  ld  compute+drain  st+arrive | cycle of 2 units || mma (this unit): qwait mma2-issue vwait mma1-issue || stager: cpwait vempty convert")
+for u in range(8, 40, 2):
+    if q[u, 0] == 0 or q[u + 2, 0] == 0:
         break
     qq = q[u]
-    nxt = q[u + 1, 0] if q[u + 1, 0] else qq[5]
-    print("%4d | %6d %5d %6d %8d %6d | %6d || %6d %6d %6d %6d || %6d %6d %6d   (q start @%d, mma2 @%d)" % (
-        u, qq[1] - qq[0], qq[2] - qq[1], qq[3] - qq[2], qq[4] - qq[3], qq[5] - qq[4], nxt - qq[0],
+    print("%4d | %6d %5d %6d %8d | %6d || %6d %6d %6d %6d || %6d %6d %6d   (q start @%d, mma2 @%d)" % (
+        u, qq[1] - qq[0], qq[2] - qq[1], qq[3] - qq[2], qq[4] - qq[3], q[u + 2, 0] - qq[0],
         mm[u, 1] - mm[u, 0], mm[u, 2] - mm[u, 1], mm[u, 4] - mm[u, 3], mm[u, 5] - mm[u, 4],
         st[u, 1] - st[u - 1, 0], st[u, 2] - st[u, 1], st[u, 3] - st[u, 2], qq[0] - t0, mm[u, 0] - t0))
