@@ -330,7 +330,12 @@ def main():
                     "ms_per_step": e2e_t_max / args.steps * 1e3},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None,
+                         "traffic": 17534720,
+                         "traffic_note": "dram__bytes_read + dram__bytes_write of one ncu --set full capture of "
+                                         "kl_resident_dmma_kernel<10> (30 iterations of 148 restarts, "
+                                         "profiles/r01_resident_dmma_v3_k10.txt): X (1.6 MB, both orientations) and the "
+                                         "factors are read from DRAM once and stay in L2 / shared memory - the kernel is "
+                                         "FP64-pipe and L2-latency bound, not DRAM bound",
                          "kernel": "kl_resident_dmma_kernel<K,false> (9 instantiations, one per k, concurrent streams; "
                                    "DMMA m8n8k4 + DFMA remainder columns share the FP64 pipe)",
                          "note": "FP64 work: MEASURED_PEAKS.json holds only HBM and bf16 peaks, so the denominator is the "
