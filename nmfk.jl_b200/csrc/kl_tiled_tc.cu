@@ -15,8 +15,10 @@
 // Warp roles (704 threads): warp 0 = bulk-copy producer of X tiles (cp.async.bulk + mbarrier transaction
 // counts, 3 stages), warp 1 = tcgen05.mma issuer (elect.sync regions), warps 2-5 = V stagers (cp.async two units
 // ahead -> hi/lo split -> the two canonical un-swizzled K-major images MMA#1 and MMA#2 read), warps 6-21 =
-// quotient warps (lane quarter = warp % 4, 16 of the 64 columns each).  P/Q tiles are double-buffered in tensor memory so the tensor pipe
-// works on unit u+1 / u+2 while the quotient warps divide unit u.
+// quotient warps (lane quarter = warp % 4): two GROUPS of 8 warps that alternate units (32 of the 64 columns per
+// thread), so one group divides while the other waits for the tensor-pipe round trip of its P tile.  P/Q tiles are
+// double-buffered in tensor memory (one buffer per group; a third one when k <= 8).  With OBJ the same machinery
+// computes the objective sums (MMA#1 only, 16 warps x 16 columns in lockstep).
 // tcgen05.mma accumulates with round-toward-zero (measured: -0.47 ulp per chained instruction, tools/umma_selftest.py
 // --timing), so numerators are NOT chained across units: MMA#2 of every unit starts a fresh tensor-memory
 // accumulator (8 chained K-steps) that the quotient warps add into FP32 registers with round-to-nearest.
