@@ -326,21 +326,61 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
         const bool vec16 = t_major ? ((a.sv_a & 3) == 0 && (a.v_rstride & 3) == 0)
                                    : (a.sv_a == 1 && (k & 3) == 0 && (a.sv_t & 3) == 0 && (a.v_rstride & 3) == 0);
         constexpr int RAWF = C::RAW_BYTES / 4, PT = C::RAWP_T, PA = C::RAWP_A;
+        constexpr int NAB = K8 / 4, NTB = TC_TS / 4;
+        constexpr int ITA = TC_TS * NAB / NS, ITB = K8 * NTB / NS;  // items per thread and pass
+        static_assert(ITA * NS == TC_TS * NAB && ITB * NS == K8 * NTB && ITA >= 1, "stager work split");
+        // per-thread constants of the two conversion passes (the items of a thread never change): raw index of the first
+        // of the 4 values, image byte offset
+        int rawA[ITA], rawB[ITB > 0 ? ITB : 1];
+        uint32_t offA[ITA], offB[ITB > 0 ? ITB : 1];
+#pragma unroll
+        for (int q = 0; q < ITA; ++q) {
+            const int it = sid + q * NS;
+            const int t = (it & 7) + 8 * (it / (8 * NAB)), ab = (it >> 3) % NAB;
+            rawA[q] = t_major ? (ab * 4) * PT + t : t * PA + ab * 4;
+            offA[q] = (t & 7) * 16 + (t >> 3) * C::SBO1 + ab * TC_LBO;
+        }
+#pragma unroll
+        for (int q = 0; q < ITB; ++q) {
+            const int it = sid + q * NS;
+            const int col = (it & 7) + 8 * (it / (8 * NTB)), tb = (it >> 3) % NTB;
+            rawB[q] = t_major ? col * PT + tb * 4 : (tb * 4) * PA + col;
+            offB[q] = 2 * C::B1_BYTES + (col & 7) * 16 + (col >> 3) * C::SBO2 + tb * TC_LBO;
+        }
+        // ... and of the 16-byte copies of the raw chunk: element offset in V relative to the first step of the unit,
+        // raw index, step within the unit, column in range
+        constexpr int NCP = K8 * (TC_TS / 4) / NS;
+        static_assert(NCP * NS == K8 * (TC_TS / 4), "copy split");
+        long long cpg[NCP];
+        int cps[NCP], cpt[NCP];
+        bool cpok[NCP];
+#pragma unroll
+        for (int i = 0; i < NCP; ++i) {
+            const int e = sid + i * NS;
+            if (t_major) {
+                const int col = e / (TC_TS / 4), t4 = (e % (TC_TS / 4)) * 4;
+                cpg[i] = (long long)t4 + (long long)col * a.sv_a;
+                cps[i] = col * PT + t4;
+                cpt[i] = t4;
+                cpok[i] = col < k;
+            } else {
+                const int tl = e / (K8 / 4), a4 = (e % (K8 / 4)) * 4;
+                cpg[i] = (long long)tl * a.sv_t + a4;
+                cps[i] = tl * PA + a4;
+                cpt[i] = tl;
+                cpok[i] = a4 < k;
+            }
+        }
         auto issue_raw = [&](int c, int b, int stage) {
             const float* V = Vg + (long long)s_act[b] * a.v_rstride;
             const int t0 = t_begin + c * TC_TS;
             float* dst = Raw + (size_t)stage * RAWF;
-            if (vec16 && t_major) {
-                for (int e = sid; e < K8 * (TC_TS / 4); e += NS) {
-                    const int col = e / (TC_TS / 4), t4 = (e % (TC_TS / 4)) * 4;
-                    const bool live = (t0 + t4 < t_end) && (col < k);
-                    tc::cp_async16_zfill(dst + col * PT + t4, live ? V + (long long)(t0 + t4) + (long long)col * a.sv_a : V, live ? 16u : 0u);
-                }
-            } else if (vec16) {
-                for (int e = sid; e < TC_TS * (K8 / 4); e += NS) {
-                    const int tl = e / (K8 / 4), a4 = (e % (K8 / 4)) * 4;
-                    const bool live = (t0 + tl < t_end) && (a4 < k);
-                    tc::cp_async16_zfill(dst + tl * PA + a4, live ? V + (long long)(t0 + tl) * a.sv_t + a4 : V, live ? 16u : 0u);
+            if (vec16) {
+                const float* Vu = V + (long long)t0 * (t_major ? 1 : a.sv_t);
+#pragma unroll
+                for (int i = 0; i < NCP; ++i) {
+                    const bool live = cpok[i] && (t0 + cpt[i] < t_end);
+                    tc::cp_async16_zfill(dst + cps[i], live ? Vu + cpg[i] : V, live ? 16u : 0u);
                 }
             } else {
                 for (int e = sid; e < TC_TS * K8; e += NS) {
@@ -373,9 +413,6 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
             advance();
         }
         tc::cp_async_commit();
-        constexpr int NAB = K8 / 4, NTB = TC_TS / 4;
-        constexpr int ITA = TC_TS * NAB / NS, ITB = K8 * NTB / NS;  // items per thread and pass
-        static_assert(ITA * NS == TC_TS * NAB && ITB * NS == K8 * NTB && ITA >= 1, "stager work split");
         for (int u = 0; u < total; ++u) {
             tc::cp_async_wait<1>();           // this thread's copies of unit u have landed (unit u + 1 may be in flight)
             tc::named_bar_sync(1, NS);        // ... and everybody else's
@@ -392,27 +429,23 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                 float v[ITA][4];
 #pragma unroll
                 for (int q = 0; q < ITA; ++q) {
-                    const int it = sid + q * NS;
-                    const int t = (it & 7) + 8 * (it / (8 * NAB)), ab = (it >> 3) % NAB;
                     if (t_major) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) v[q][j] = raw[(ab * 4 + j) * PT + t];
+                        for (int j = 0; j < 4; ++j) v[q][j] = raw[rawA[q] + j * PT];
                     } else {
-                        const float4 w = *reinterpret_cast<const float4*>(raw + t * PA + ab * 4);
+                        const float4 w = *reinterpret_cast<const float4*>(raw + rawA[q]);
                         v[q][0] = w.x, v[q][1] = w.y, v[q][2] = w.z, v[q][3] = w.w;
                     }
                 }
 #pragma unroll
                 for (int q = 0; q < ITA; ++q) {
-                    const int it = sid + q * NS;
-                    const int t = (it & 7) + 8 * (it / (8 * NAB)), ab = (it >> 3) % NAB;
                     float h[4], l[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         h[j] = __uint_as_float(__float_as_uint(v[q][j]) & 0xffffe000u);
                         l[j] = v[q][j] - h[j];
                     }
-                    const uint32_t off = (t & 7) * 16 + (t >> 3) * C::SBO1 + ab * TC_LBO;
+                    const uint32_t off = offA[q];
                     *reinterpret_cast<float4*>(base + off) = make_float4(h[0], h[1], h[2], h[3]);
                     *reinterpret_cast<float4*>(base + C::B1_BYTES + off) = make_float4(l[0], l[1], l[2], l[3]);
                 }
@@ -422,27 +455,23 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
                 float v[ITB][4];
 #pragma unroll
                 for (int q = 0; q < ITB; ++q) {
-                    const int it = sid + q * NS;
-                    const int col = (it & 7) + 8 * (it / (8 * NTB)), tb = (it >> 3) % NTB;
                     if (t_major) {
-                        const float4 w = *reinterpret_cast<const float4*>(raw + col * PT + tb * 4);
+                        const float4 w = *reinterpret_cast<const float4*>(raw + rawB[q]);
                         v[q][0] = w.x, v[q][1] = w.y, v[q][2] = w.z, v[q][3] = w.w;
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) v[q][i] = raw[(tb * 4 + i) * PA + col];
+                        for (int i = 0; i < 4; ++i) v[q][i] = raw[rawB[q] + i * PA];
                     }
                 }
 #pragma unroll
                 for (int q = 0; q < ITB; ++q) {
-                    const int it = sid + q * NS;
-                    const int col = (it & 7) + 8 * (it / (8 * NTB)), tb = (it >> 3) % NTB;
                     float h[4], l[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         h[i] = __uint_as_float(__float_as_uint(v[q][i]) & 0xffffe000u);
                         l[i] = v[q][i] - h[i];
                     }
-                    const uint32_t off = 2 * C::B1_BYTES + (col & 7) * 16 + (col >> 3) * C::SBO2 + tb * TC_LBO;
+                    const uint32_t off = offB[q];
                     *reinterpret_cast<float4*>(base + off) = make_float4(h[0], h[1], h[2], h[3]);
                     *reinterpret_cast<float4*>(base + C::B2_BYTES + off) = make_float4(l[0], l[1], l[2], l[3]);
                 }
