@@ -38,20 +38,20 @@ constexpr int TC_NRAW = 4;
 constexpr uint32_t TC_LBO = 128;
 
 // K8 / N2: k rounded up to the K granularity of MMA#1 (8) / the N granularity of MMA#2 (16).
-// WIDE = true : one CTA per SM, chunks of 64 steps, 16 quotient + 4 stager warps, 512 tensor-memory columns (k > 16).
-// WIDE = false: TWO CTAs per SM, chunks of 32 steps, 8 quotient + 2 stager warps, 256 columns each (k <= 16): the two
-//               CTAs run out of phase, so one divides (MUFU-bound) while the other waits on its tensor-pipe round trip.
-template <int K8, int N2, bool WIDE>
+// One CTA per SM: chunks of 64 steps, 16 quotient + 4 stager warps, all 512 tensor-memory columns.  (A configuration with
+// TWO CTAs per SM - chunks of 32 steps, 8 quotient + 2 stager warps, 256 columns each - measured slower on C3, 3083 vs
+// 3489 restart-iterations/s at the time: the per-unit hand-offs are paid twice as often.  It was removed.)
+template <int K8, int N2>
 struct TcCfg {
-    static constexpr int TS = WIDE ? 64 : 32;                         // steps per chunk
+    static constexpr int TS = 64;                                     // steps per chunk
     static constexpr int NXS = 3;                                     // X tile stages
     static constexpr int NVB = K8 <= 16 ? 4 : 3;                      // V image buffers (shared memory budget for k > 16)
-    static constexpr int RPAD = (WIDE && K8 > 24) ? 0 : 4;            // raw V chunk padding (shared memory budget at K8 = 32)
+    static constexpr int RPAD = K8 > 24 ? 0 : 4;                      // raw V chunk padding (shared memory budget at K8 = 32)
     static constexpr int QW = TS / 4;                                 // quotient warps: lane quarter = warp % 4, 16 columns each
-    static constexpr int SW = WIDE ? 4 : 2;                           // V stager warps
+    static constexpr int SW = 4;                                      // V stager warps
     static constexpr int QW0 = 2 + SW;                                // first quotient warp
     static constexpr int THREADS = (QW0 + QW) * 32;
-    static constexpr int TCOLS = WIDE ? 512 : 256;                    // tensor-memory columns of the CTA
+    static constexpr int TCOLS = 512;                                 // tensor-memory columns of the CTA
     static constexpr int NCS = QW / 4;                                // column groups of quotient warps
     static constexpr int NST = N2 == 16 ? 2 : 1;                      // MMA#2: Qhi * [Vhi ; Vlo] stacked along N
     static constexpr int ACOLS = NST * N2;                            // columns of one per-unit numerator buffer
@@ -98,9 +98,9 @@ __device__ __forceinline__ float rcp_fast(float p) {
 
 // OBJ = true: objective mode.  Only MMA#1 runs (P = U V^T); the quotient warps accumulate (x - p)^2 instead of dividing,
 // nothing is written back to the factors: replaces tiled_objective_kernel (NMFkMultiplicative.jl:74,125) for Float32.
-template <int K8, int N2, bool WIDE, bool OBJ>
-__global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)) tc_pass_kernel(const TiledPassArgs a, int* errflag) {
-    using C = TcCfg<K8, N2, WIDE>;
+template <int K8, int N2, bool OBJ>
+__global__ void __launch_bounds__((TcCfg<K8, N2>::THREADS), 1) tc_pass_kernel(const TiledPassArgs a, int* errflag) {
+    using C = TcCfg<K8, N2>;
     constexpr int TC_NXS = C::NXS, TC_NVB = C::NVB;
     constexpr int TC_TS = C::TS, TC_QWARPS = C::QW, TC_SWARPS = C::SW, TC_QW0 = C::QW0, TC_THREADS = C::THREADS;
     constexpr int RB = C::RB;
@@ -710,28 +710,26 @@ __global__ void __launch_bounds__((TcCfg<K8, N2, WIDE>::THREADS), (WIDE ? 1 : 2)
     if (warp == 0) tc::tmem_dealloc<C::TCOLS>(tbase);
 }
 
-template <int K8, int N2, bool WIDE, bool OBJ>
+template <int K8, int N2, bool OBJ>
 cudaError_t launch_tc(const TiledPassArgs& a, int* d_errflag, cudaStream_t s) {
-    using C = TcCfg<K8, N2, WIDE>;
+    using C = TcCfg<K8, N2>;
     const int ngroups = (a.R + C::RB - 1) / C::RB;
     const long long grid = (long long)a.S * a.nblocks * ngroups;
     if (grid > 2147483647ll) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(tc_pass_kernel<K8, N2, WIDE, OBJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(tc_pass_kernel<K8, N2, OBJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) return e;
-    tc_pass_kernel<K8, N2, WIDE, OBJ><<<(unsigned)grid, C::THREADS, C::SMEM, s>>>(a, d_errflag);
+    tc_pass_kernel<K8, N2, OBJ><<<(unsigned)grid, C::THREADS, C::SMEM, s>>>(a, d_errflag);
     return cudaGetLastError();
 }
 
 }  // namespace
 
 int tc_pass_group(int k) {
-    if (k <= 8) return TcCfg<8, 16, true>::RB;
-    if (k <= 16) return TcCfg<16, 16, true>::RB;
-    if (k <= 24) return TcCfg<24, 32, true>::RB;
-    return TcCfg<32, 32, true>::RB;
+    if (k <= 8) return TcCfg<8, 16>::RB;
+    if (k <= 16) return TcCfg<16, 16>::RB;
+    if (k <= 24) return TcCfg<24, 32>::RB;
+    return TcCfg<32, 32>::RB;
 }
-// The two-CTAs-per-SM configuration (WIDE = false, chunks of 32 steps) measured SLOWER than the wide one on C3
-// (3083 vs 3489 restart-iterations/s: the per-unit hand-offs are paid twice as often), so every k uses WIDE.
 int tc_pass_ctas_per_sm(int) { return 1; }
 int tc_pass_chunk(int) { return 64; }
 
@@ -741,17 +739,17 @@ bool tc_pass_supported(const TiledPassArgs& a) {
 }
 
 cudaError_t launch_tc_pass(const TiledPassArgs& a, int* d_errflag, cudaStream_t s) {
-    if (a.k <= 8) return launch_tc<8, 16, true, false>(a, d_errflag, s);
-    if (a.k <= 16) return launch_tc<16, 16, true, false>(a, d_errflag, s);
-    if (a.k <= 24) return launch_tc<24, 32, true, false>(a, d_errflag, s);
-    return launch_tc<32, 32, true, false>(a, d_errflag, s);
+    if (a.k <= 8) return launch_tc<8, 16, false>(a, d_errflag, s);
+    if (a.k <= 16) return launch_tc<16, 16, false>(a, d_errflag, s);
+    if (a.k <= 24) return launch_tc<24, 32, false>(a, d_errflag, s);
+    return launch_tc<32, 32, false>(a, d_errflag, s);
 }
 
 cudaError_t launch_tc_objective(const TiledPassArgs& a, int* d_errflag, cudaStream_t s) {
-    if (a.k <= 8) return launch_tc<8, 16, true, true>(a, d_errflag, s);
-    if (a.k <= 16) return launch_tc<16, 16, true, true>(a, d_errflag, s);
-    if (a.k <= 24) return launch_tc<24, 32, true, true>(a, d_errflag, s);
-    return launch_tc<32, 32, true, true>(a, d_errflag, s);
+    if (a.k <= 8) return launch_tc<8, 16, true>(a, d_errflag, s);
+    if (a.k <= 16) return launch_tc<16, 16, true>(a, d_errflag, s);
+    if (a.k <= 24) return launch_tc<24, 32, true>(a, d_errflag, s);
+    return launch_tc<32, 32, true>(a, d_errflag, s);
 }
 
 }  // namespace nmfk
