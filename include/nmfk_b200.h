@@ -183,7 +183,16 @@ int32_t nmfk_ctx_comm_destroy(nmfk_ctx* ctx);
 int32_t nmfk_batch_cluster(nmfk_batch* b, int32_t clusterWmatrix, int32_t* order, int32_t* labels, double* sil,
                            double* clustersil, double* robustness, void* centroids, int32_t* centroid_cols);
 
+/* Wmean, Hmean, Wvar, Hvar of finalize(Wa, Ha, idx) (NMFkFinalize.jl:68-74): per cluster, the mean and the corrected
+ * variance over the nNMF trials of the column of W / row of H that clustersolutions assigned to it - what execute_run returns
+ * with best=false (NMFkExecute.jl:655-658) and what the "-all" result file stores (:650-654).  order (R) and labels (k x R,
+ * 1-based, column-major) are the outputs of nmfk_batch_cluster; W outputs are n x k, H outputs k x m (column-major, the
+ * batch's dtype); any output may be NULL. */
+int32_t nmfk_batch_cluster_means(nmfk_batch* b, const int32_t* order, const int32_t* labels, void* Wmean, void* Hmean,
+                                 void* Wvar, void* Hvar);
+
 /* ---- one-call forms --------------------------------------------------------------------- */
+
 /* NMFmultiplicative for R stacked restarts at one k, host buffers in and out
  * (NMFkMultiplicative.jl:24-127 + NMFkExecute.jl:791-804 when p->normalize != 0). */
 int32_t nmfk_run_batch(nmfk_ctx* ctx, int32_t k, int32_t R, const void* Winit, const void* Hinit,

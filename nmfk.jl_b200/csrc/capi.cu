@@ -781,6 +781,55 @@ int32_t nmfk_fit(nmfk_ctx* c, int32_t k, const void* W, const void* H, double* p
     return NMFK_OK;
 }
 
+// Wmean, Hmean, Wvar, Hvar of finalize (NMFkFinalize.jl:68-74): what execute_run returns with best=false (:655-658) and what
+// the "-all" result file stores (:650-654).  order / labels as returned by nmfk_batch_cluster (labels k x R, 1-based, column t =
+// trial t in sorted order).  Any output may be NULL.
+int32_t nmfk_batch_cluster_means(nmfk_batch* b, const int32_t* order, const int32_t* labels, void* Wmean, void* Hmean,
+                                 void* Wvar, void* Hvar) {
+    if (!b || !order || !labels) return fail(b ? b->ctx : nullptr, NMFK_E_INVALID, "nmfk_batch_cluster_means: NULL argument");
+    nmfk_ctx* c = b->ctx;
+    CU(c, cudaSetDevice(c->device));
+    const int k = b->k, R = b->R;
+    const long long n = c->n, m = c->m;
+    if ((Wmean || Wvar) && !b->W) return fail(c, NMFK_E_INVALID, "nmfk_batch_cluster_means: W statistics on an H-only batch");
+    std::vector<int32_t> amap((size_t)k * R, -1);
+    for (int t = 0; t < R; ++t) {
+        if (order[t] < 0 || order[t] >= R) return fail(c, NMFK_E_INVALID, "nmfk_batch_cluster_means: order out of range");
+        for (int a = 0; a < k; ++a) {
+            const int lab = labels[(size_t)t * k + a];
+            if (lab >= 1 && lab <= k && amap[(size_t)(lab - 1) * R + t] < 0) amap[(size_t)(lab - 1) * R + t] = a;
+        }
+    }
+    const size_t es = esize(c->dtype);
+    int32_t *d_order = nullptr, *d_amap = nullptr;
+    unsigned char* d_out = nullptr;
+    const size_t wbytes = (size_t)n * k * es, hbytes = (size_t)k * m * es;
+    cudaError_t e = cudaMalloc(&d_order, (size_t)R * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_amap, amap.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, 2 * (wbytes + hbytes));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_order, order, (size_t)R * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_amap, amap.data(), amap.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
+    unsigned char *dWm = d_out, *dWv = d_out + wbytes, *dHm = d_out + 2 * wbytes, *dHv = dHm + hbytes;
+    if (e == cudaSuccess && (Wmean || Wvar)) {
+        e = launch_cluster_means(b->W, (int)n, k, R, 1, d_order, d_amap, dWm, dWv, c->dtype, c->stream);
+        c->launches += 1;
+    }
+    if (e == cudaSuccess && (Hmean || Hvar)) {
+        e = launch_cluster_means(b->H, (int)m, k, R, 0, d_order, d_amap, dHm, dHv, c->dtype, c->stream);
+        c->launches += 1;
+    }
+    if (e == cudaSuccess && Wmean) e = cudaMemcpyAsync(Wmean, dWm, wbytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && Wvar) e = cudaMemcpyAsync(Wvar, dWv, wbytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && Hmean) e = cudaMemcpyAsync(Hmean, dHm, hbytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && Hvar) e = cudaMemcpyAsync(Hvar, dHv, hbytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_order);
+    cudaFree(d_amap);
+    cudaFree(d_out);
+    CU(c, e);
+    return NMFK_OK;
+}
+
 int32_t nmfk_run_batch(nmfk_ctx* c, int32_t k, int32_t R, const void* Winit, const void* Hinit, const nmfk_params* p,
                        void* W_out, void* H_out, double* obj_ssq, double* obj_norm, int32_t* iters,
                        int32_t* stop_reason) {

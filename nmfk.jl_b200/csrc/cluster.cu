@@ -302,6 +302,55 @@ cudaError_t launch_zero_nan(void* p, long long len, int dtype, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// Wmean / Wvar (or Hmean / Hvar) of NMFkFinalize.jl:68-74: for cluster c and trial t (sorted order) take the column of W_t
+// (row of H_t) that clustersolutions assigned to c, then mean and corrected variance over the R trials.
+// amap[c * R + t] = 0-based row / column index of trial t's member of cluster c (-1: none), order[t] = restart of trial t.
+// Two passes in Float64 (mean, then squared deviations) like Statistics.mean / Statistics.var.
+template <typename T>
+__global__ void __launch_bounds__(256) cluster_means_kernel(const T* __restrict__ F, int len, int k, int R, int use_W,
+                                                            const int32_t* __restrict__ order, const int32_t* __restrict__ amap,
+                                                            T* __restrict__ mean_out, T* __restrict__ var_out) {
+    const int c = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= len) return;
+    const long long rstride = (long long)len * k;
+    auto at = [&](int t) -> double {
+        const int a = amap[c * R + t];
+        const T* Fr = F + (long long)order[t] * rstride;
+        return (double)(use_W ? Fr[(long long)e + (long long)a * len] : Fr[(long long)a + (long long)e * k]);
+    };
+    double sum = 0.0;
+    int cnt = 0;
+    for (int t = 0; t < R; ++t)
+        if (amap[c * R + t] >= 0) {
+            sum += at(t);
+            ++cnt;
+        }
+    const double mean = cnt > 0 ? sum / cnt : nan("");
+    double ss = 0.0;
+    for (int t = 0; t < R; ++t)
+        if (amap[c * R + t] >= 0) {
+            const double d = at(t) - mean;
+            ss = fma(d, d, ss);
+        }
+    const double var = cnt > 1 ? ss / (cnt - 1) : nan("");
+    const long long o = use_W ? ((long long)e + (long long)c * len) : ((long long)c + (long long)e * k);
+    mean_out[o] = (T)mean;
+    var_out[o] = (T)var;
+}
+
+cudaError_t launch_cluster_means(const void* F, int len, int k, int R, int use_W, const int32_t* d_order, const int32_t* d_amap,
+                                 void* mean_out, void* var_out, int dtype, cudaStream_t s) {
+    dim3 g((len + 255) / 256, k);
+    if (dtype == 1)
+        cluster_means_kernel<double><<<g, 256, 0, s>>>((const double*)F, len, k, R, use_W, d_order, d_amap, (double*)mean_out,
+                                                       (double*)var_out);
+    else
+        cluster_means_kernel<float><<<g, 256, 0, s>>>((const float*)F, len, k, R, use_W, d_order, d_amap, (float*)mean_out,
+                                                      (float*)var_out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_cluster(const ClusterArgs& a, int dtype, cudaStream_t s) {
     const int N = a.R * a.k, ld = a.len + 1;
     cudaError_t e;

@@ -114,6 +114,9 @@ struct ClusterArgs {
 };
 cudaError_t launch_cluster(const ClusterArgs& a, int dtype, cudaStream_t s);
 cudaError_t launch_zero_nan(void* p, long long len, int dtype, cudaStream_t s);
+// per-cluster means / corrected variances over the trials (NMFkFinalize.jl:68-74); outputs are device buffers of the factor type
+cudaError_t launch_cluster_means(const void* F, int len, int k, int R, int use_W, const int32_t* d_order, const int32_t* d_amap,
+                                 void* mean_out, void* var_out, int dtype, cudaStream_t s);
 
 // micro-benchmarks
 cudaError_t measure_peak(int which, double* value, cudaStream_t s);

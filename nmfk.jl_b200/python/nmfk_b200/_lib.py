@@ -65,6 +65,7 @@ SIGNATURES = {
     "nmfk_batch_get": (_i32, [_P, _P, _P, _pdbl, _pdbl, _pi32, _pi32]),
     "nmfk_batch_objective": (_i32, [_P, _dbl, _pdbl]),
     "nmfk_batch_cluster": (_i32, [_P, _i32, _pi32, _pi32, _pdbl, _pdbl, _pdbl, _P, _pi32]),
+    "nmfk_batch_cluster_means": (_i32, [_P, _pi32, _pi32, _P, _P, _P, _P]),
     "nmfk_run_batch": (_i32, [_P, _i32, _i32, _P, _P, C.POINTER(Params), _P, _P, _pdbl, _pdbl, _pi32, _pi32]),
     "nmfk_trace": (_i32, [_P, _i32, _P, _P, C.POINTER(Params), _i32, _P, _P, _pdbl]),
     "nmfk_execute_run": (_i32, [_P, _i32, _i32, _P, _P, _u64, C.POINTER(Params), _P, _P, _pdbl, _pdbl, _pdbl, _pi64]),

@@ -207,6 +207,20 @@ class Batch:
                     centroids=cent[:cols.value].T if cols.value else None)
 
 
+    def cluster_means(self, order: np.ndarray, labels: np.ndarray):
+        """Wmean, Hmean, Wvar, Hvar of finalize (NMFkFinalize.jl:68-74) from the outputs of `cluster()`:
+        -> dict(W (n,k), H (k,m), Wvar (n,k), Hvar (k,m))."""
+        c = self.ctx
+        k = self.k
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        lab = np.ascontiguousarray(np.asarray(labels, dtype=np.int32).T)  # (R, k): column-major k x R
+        Wm, Wv = np.empty((k, c.n), dtype=c.np_dtype), np.empty((k, c.n), dtype=c.np_dtype)
+        Hm, Hv = np.empty((c.m, k), dtype=c.np_dtype), np.empty((c.m, k), dtype=c.np_dtype)
+        check(c._lib.nmfk_batch_cluster_means(self._h, order.ctypes.data_as(_lib._pi32), lab.ctypes.data_as(_lib._pi32),
+                                              _ptr(Wm), _ptr(Hm), _ptr(Wv), _ptr(Hv)), c._h)
+        return dict(W=Wm.T, H=Hm.T, Wvar=Wv.T, Hvar=Hv.T)
+
+
 # ------------------------------------------------------------------------------------------
 # reference-shaped functions
 # ------------------------------------------------------------------------------------------

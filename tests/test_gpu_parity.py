@@ -480,3 +480,25 @@ def test_execute_through_tensor_tiled_engines_same_decisions(ctx):
         r2, r4 = np.asarray(out[2][1][1:5], dtype=float), np.asarray(out[4][1][1:5], dtype=float)
         assert np.array_equal(r2 > 0.5, r4 > 0.5)
         assert np.allclose(np.asarray(out[2][0][1:5], dtype=float), np.asarray(out[4][0][1:5], dtype=float), rtol=tol, atol=tol)
+
+
+def test_cluster_means_and_variances_match_finalize(ctx):
+    """Wmean / Hmean / Wvar / Hvar of finalize (NMFkFinalize.jl:68-74; what best=false returns) against the oracle, from the
+    same restart solutions, sort order and labels."""
+    for dt, tol in ((np.float64, 1e-12), (np.float32, 2e-6)):
+        X = synth.mixture(90, 40, 3, seed=12, dtype=dt)
+        k, R = 4, 7
+        ctx.set_X(X)
+        b = ctx.batch(k, R)
+        b.init_random(321)
+        ctx.solve([b], nb.default_params(maxiter=300))
+        cl = b.cluster()
+        sol = b.get()  # after cluster(): NaN entries zeroed like the reference does before finalize
+        st = b.cluster_means(cl["order"], cl["labels"])
+        b.close()
+        Wa = [np.asarray(sol["W"][r], dtype=dt) for r in cl["order"]]
+        Ha = [np.asarray(sol["H"][r], dtype=dt) for r in cl["order"]]
+        Wm, Hm, _, Wv, Hv = o.finalize(Wa, Ha, np.asarray(cl["labels"]), False)
+        for got, ref in ((st["W"], Wm), (st["H"], Hm), (st["Wvar"], Wv), (st["Hvar"], Hv)):
+            assert got.shape == ref.shape
+            assert np.allclose(got, ref, rtol=tol, atol=tol * max(1.0, float(np.max(np.abs(ref)))))
