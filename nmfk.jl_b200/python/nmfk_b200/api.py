@@ -112,6 +112,15 @@ class Context:
     def last_solve_ms(self) -> float:
         return float(self._lib.nmfk_last_solve_ms(self._h))
 
+    def fit(self, W: np.ndarray, H: np.ndarray) -> float:
+        """normnan(X - W*H) with NaN residuals zeroed (NMFkExecute.jl:664-668, :212-222) for host factors W (n,k), H (k,m)."""
+        Wf, Hf = _f(W, self.np_dtype), _f(H, self.np_dtype)
+        k = Wf.shape[1]
+        assert Wf.shape == (self.n, k) and Hf.shape == (k, self.m)
+        phi = C.c_double()
+        check(self._lib.nmfk_fit(self._h, k, _ptr(Wf), _ptr(Hf), C.byref(phi)), self._h)
+        return phi.value
+
     def measure_peak(self, which: int) -> float:
         v = C.c_double()
         check(self._lib.nmfk_measure_peak(self._h, which, C.byref(v)), self._h)
@@ -292,10 +301,37 @@ def execute_singlerun(X, nk: int, *, Winit=None, Hinit=None, seed: int = -1, clu
             ctx.close()
 
 
+def _execute_run_means(ctx, X, nk, nNMF, clusterWmatrix, seed0, inits, p, details):
+    """best=false (NMFkExecute.jl:655-658 not taken): Wa, Ha = the per-cluster means of finalize (:637), phi and aic
+    from them (:664-708).  Same device calls as the best=true path, composed on the host."""
+    import math
+    n, m, dt = ctx.n, ctx.m, ctx.np_dtype
+    b = ctx.batch(nk, nNMF)
+    try:
+        if inits is not None:
+            b.set_init(np.asarray(inits[0], dtype=dt), np.asarray(inits[1], dtype=dt))
+        else:
+            b.init_random(seed0)
+        ctx.solve([b], p)
+        cl = b.cluster(clusterWmatrix)
+        st = b.cluster_means(cl["order"], cl["labels"])
+        tot = int(b.get(factors=False)["iters"].sum())
+    finally:
+        b.close()
+    Wa, Ha = np.asfortranarray(st["W"]), np.asfortranarray(st["H"])
+    phi = ctx.fit(Wa, Ha)
+    nobs = int(np.sum(~np.isnan(np.asarray(X))))
+    aic = 2 * (Wa.size + Ha.size) + nobs * math.log(phi / nobs) if phi > 0 else -math.inf
+    if details is not None:
+        details.update(total_iters=tot, solve_ms=ctx.last_solve_ms)
+    return Wa, Ha, dt(phi), dt(cl["robustness"]), aic
+
+
 def execute_run(X, nk: int, nNMF: int, *, clusterWmatrix: bool = False, seed: Optional[int] = None, inits=None,
-                ctx: Context = None, details: Optional[dict] = None, **kw):
+                ctx: Context = None, details: Optional[dict] = None, best: bool = True, **kw):
     """`execute_run(X, nk, nNMF; ...)` NMFkExecute.jl:483-711 (defaults acceptratio=1,
     acceptfactor=Inf, nanaction=:zeroed, best=true) -> (Wa, Ha, phi, minsilhouette, aic).
+    best=False returns the per-cluster means of `finalize` instead of the best restart (nk > 1).
     `seed`: restart i draws from Philox(key=seed+i) (the `seed=kwseed+i` of :536);
     `inits=(Winit (R,n,k), Hinit (R,k,m))` injects explicit initialisations."""
     own = ctx is None
@@ -315,6 +351,10 @@ def execute_run(X, nk: int, nNMF: int, *, clusterWmatrix: bool = False, seed: Op
             Hi = np.ascontiguousarray(np.transpose(np.asarray(inits[1], dtype=dt), (0, 2, 1)))
             assert Wi.shape == (nNMF, nk, n) and Hi.shape == (nNMF, m, nk)
         seed0 = int(seed) if seed is not None else int(np.random.randint(0, 2 ** 31))
+        if not best:
+            if nk == 1:
+                raise NMFkError(-6, "best=false with nk == 1 is not on the B200 path")
+            return _execute_run_means(ctx, X, nk, nNMF, clusterWmatrix, seed0, inits, p, details)
         check(ctx._lib.nmfk_execute_run(ctx._h, nk, nNMF, _ptr(Wi), _ptr(Hi), seed0, C.byref(p), _ptr(Wb), _ptr(Hb),
                                         C.byref(phi), C.byref(rob), C.byref(aic), C.byref(tot)), ctx._h)
         if details is not None:

@@ -456,10 +456,12 @@ def execute_run(
     inits: Optional[Sequence] = None,
     init_fn: Optional[Callable[[int, int, int, int], tuple]] = None,
     details: Optional[dict] = None,
+    best: bool = True,
     **kw,
 ):
     """`execute_run(X::AbstractMatrix, nk, nNMF; ...)` src/NMFkExecute.jl:483-711 with the
-    defaults acceptratio=1, acceptfactor=Inf, nanaction=:zeroed, best=true, serial.
+    defaults acceptratio=1, acceptfactor=Inf, nanaction=:zeroed, serial; best=false returns the
+    per-cluster means of finalize (:637, :655-658) instead of the best restart (nk > 1 only).
 
     Initialisations: the reference draws from Julia's RNG (seed+i per restart when `seed` is
     given, :532-537).  Here `inits[i] = (Winit, Hinit)` or `init_fn(i, n, nk, m)` (i is the
@@ -502,9 +504,13 @@ def execute_run(
         for i, c in enumerate(ci):  # :631-635
             Wbest[:, i] = WBig[bestIdx][:, c - 1]
             Hbest[i, :] = HBig[bestIdx][c - 1, :]
-        _, _, clustersil, _, _ = finalize(Ws, Hs, labels, clusterWmatrix)  # :637
+        Wmean, Hmean, clustersil, _, _ = finalize(Ws, Hs, labels, clusterWmatrix)  # :637
         minsilhouette = T.type(np.min(clustersil))  # :638
     Wa, Ha = Wbest, Hbest  # best == true, :655-658
+    if not best:
+        if nk == 1:
+            raise NotImplementedError("best=false with nk == 1 uses finalize(WBig, HBig) (:648), not restated")
+        Wa, Ha = Wmean, Hmean
     E = X - Wa @ Ha  # :664
     E[np.isnan(E)] = 0  # :667
     phi_final = normnan(E)  # :668

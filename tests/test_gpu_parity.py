@@ -502,3 +502,15 @@ def test_cluster_means_and_variances_match_finalize(ctx):
         for got, ref in ((st["W"], Wm), (st["H"], Hm), (st["Wvar"], Wv), (st["Hvar"], Hv)):
             assert got.shape == ref.shape
             assert np.allclose(got, ref, rtol=tol, atol=tol * max(1.0, float(np.max(np.abs(ref)))))
+
+
+def test_execute_run_best_false_returns_cluster_means(ctx):
+    """execute_run(...; best=false): Wa, Ha are the per-cluster means of finalize, phi / aic are derived from them
+    (NMFkExecute.jl:637, 655-708) - against the oracle from the same initial factors."""
+    X = synth.mixture(120, 30, 3, seed=3)
+    k, R = 3, 6
+    W0, H0 = synth.philox_inits(50, R, 120, k, 30)
+    Wg, Hg, phig, robg, aicg = nb.execute_run(X, k, R, inits=(W0, H0), ctx=ctx, best=False)
+    Wo, Ho, phio, robo, aico = o.execute_run(X.copy(), k, R, inits=[(W0[r].copy(), H0[r].copy()) for r in range(R)], best=False)
+    assert relerr(Wg, Wo) < 1e-7 and relerr(Hg, Ho) < 1e-7
+    assert abs(phig - phio) <= 1e-7 * max(phio, 1e-9) and abs(robg - robo) < 1e-8 and abs(aicg - aico) < 1e-5
