@@ -144,3 +144,20 @@ def test_silhouettes_against_sklearn():
     assert np.allclose(s, ref, atol=1e-12)
     from scipy.spatial.distance import cdist
     assert np.allclose(D, cdist(V, V, "cosine"), atol=1e-12)
+
+
+def test_finalize_means_and_variances_hand_case():
+    """finalize (NMFkFinalize.jl:68-74): per-cluster mean / corrected variance over the trials of the member the labels
+    pick, on a case small enough to do by hand; best=false of execute_run returns exactly these means."""
+    import numpy as np
+    from oracle import nmfk_oracle as o
+    # 3 trials, k = 2: trial 2 has its rows swapped with respect to the clusters
+    H = [np.array([[1.0, 2.0], [10.0, 20.0]]), np.array([[30.0, 40.0], [3.0, 4.0]]), np.array([[5.0, 6.0], [50.0, 60.0]])]
+    W = [np.array([[1.0, 100.0]]), np.array([[300.0, 3.0]]), np.array([[5.0, 500.0]])]
+    idx = np.array([[1, 2, 1], [2, 1, 2]])  # labels[a, t]
+    Wm, Hm, csil, Wv, Hv = o.finalize(W, H, idx, False)
+    assert np.allclose(Hm, [[3.0, 4.0], [30.0, 40.0]])
+    assert np.allclose(Wm, [[3.0, 300.0]])
+    assert np.allclose(Hv, [[4.0, 4.0], [400.0, 400.0]])  # var([1,3,5]) = 4, var([10,30,50]) = 400 (corrected)
+    assert np.allclose(Wv, [[4.0, 40000.0]])
+    assert csil.shape == (2, 1)
