@@ -254,10 +254,23 @@ def _params_from_kw(kw: dict, **defaults) -> Params:
 def NMFmultiplicative(X, k: int, *, Winit=None, Hinit=None, seed: int = -1, lam: float = 1e-32, ctx: Context = None,
                       **kw):
     """`NMFk.NMFmultiplicative(X, k; ...)` NMFkMultiplicative.jl:24-127 -> (W, H, objvalue) with
-    objvalue the sum of squares of :125.  maxiter defaults to 1000000 as in the direct call."""
+    objvalue the sum of squares of :125.  maxiter defaults to 1000000 as in the direct call.
+    `normalizevector` (length n, :27-31, :119-122): the rows of X are divided by it for the solve, W is scaled back and
+    the objective is taken against the caller's X.  (The reference substitutes lambda for zeros BEFORE dividing, so its
+    substituted entries are lambda / normalizevector[i]; here they are lambda: a 1e-32-scale difference.)"""
     own = ctx is None
     ctx = ctx or Context()
     try:
+        nv = kw.pop("normalizevector", None)
+        if nv is not None and len(nv) != 0:
+            Xh = np.asarray(X)
+            nv = np.asarray(nv, dtype=Xh.dtype).reshape(-1)
+            if nv.shape[0] != Xh.shape[0]:
+                raise NMFkError(-4, "Length of normalizing vector does not match: %d vs %d" % (nv.shape[0], Xh.shape[0]))
+            W, H, _ = NMFmultiplicative(Xh / nv[:, None], k, Winit=Winit, Hinit=Hinit, seed=seed, lam=lam, ctx=ctx, **kw)
+            W = np.asfortranarray(W * nv[:, None])
+            ctx.set_X(Xh, lam)
+            return W, H, float(ctx.fit(W, H)) ** 2
         if own or X is not None:
             ctx.set_X(X, lam)
         p = _params_from_kw(kw, maxiter=kw.pop("maxiter", 1000000), normalize=0)

@@ -514,3 +514,15 @@ def test_execute_run_best_false_returns_cluster_means(ctx):
     Wo, Ho, phio, robo, aico = o.execute_run(X.copy(), k, R, inits=[(W0[r].copy(), H0[r].copy()) for r in range(R)], best=False)
     assert relerr(Wg, Wo) < 1e-7 and relerr(Hg, Ho) < 1e-7
     assert abs(phig - phio) <= 1e-7 * max(phio, 1e-9) and abs(robg - robo) < 1e-8 and abs(aicg - aico) < 1e-5
+
+
+def test_normalizevector_matches_oracle(ctx):
+    """NMFmultiplicative(X, k; normalizevector) (NMFkMultiplicative.jl:27-31, 119-122) through the host mirror."""
+    X = synth.mixture(60, 25, 3, seed=8)
+    nv = np.random.default_rng(1).random(60) + 0.5
+    W0, H0 = synth.philox_inits(4, 1, 60, 3, 25)
+    Wg, Hg, og = nb.NMFmultiplicative(X, 3, Winit=W0[0], Hinit=H0[0], normalizevector=nv, maxiter=200, ctx=ctx)
+    Wo, Ho, oo = o.nmf_multiplicative(X.copy(order="F"), 3, Winit=W0[0].copy(), Hinit=H0[0].copy(), normalizevector=nv, maxiter=200)
+    assert relerr(Wg, Wo) < 1e-8 and relerr(Hg, Ho) < 1e-8 and abs(og - oo) <= 1e-7 * max(oo, 1e-12)
+    with pytest.raises(nb.NMFkError):
+        nb.NMFmultiplicative(X, 3, normalizevector=nv[:-1], ctx=ctx)
