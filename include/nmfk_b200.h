@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NMFK_ABI_VERSION 1
+#define NMFK_ABI_VERSION 2
 
 enum nmfk_dtype { NMFK_F32 = 0, NMFK_F64 = 1 };
 
@@ -74,7 +74,7 @@ typedef struct nmfk_params {
     double tol;             /* tol=1e-19 (as reached from execute, NMFkExecute.jl:729) */
     double tolOF;           /* tolOF=1e-3 */
     double eps_clamp;       /* eps() == eps(Float64) = 2.220446049250313e-16, NMFkMultiplicative.jl:99-100 */
-    double weight;          /* scalar weight=1 (vector/matrix weights are not on the B200 path yet) */
+    double weight;          /* scalar weight=1; vector / matrix weights are set on the ctx with nmfk_set_weight and multiply this */
     int32_t maxiter;        /* maxiter=10000 from execute (NMFkExecute.jl:729); 1000000 when called directly */
     int32_t maxbaditers;    /* 10 */
     int32_t maxreattempts;  /* 2 */
@@ -83,11 +83,32 @@ typedef struct nmfk_params {
     int32_t Wfixed;         /* Wfixed=false */
     int32_t Hfixed;         /* Hfixed=false */
     int32_t normalize;      /* execute_singlerun_compute's modifymatrices && mixture==:null: 1 = rows of H sum to one
-                               (NMFkExecute.jl:800-804); 2 = clusterWmatrix variant (:796-799); 0 = raw W,H */
+                               (NMFkExecute.jl:800-804); 2 = its own clusterWmatrix=true branch (:796-799), reached only by a
+                               direct call: execute_run never forwards clusterWmatrix to the restarts (:516-540); 0 = raw W,H */
     int32_t iter_limit;     /* >0: pause every restart once iters reaches this value (resumable); 0 = none */
     int32_t engine;         /* nmfk_engine */
-    int32_t reserved[4];
+    int32_t clusterWmatrix; /* execute_run's own keyword (NMFkExecute.jl:483, 620-637): cluster the columns of W instead of the
+                               rows of H.  Used by nmfk_execute_run / nmfk_execute only; independent of `normalize` */
+    int32_t stop_rule;      /* 0 = NMFmultiplicative(::AbstractMatrix) (NMFkMultiplicative.jl:64-118);
+                               1 = NMFmultiplicative(::DArray) (:129-197): no tolOF/baditers/reattempts logic, no weight,
+                                   no NaN imputation; stops on objvalue < tol, inc > stopconv (default 10000) or maxiter */
+    int32_t variant;        /* nmfk_variant: 0 = KL (method=:simple), 1 = FRO (method=:nmf, algorithm=:multdiv) */
+    int32_t reserved[1];
 } nmfk_params;
+
+/* Which multiplicative update the solve runs.
+ * NMFK_VARIANT_KL  : NMFmultiplicative (NMFkMultiplicative.jl:67,70) - the reference's method=:simple, the default.
+ * NMFK_VARIANT_FRO : H <- H .* (W'X) ./ (W'W*H + d), W <- W .* (X*H') ./ (W*H*H' + d), d = sqrt(eps(T)): the update
+ *   execute_singlerun_compute reaches with method=:nmf, algorithm=:multdiv (NMFkExecute.jl:763-766:
+ *   NMF.MultUpdate(obj=:mse), third-party NMF.jl, restated in oracle/nmfk_oracle.py).  All R restarts of a batch are
+ *   STACKED: W'X is one (R*k x n)(n x m) GEMM and X*H' one (n x m)(m x R*k) GEMM on the tensor cores (tcgen05 kind::tf32
+ *   with the 3-term split for Float32, DMMA for Float64).  Stops when every column of W and row of H moved by less than
+ *   `tol` relative (NMF.jl stop_condition) or at maxiter. */
+enum nmfk_variant { NMFK_VARIANT_KL = 0, NMFK_VARIANT_FRO = 1 };
+
+/* Solution filtering of execute_run (NMFkExecute.jl:551-596): which of the R sorted restarts reach clustersolutions /
+ * finalize.  Defaults acceptratio=1, acceptfactor=Inf, nanaction=:zeroed keep all of them. */
+enum nmfk_nanaction { NMFK_NAN_ZEROED = 0, NMFK_NAN_REMOVED = 1 };
 
 /* facts about X found by the preprocessing kernel (NMFpreprocessing!, NMFkMultiplicative.jl:3-22) */
 typedef struct nmfk_xinfo {
@@ -122,6 +143,11 @@ int32_t nmfk_ctx_sync(nmfk_ctx* ctx); /* cudaStreamSynchronize on every stream o
 int32_t nmfk_set_X(nmfk_ctx* ctx, const void* X, int64_t n, int64_t m, int32_t dtype, double lambda,
                    const void* normalizevector, int32_t on_device);
 int32_t nmfk_get_xinfo(const nmfk_ctx* ctx, nmfk_xinfo* out);
+/* The `weight` keyword when it is not a scalar (execute_run's assertion NMFkExecute.jl:484; used in the objective
+ * sum((((X - W*H) .* weight)[.!inan]).^2) of NMFkMultiplicative.jl:74,125).  rows x cols must be (n,1): one weight per
+ * row (a Julia Vector of length n), (1,m): one per column, or (n,m): one per entry; column-major, dtype of X, host
+ * memory.  The effective weight is params.weight times this array.  w == NULL clears it.  Call after nmfk_set_X. */
+int32_t nmfk_set_weight(nmfk_ctx* ctx, const void* w, int64_t rows, int64_t cols);
 
 /* ---- batches of restarts: replace the restart loop of execute_run (NMFkExecute.jl:510-544) - */
 int32_t nmfk_batch_create(nmfk_ctx* ctx, int32_t k, int32_t R, nmfk_batch** out);
@@ -132,6 +158,12 @@ int32_t nmfk_batch_set_init(nmfk_batch* b, const void* Winit, const void* Hinit)
  * numpy.random.Generator(Philox(key=seed0 + r + 1)).random(), W (column-major) then H - the draw
  * order of NMFkMultiplicative.jl:38,48 and the `seed=kwseed+i` of NMFkExecute.jl:536. */
 int32_t nmfk_batch_init_random(nmfk_batch* b, uint64_t seed0);
+/* Winit and Hinit independently, as the reference treats them (NMFkMultiplicative.jl:37-55): a NULL factor is drawn on the
+ * device from restart r's Philox stream (key seed0 + r + 1) - after Random.seed!(seed) the reference draws W = rand(n,k)
+ * only if Winit is empty and then H = rand(k,m) only if Hinit is empty, so a lone missing factor takes the FIRST numbers of
+ * the stream.  This is the caller pattern of NMFkProgressive.jl:19,47,72,96 (Hinit + Hfixed) and NMFkMapping.jl:54
+ * (Winit + Wfixed).  Both NULL == nmfk_batch_init_random; both given == nmfk_batch_set_init. */
+int32_t nmfk_batch_set_init_partial(nmfk_batch* b, const void* Winit, const void* Hinit, uint64_t seed0);
 /* Run NMFmultiplicative (+ the post-run objective and normalisation of execute_singlerun_compute,
  * NMFkExecute.jl:791-804) for every restart of every batch; batches run concurrently. */
 int32_t nmfk_solve(nmfk_ctx* ctx, nmfk_batch* const* batches, int32_t nbatches, const nmfk_params* p);
@@ -143,10 +175,8 @@ int32_t nmfk_batch_get(nmfk_batch* b, void* W_out, void* H_out, double* obj_ssq,
  * lambda-substituted X, i.e. the quantity of NMFkMultiplicative.jl:74, for every restart. */
 int32_t nmfk_batch_objective(nmfk_batch* b, double weight, double* obj_ssq);
 
-/* ---- multi-GPU plumbing (restart sharding, NMFkExecute.jl:511-526 `pmap` over restarts) ------------
- * One process per GPU: every rank solves its own restarts; the H stacks and objectives are then
- * all-gathered (NCCL via torch.distributed on the device pointers below) and the rank that owns a
- * k imports them into an H-only batch to run nmfk_batch_cluster over all R_total solutions. */
+/* ---- building blocks of the restart-sharded sweep (nmfk_sweep below composes them over the library's own NCCL
+ * communicator; they stay exported for hosts that bring their own transport) ------------------------------------------- */
 int32_t nmfk_batch_create_hstack(nmfk_ctx* ctx, int32_t k, int32_t R, nmfk_batch** out); /* no W stack */
 /* device pointers of the factor stacks (W may come back NULL for an H-only batch) */
 int32_t nmfk_batch_device_ptrs(nmfk_batch* b, void** W, void** H);
@@ -182,6 +212,15 @@ int32_t nmfk_ctx_comm_destroy(nmfk_ctx* ctx);
  *                      *centroid_cols tells which)                                              */
 int32_t nmfk_batch_cluster(nmfk_batch* b, int32_t clusterWmatrix, int32_t* order, int32_t* labels, double* sil,
                            double* clustersil, double* robustness, void* centroids, int32_t* centroid_cols);
+/* Solution filtering of execute_run before clustering (NMFkExecute.jl:551-596): acceptratio < 1 keeps the first
+ * ceil(R * acceptratio) sorted solutions, acceptfactor < Inf keeps those with objvalue < acceptfactor * best, nanaction
+ * NMFK_NAN_REMOVED drops solutions that hold NaN instead of zeroing them.  Like the reference, the three masks are ANDed
+ * position by position although idxnan is indexed by restart number and the other two by sorted position (:560-596).
+ * The selection is stored in the batch: nmfk_batch_cluster / nmfk_batch_cluster_means then work on the *nkept kept
+ * solutions (their `order` / `labels` / `sil` outputs have nkept columns).  order_kept (R entries, first *nkept valid).
+ * Defaults (1, Inf, NMFK_NAN_ZEROED) select everything, which is also the state of a fresh batch. */
+int32_t nmfk_batch_select(nmfk_batch* b, double acceptratio, double acceptfactor, int32_t nanaction, int32_t* order_kept,
+                          int32_t* nkept);
 
 /* Wmean, Hmean, Wvar, Hvar of finalize(Wa, Ha, idx) (NMFkFinalize.jl:68-74): per cluster, the mean and the corrected
  * variance over the nNMF trials of the column of W / row of H that clustersolutions assigned to it - what execute_run returns
@@ -218,6 +257,22 @@ int32_t nmfk_execute(nmfk_ctx* ctx, const int32_t* ks, int32_t nks, int32_t R, c
                      const void* const* Hinit, uint64_t seed0, const nmfk_params* p, double cutoff,
                      void* const* W_out, void* const* H_out, double* fitquality, double* robustness, double* aic,
                      int32_t* kopt, int64_t* total_iters);
+
+/* ---- restart-sharded sweep over the GPUs of one box (the reference's `pmap` over restarts, NMFkExecute.jl:511-526) -----
+ * One process per GPU, each with its own ctx that holds the whole X (nmfk_set_X on every rank).
+ * nmfk_ctx_sweep_comm_init creates the library's own NCCL communicator (id128 from nmfk_comm_unique_id on one rank, sent
+ * to the others by the caller - e.g. Julia's remotecall); nranks == 1 needs no id and makes nmfk_sweep == nmfk_execute.
+ * nmfk_sweep = execute(X, ks, nNMF = nranks * R_local): rank q solves restarts q*R_local+1 .. (q+1)*R_local of every k
+ * (device Philox keys seed0 + global restart number, or this rank's slices Winit[i] / Hinit[i] of R_local matrices); there
+ * is no collective inside the iteration loop.  Per k, one all-gather of the H stacks and of the restart states and one
+ * broadcast of the best restart's W cross NVLink; the clustering + silhouettes of the nranks*R_local solutions of the i-th
+ * k run on rank i mod nranks.  EVERY rank must make the same call and EVERY rank receives all outputs (as nmfk_execute);
+ * *total_iters is the global count, *total_iters_local this rank's share.  clusterWmatrix is not available across ranks. */
+int32_t nmfk_ctx_sweep_comm_init(nmfk_ctx* ctx, int32_t nranks, int32_t rank, const void* id128);
+int32_t nmfk_sweep(nmfk_ctx* ctx, const int32_t* ks, int32_t nks, int32_t R_local, const void* const* Winit,
+                   const void* const* Hinit, uint64_t seed0, const nmfk_params* p, double cutoff, void* const* W_out,
+                   void* const* H_out, double* fitquality, double* robustness, double* aic, int32_t* kopt, int64_t* total_iters,
+                   int64_t* total_iters_local);
 
 /* getk (NMFkPostprocess.jl:7-41): returns k, 0 (all NaN) or -1 (nothing). */
 int32_t nmfk_getk(const int32_t* ks, const double* robustness, int32_t nks, double cutoff, int32_t strict);

@@ -3,9 +3,9 @@
 // execute_run / execute (/root/reference/src/NMFkExecute.jl:178-233, 483-711).
 // Host-side logic only; every numeric step runs in the CUDA kernels of this directory.
 #include <dlfcn.h>
-#include <nccl.h>  // types and prototypes only: the library is bound at run time (dlopen), see ShardNccl
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -20,6 +20,26 @@
 
 using namespace nmfk;
 
+// NCCL is bound at run time (dlopen, see ShardNccl): only the handful of types / prototypes used here are declared, with the
+// values of nccl.h (2.x ABI), so the library builds on hosts without the NCCL headers.
+extern "C" {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclUint8 = 1, ncclInt32 = 2, ncclInt64 = 4, ncclFloat = 7, ncclDouble = 8 } ncclDataType_t;
+typedef enum { ncclSum = 0 } ncclRedOp_t;
+ncclResult_t ncclGetUniqueId(ncclUniqueId* uniqueId);
+ncclResult_t ncclCommInitRank(ncclComm_t* comm, int nranks, ncclUniqueId commId, int rank);
+ncclResult_t ncclCommDestroy(ncclComm_t comm);
+const char* ncclGetErrorString(ncclResult_t result);
+ncclResult_t ncclAllReduce(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype, ncclRedOp_t op,
+                           ncclComm_t comm, cudaStream_t stream);
+ncclResult_t ncclAllGather(const void* sendbuff, void* recvbuff, size_t sendcount, ncclDataType_t datatype, ncclComm_t comm,
+                           cudaStream_t stream);
+ncclResult_t ncclBroadcast(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype, int root,
+                           ncclComm_t comm, cudaStream_t stream);
+}
+
 struct nmfk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -28,6 +48,18 @@ struct nmfk_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     void* Xp = nullptr;
     void* Xpt = nullptr;
+    // normalizevector (NMFkMultiplicative.jl:27-31): the solver streams Xn = Xp ./ nv (and its transpose); Xp stays the
+    // caller's matrix for the final objective (:119-125)
+    void* Xn = nullptr;
+    void* Xnt = nullptr;
+    void* nv = nullptr;
+    // non-scalar `weight` (nmfk_set_weight): per row, per column, or per entry; element type of X
+    void* wrow = nullptr;
+    void* wcol = nullptr;
+    void* wmat = nullptr;
+    // persistent device scratch of the clustering phase (grown on demand, never shrunk)
+    void* scratch = nullptr;
+    size_t scratch_cap = 0;
     int64_t n = 0, m = 0;
     int dtype = NMFK_F64;
     double lambda = 1e-32;
@@ -42,6 +74,9 @@ struct nmfk_ctx {
     ShardComm shard{nullptr, 1, 0, nullptr};
     bool sharded = false;
     int64_t row0 = 0, n_global = 0;
+    // restart-sharded sweep (nmfk_ctx_sweep_comm_init): the library's own communicator over the ranks that share the restarts
+    void* sweep_comm = nullptr;  // ncclComm_t
+    int sweep_nranks = 1, sweep_rank = 0;
 };
 
 struct nmfk_batch {
@@ -53,6 +88,10 @@ struct nmfk_batch {
     int32_t* canon = nullptr;
     void* ximp = nullptr;
     bool inited = false;
+    // nmfk_batch_select: sorted restart indices that reach clustersolutions / finalize (empty = all R)
+    bool has_sel = false;
+    std::vector<int32_t> sel;
+    int32_t nanaction = NMFK_NAN_ZEROED;
 };
 
 static thread_local std::string g_err;
@@ -73,6 +112,60 @@ static int32_t fail(nmfk_ctx* c, int32_t code, const std::string& msg) {
             return fail((ctx), (int32_t)e__, std::string(#call) + ": " + cudaGetErrorString(e__));      \
     } while (0)
 
+namespace {
+// device allocation freed on scope exit (error paths of the entry points below must not leak GBs)
+struct DevBuf {
+    void* p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    void* release() {
+        void* q = p;
+        p = nullptr;
+        return q;
+    }
+    template <typename T>
+    T* as() const {
+        return static_cast<T*>(p);
+    }
+};
+
+void free_X(nmfk_ctx* c) {
+    for (void** q : {&c->Xp, &c->Xpt, &c->Xn, &c->Xnt, &c->nv, &c->wrow, &c->wcol, &c->wmat}) {
+        if (*q) cudaFree(*q);
+        *q = nullptr;
+    }
+    c->has_X = false;
+}
+
+// persistent scratch of the ctx (clustering phase): at least `bytes`, contents undefined
+cudaError_t ctx_scratch(nmfk_ctx* c, size_t bytes, void** out) {
+    if (c->scratch_cap < bytes) {
+        if (c->scratch) cudaFree(c->scratch);
+        c->scratch = nullptr;
+        c->scratch_cap = 0;
+        cudaError_t e = cudaMalloc(&c->scratch, bytes);
+        if (e != cudaSuccess) return e;
+        c->scratch_cap = bytes;
+    }
+    *out = c->scratch;
+    return cudaSuccess;
+}
+}  // namespace
+
+namespace nmfk {
+cudaError_t launch_rownormalize(const void* Xp, void* Xn, void* Xnt, int64_t n, int64_t m, const void* nv, int dtype,
+                                cudaStream_t s);
+cudaError_t launch_scale_rows(void* W, int64_t n, int k, const void* nv, int dtype, cudaStream_t s);
+cudaError_t launch_renormalize(void* W, void* H, int64_t n, int64_t m, int k, int normalize, int dtype, cudaStream_t s);
+cudaError_t launch_count_nan(const void* W, const void* H, int64_t wlen, int64_t hlen, int R, int dtype, int32_t* d_flags,
+                             cudaStream_t s);
+}  // namespace nmfk
+
 // NCCL is bound with dlopen at the first nmfk_comm_* call: in a process that already loaded a
 // libnccl.so.2 (torch ships its own) that copy is reused, otherwise the system library is loaded;
 // libnmfk_b200.so itself has no link-time dependency on NCCL.
@@ -84,6 +177,8 @@ struct ShardNccl {
     decltype(&ncclAllReduce) allReduce = nullptr;
     decltype(&ncclCommDestroy) commDestroy = nullptr;
     decltype(&ncclGetErrorString) getErrorString = nullptr;
+    decltype(&ncclAllGather) allGather = nullptr;
+    decltype(&ncclBroadcast) broadcast = nullptr;
     std::string err;
     bool load() {
         if (lib) return true;
@@ -100,7 +195,9 @@ struct ShardNccl {
         allReduce = reinterpret_cast<decltype(allReduce)>(dlsym(lib, "ncclAllReduce"));
         commDestroy = reinterpret_cast<decltype(commDestroy)>(dlsym(lib, "ncclCommDestroy"));
         getErrorString = reinterpret_cast<decltype(getErrorString)>(dlsym(lib, "ncclGetErrorString"));
-        if (!getUniqueId || !commInitRank || !allReduce || !commDestroy || !getErrorString) {
+        allGather = reinterpret_cast<decltype(allGather)>(dlsym(lib, "ncclAllGather"));
+        broadcast = reinterpret_cast<decltype(broadcast)>(dlsym(lib, "ncclBroadcast"));
+        if (!getUniqueId || !commInitRank || !allReduce || !commDestroy || !getErrorString || !allGather || !broadcast) {
             err = "NCCL library lacks a required symbol";
             lib = nullptr;
             return false;
@@ -161,6 +258,29 @@ int32_t nmfk_ctx_comm_destroy(nmfk_ctx* c) {
     if (c->sharded && c->shard.comm) g_nccl.commDestroy(static_cast<ncclComm_t>(c->shard.comm));
     c->shard = ShardComm{nullptr, 1, 0, nullptr};
     c->sharded = false;
+    if (c->sweep_comm) g_nccl.commDestroy(static_cast<ncclComm_t>(c->sweep_comm));
+    c->sweep_comm = nullptr;
+    c->sweep_nranks = 1;
+    c->sweep_rank = 0;
+    return NMFK_OK;
+}
+
+int32_t nmfk_ctx_sweep_comm_init(nmfk_ctx* c, int32_t nranks, int32_t rank, const void* id128) {
+    if (!c || nranks < 1 || rank < 0 || rank >= nranks) return fail(c, NMFK_E_INVALID, "nmfk_ctx_sweep_comm_init: bad arguments");
+    if (c->sweep_comm) return fail(c, NMFK_E_INVALID, "nmfk_ctx_sweep_comm_init: ctx already has a sweep communicator");
+    CU(c, cudaSetDevice(c->device));
+    if (nranks > 1) {
+        if (!id128) return fail(c, NMFK_E_INVALID, "nmfk_ctx_sweep_comm_init: NULL unique id");
+        if (!g_nccl.load()) return fail(c, NMFK_E_UNSUPPORTED, g_nccl.err);
+        ncclUniqueId id;
+        std::memcpy(&id, id128, 128);
+        ncclComm_t comm = nullptr;
+        const ncclResult_t r = g_nccl.commInitRank(&comm, nranks, id, rank);
+        if (r != ncclSuccess) return fail(c, NMFK_E_UNSUPPORTED, std::string("ncclCommInitRank: ") + g_nccl.getErrorString(r));
+        c->sweep_comm = comm;
+    }
+    c->sweep_nranks = nranks;
+    c->sweep_rank = rank;
     return NMFK_OK;
 }
 
@@ -199,10 +319,18 @@ int32_t nmfk_ctx_create(int32_t device, nmfk_ctx** out) {
     if (device < 0 || device >= ndev) return fail(nullptr, NMFK_E_INVALID, "nmfk_ctx_create: bad device index");
     nmfk_ctx* c = new nmfk_ctx();
     c->device = device;
-    CU(c, cudaSetDevice(device));
-    CU(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(c, cudaEventCreate(&c->ev0));
-    CU(c, cudaEventCreate(&c->ev1));
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e != cudaSuccess) {
+        const std::string msg = std::string("nmfk_ctx_create: ") + cudaGetErrorString(e);
+        if (c->ev0) cudaEventDestroy(c->ev0);
+        if (c->ev1) cudaEventDestroy(c->ev1);
+        if (c->stream) cudaStreamDestroy(c->stream);
+        delete c;
+        return fail(nullptr, (int32_t)e, msg);
+    }
     *out = c;
     return NMFK_OK;
 }
@@ -212,8 +340,8 @@ int32_t nmfk_ctx_destroy(nmfk_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     nmfk_ctx_comm_destroy(c);
-    if (c->Xp) cudaFree(c->Xp);
-    if (c->Xpt) cudaFree(c->Xpt);
+    free_X(c);
+    if (c->scratch) cudaFree(c->scratch);
     if (c->d_partials) cudaFree(c->d_partials);
     for (auto s : c->pool) cudaStreamDestroy(s);
     for (auto e : c->pool_ev) cudaEventDestroy(e);
@@ -239,46 +367,43 @@ int32_t nmfk_set_X(nmfk_ctx* c, const void* X, int64_t n, int64_t m, int32_t dty
     if (dtype != NMFK_F32 && dtype != NMFK_F64) return fail(c, NMFK_E_INVALID, "nmfk_set_X: bad dtype");
     if (n <= 0 || m <= 0) return fail(c, NMFK_E_EMPTY, "Input array has a zero dimension!");
     if (n > INT32_MAX || m > INT32_MAX) return fail(c, NMFK_E_UNSUPPORTED, "nmfk_set_X: dimension exceeds int32");
-    if (normalizevector)
-        return fail(c, NMFK_E_UNSUPPORTED, "nmfk_set_X: normalizevector is not on the B200 path yet");
     CU(c, cudaSetDevice(c->device));
-    c->has_X = false;
-    if (c->Xp) cudaFree(c->Xp);
-    if (c->Xpt) cudaFree(c->Xpt);
-    c->Xp = c->Xpt = nullptr;
-    const size_t bytes = (size_t)n * m * esize(dtype);
-    CU(c, cudaMalloc(&c->Xp, bytes));
-    CU(c, cudaMalloc(&c->Xpt, bytes));
-    void* raw = nullptr;
+    free_X(c);
+    const size_t es = esize(dtype);
+    const size_t bytes = (size_t)n * m * es;
+    DevBuf Xp, Xpt, raw, stats, rf, cf, bm, Xn, Xnt, nv;
+    CU(c, Xp.alloc(bytes));
+    CU(c, Xpt.alloc(bytes));
     const void* src = X;
     if (!on_device) {
-        CU(c, cudaMalloc(&raw, bytes));
-        CU(c, cudaMemcpyAsync(raw, X, bytes, cudaMemcpyHostToDevice, c->stream));
-        src = raw;
+        CU(c, raw.alloc(bytes));
+        CU(c, cudaMemcpyAsync(raw.p, X, bytes, cudaMemcpyHostToDevice, c->stream));
+        src = raw.p;
     }
-    PreStats* d_stats = nullptr;
-    unsigned char *d_rf = nullptr, *d_cf = nullptr;
-    double* d_bm = nullptr;
     const long long nb = ((n + 31) / 32) * ((m + 31) / 32);
-    CU(c, cudaMalloc(&d_stats, sizeof(PreStats)));
-    CU(c, cudaMalloc(&d_rf, (size_t)n));
-    CU(c, cudaMalloc(&d_cf, (size_t)m));
-    CU(c, cudaMalloc(&d_bm, (size_t)nb * sizeof(double)));
-    cudaError_t e = launch_preprocess(src, c->Xp, c->Xpt, n, m, dtype, lambda, d_stats, d_rf, d_cf, d_bm, (int)nb, c->stream);
+    CU(c, stats.alloc(sizeof(PreStats)));
+    CU(c, rf.alloc((size_t)n));
+    CU(c, cf.alloc((size_t)m));
+    CU(c, bm.alloc((size_t)nb * sizeof(double)));
+    CU(c, launch_preprocess(src, Xp.p, Xpt.p, n, m, dtype, lambda, stats.as<PreStats>(), rf.as<unsigned char>(),
+                            cf.as<unsigned char>(), bm.as<double>(), (int)nb, c->stream));
     c->launches += 3;
+    if (normalizevector) {  // X ./= normalizevector after the lambda substitution (NMFkMultiplicative.jl:25-28)
+        CU(c, Xn.alloc(bytes));
+        CU(c, Xnt.alloc(bytes));
+        CU(c, nv.alloc((size_t)n * es));
+        CU(c, cudaMemcpyAsync(nv.p, normalizevector, (size_t)n * es, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                              c->stream));
+        CU(c, launch_rownormalize(Xp.p, Xn.p, Xnt.p, n, m, nv.p, dtype, c->stream));
+        c->launches += 2;
+    }
     PreStats hs{};
-    std::vector<double> bm((size_t)nb);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(bm.data(), d_bm, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(d_stats);
-    cudaFree(d_rf);
-    cudaFree(d_cf);
-    cudaFree(d_bm);
-    if (raw) cudaFree(raw);
-    CU(c, e);
+    std::vector<double> bmh((size_t)nb);
+    CU(c, cudaMemcpyAsync(&hs, stats.p, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(bmh.data(), bm.p, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
     double xmin = std::numeric_limits<double>::infinity();
-    for (double v : bm) xmin = std::min(xmin, v);
+    for (double v : bmh) xmin = std::min(xmin, v);
     c->n = n;
     c->m = m;
     c->dtype = dtype;
@@ -293,13 +418,39 @@ int32_t nmfk_set_X(nmfk_ctx* c, const void* X, int64_t n, int64_t m, int32_t dty
     c->info.xmin = xmin;
     c->info.dtype = dtype;
     // `minimum(X) < 0` is false when X holds a NaN (minimum propagates it): NMFkMultiplicative.jl:4
-    if (hs.nneg > 0 && hs.nnan == 0) {
-        cudaFree(c->Xp);
-        cudaFree(c->Xpt);
-        c->Xp = c->Xpt = nullptr;
-        return fail(c, NMFK_E_NEGATIVE, "All matrix entries must be nonnegative!");
-    }
+    if (hs.nneg > 0 && hs.nnan == 0) return fail(c, NMFK_E_NEGATIVE, "All matrix entries must be nonnegative!");
+    c->Xp = Xp.release();
+    c->Xpt = Xpt.release();
+    c->Xn = Xn.release();
+    c->Xnt = Xnt.release();
+    c->nv = nv.release();
     c->has_X = true;
+    return NMFK_OK;
+}
+
+int32_t nmfk_set_weight(nmfk_ctx* c, const void* w, int64_t rows, int64_t cols) {
+    if (!c) return fail(nullptr, NMFK_E_INVALID, "ctx is NULL");
+    if (!c->has_X) return fail(c, NMFK_E_NO_X, "nmfk_set_X has not been called");
+    CU(c, cudaSetDevice(c->device));
+    for (void** q : {&c->wrow, &c->wcol, &c->wmat}) {
+        if (*q) cudaFree(*q);
+        *q = nullptr;
+    }
+    if (!w) return NMFK_OK;
+    // @assert typeof(weight) <: Number || length(weight) == size(X, 1) || size(weight, 2) == size(X, 2) || size(weight) == size(X)
+    void** dst = nullptr;
+    if (rows == c->n && cols == c->m)
+        dst = &c->wmat;
+    else if (rows == c->n && cols == 1)
+        dst = &c->wrow;
+    else if (rows == 1 && cols == c->m)
+        dst = &c->wcol;
+    else
+        return fail(c, NMFK_E_SHAPE, "nmfk_set_weight: weight must be n x 1, 1 x m or n x m");
+    const size_t bytes = (size_t)rows * cols * esize(c->dtype);
+    CU(c, cudaMalloc(dst, bytes));
+    CU(c, cudaMemcpyAsync(*dst, w, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
     return NMFK_OK;
 }
 
@@ -424,36 +575,51 @@ static bool has_nan_host(const T* p, size_t len) {
     return false;
 }
 
-int32_t nmfk_batch_set_init(nmfk_batch* b, const void* Winit, const void* Hinit) {
-    if (!b || !Winit || !Hinit) return fail(b ? b->ctx : nullptr, NMFK_E_INVALID, "nmfk_batch_set_init: NULL argument");
+static void reset_selection(nmfk_batch* b) {
+    b->has_sel = false;
+    b->sel.clear();
+    b->nanaction = NMFK_NAN_ZEROED;
+}
+
+int32_t nmfk_batch_set_init_partial(nmfk_batch* b, const void* Winit, const void* Hinit, uint64_t seed0) {
+    if (!b) return fail(nullptr, NMFK_E_INVALID, "nmfk_batch_set_init_partial: NULL batch");
     nmfk_ctx* c = b->ctx;
     CU(c, cudaSetDevice(c->device));
+    if (!b->W) return fail(c, NMFK_E_INVALID, "nmfk_batch_set_init: H-only batch");
     const size_t wl = (size_t)c->n * b->k * b->R, hl = (size_t)b->k * c->m * b->R;
-    bool wn, hn;
+    bool wn = false, hn = false;
     if (c->dtype == NMFK_F64) {
-        wn = has_nan_host((const double*)Winit, wl);
-        hn = has_nan_host((const double*)Hinit, hl);
+        wn = Winit && has_nan_host((const double*)Winit, wl);
+        hn = Hinit && has_nan_host((const double*)Hinit, hl);
     } else {
-        wn = has_nan_host((const float*)Winit, wl);
-        hn = has_nan_host((const float*)Hinit, hl);
+        wn = Winit && has_nan_host((const float*)Winit, wl);
+        hn = Hinit && has_nan_host((const float*)Hinit, hl);
     }
     if (wn) return fail(c, NMFK_E_NAN_INIT, "Initial values for the W matrix entries include NaNs!");
     if (hn) return fail(c, NMFK_E_NAN_INIT, "Initial values for the H matrix entries include NaNs!");
-    CU(c, cudaMemcpyAsync(b->W, Winit, wl * esize(c->dtype), cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(b->H, Hinit, hl * esize(c->dtype), cudaMemcpyHostToDevice, c->stream));
+    if (c->sharded && (c->row0 + c->n > c->n_global))
+        return fail(c, NMFK_E_SHAPE, "row-sharded ctx: row0 + local rows exceeds n_global");
+    if (Winit) CU(c, cudaMemcpyAsync(b->W, Winit, wl * esize(c->dtype), cudaMemcpyHostToDevice, c->stream));
+    if (Hinit) CU(c, cudaMemcpyAsync(b->H, Hinit, hl * esize(c->dtype), cudaMemcpyHostToDevice, c->stream));
+    if (!Winit || !Hinit) {
+        // the missing factor(s) from restart r's Philox stream: W = rand(n,k) only if Winit is empty, THEN H = rand(k,m) only
+        // if Hinit is empty (NMFkMultiplicative.jl:37-55), so a lone missing factor takes the first numbers of the stream
+        CU(c, launch_philox_init(Winit ? nullptr : b->W, Hinit ? nullptr : b->H, c->sharded ? c->n_global : c->n,
+                                 c->sharded ? c->row0 : 0, c->n, b->k, c->m, b->R, seed0, c->dtype, c->stream));
+        c->launches += 1;
+    }
+    reset_selection(b);
     return reset_state(b);
+}
+
+int32_t nmfk_batch_set_init(nmfk_batch* b, const void* Winit, const void* Hinit) {
+    if (!b || !Winit || !Hinit) return fail(b ? b->ctx : nullptr, NMFK_E_INVALID, "nmfk_batch_set_init: NULL argument");
+    return nmfk_batch_set_init_partial(b, Winit, Hinit, 0);
 }
 
 int32_t nmfk_batch_init_random(nmfk_batch* b, uint64_t seed0) {
     if (!b) return fail(nullptr, NMFK_E_INVALID, "nmfk_batch_init_random: NULL batch");
-    nmfk_ctx* c = b->ctx;
-    CU(c, cudaSetDevice(c->device));
-    if (c->sharded && (c->row0 + c->n > c->n_global))
-        return fail(c, NMFK_E_SHAPE, "row-sharded ctx: row0 + local rows exceeds n_global");
-    CU(c, launch_philox_init(b->W, b->H, c->sharded ? c->n_global : c->n, c->sharded ? c->row0 : 0, c->n, b->k, c->m, b->R,
-                             seed0, c->dtype, c->stream));
-    c->launches += 1;
-    return reset_state(b);
+    return nmfk_batch_set_init_partial(b, nullptr, nullptr, seed0);
 }
 
 static int32_t check_params(nmfk_ctx* c, const nmfk_params* p) {
@@ -461,13 +627,18 @@ static int32_t check_params(nmfk_ctx* c, const nmfk_params* p) {
     if (p->check_every < 1 || p->maxiter < 0 || p->maxbaditers < 1 || p->maxreattempts < 1)
         return fail(c, NMFK_E_INVALID, "params: check_every, maxbaditers, maxreattempts must be >= 1, maxiter >= 0");
     if (p->normalize < 0 || p->normalize > 2) return fail(c, NMFK_E_INVALID, "params: normalize must be 0, 1 or 2");
+    if (p->stop_rule < 0 || p->stop_rule > 1) return fail(c, NMFK_E_INVALID, "params: stop_rule must be 0 or 1");
+    if (p->variant != NMFK_VARIANT_KL && p->variant != NMFK_VARIANT_FRO) return fail(c, NMFK_E_INVALID, "params: unknown variant");
+    if (p->stop_rule == 1 && c && c->info.nnan > 0)
+        return fail(c, NMFK_E_UNSUPPORTED, "stop_rule 1 (the DArray method) with NaN entries in X is not supported: the reference "
+                                           "itself returns objvalue = NaN there (NMFkMultiplicative.jl:193-195)");
     return NMFK_OK;
 }
 
 static void fill_args(const nmfk_batch* b, const nmfk_params* p, SolveArgs& a) {
     const nmfk_ctx* c = b->ctx;
-    a.X = c->Xp;
-    a.Xt = c->Xpt;
+    a.X = c->Xn ? c->Xn : c->Xp;  // normalizevector: the solver works on X ./ normalizevector
+    a.Xt = c->Xn ? c->Xnt : c->Xpt;
     a.W = b->W;
     a.H = b->H;
     a.st = b->st;
@@ -493,6 +664,16 @@ static void fill_args(const nmfk_batch* b, const nmfk_params* p, SolveArgs& a) {
     a.tolOF = p->tolOF;
     a.eps_clamp = p->eps_clamp;
     a.weight = p->weight;
+    a.wref = WeightRef{c->wrow, c->wcol, c->wmat};
+    if (p->stop_rule == 1) {
+        // NMFmultiplicative(::DArray) (NMFkMultiplicative.jl:129-197): no tolOF / baditers / reattempts logic and no weight;
+        // the loop ends on objvalue < tol, inc > stopconv or maxiter
+        a.maxbad = INT32_MAX;
+        a.maxre = INT32_MAX;
+        a.weight = 1.0;
+        a.wref = WeightRef{nullptr, nullptr, nullptr};
+    }
+    if (c->Xn) a.normalize = 0;  // the normalizevector epilogue (finish_normalizevector) rescales W first, then normalises
     a.tiled_tc = p->engine != NMFK_ENGINE_TILED_SCALAR;
     a.shard = c->sharded ? &c->shard : nullptr;
 }
@@ -502,6 +683,37 @@ namespace nmfk {
 cudaError_t solve_tiled(const SolveArgs& a, int dtype, cudaStream_t s, int64_t* launches);
 bool tiled_supported(int k);
 }  // namespace nmfk
+
+// Epilogue of NMFmultiplicative with a normalizevector (NMFkMultiplicative.jl:119-125) followed by the objective / normalisation
+// of execute_singlerun_compute (NMFkExecute.jl:791-804), for the restarts an engine has just finished (done == 1) on the
+// normalised matrix: W .*= normalizevector; objvalue against the caller's X; then the H-row (or W-column) normalisation.
+static int32_t finish_normalizevector(nmfk_batch* b, const nmfk_params* p) {
+    nmfk_ctx* c = b->ctx;
+    std::vector<UnitState> st((size_t)b->R);
+    CU(c, cudaMemcpy(st.data(), b->st, st.size() * sizeof(UnitState), cudaMemcpyDeviceToHost));
+    const size_t es = esize(c->dtype);
+    bool touched = false;
+    for (int r = 0; r < b->R; ++r) {
+        if (st[r].stop == 0 || st[r].done != 1) continue;
+        char* W = (char*)b->W + (size_t)r * c->n * b->k * es;
+        char* H = (char*)b->H + (size_t)r * b->k * c->m * es;
+        CU(c, launch_scale_rows(W, c->n, b->k, c->nv, c->dtype, c->stream));
+        double o[2];
+        int32_t rc = residual(c, b->k, W, H, 1, p->weight, o);  // against the caller's X (c->Xp), zeros restored
+        if (rc) return rc;
+        st[r].obj_ssq = o[0];
+        st[r].obj_norm = std::sqrt(o[1]);
+        CU(c, launch_renormalize(W, H, c->n, c->m, b->k, p->normalize, c->dtype, c->stream));
+        c->launches += 1 + (p->normalize != 0);
+        st[r].done = 2;
+        touched = true;
+    }
+    if (touched) {
+        CU(c, cudaMemcpyAsync(b->st, st.data(), st.size() * sizeof(UnitState), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    return NMFK_OK;
+}
 
 int32_t nmfk_solve(nmfk_ctx* c, nmfk_batch* const* batches, int32_t nb, const nmfk_params* p) {
     if (!c || !batches || nb < 1) return fail(c, NMFK_E_INVALID, "nmfk_solve: bad arguments");
@@ -546,10 +758,17 @@ int32_t nmfk_solve(nmfk_ctx* c, nmfk_batch* const* batches, int32_t nb, const nm
         const bool fits_scalar = resident_fits(a.n, a.m, a.k, es);
         bool resident = fits_dmma || fits_scalar;
         if (p->engine == NMFK_ENGINE_TILED || p->engine == NMFK_ENGINE_TILED_SCALAR) resident = false;
+        if (a.wref.any()) {  // per-row / per-column / per-entry weights live in the tiled engine's scalar objective kernel
+            if (p->engine == NMFK_ENGINE_RESIDENT || p->engine == NMFK_ENGINE_RESIDENT_SCALAR)
+                return fail(c, NMFK_E_UNSUPPORTED, "vector / matrix weights: only the tiled engine is available");
+            resident = false;
+        }
         if (c->sharded) {  // rows of X / W live on several GPUs: only the tiled engine exchanges partials
             if (p->engine == NMFK_ENGINE_RESIDENT || p->engine == NMFK_ENGINE_RESIDENT_SCALAR)
                 return fail(c, NMFK_E_UNSUPPORTED, "row-sharded ctx: only the tiled engine is available");
             if (p->normalize == 2) return fail(c, NMFK_E_UNSUPPORTED, "row-sharded ctx: clusterWmatrix normalisation is not available");
+            if (c->Xn || a.wref.any())
+                return fail(c, NMFK_E_UNSUPPORTED, "row-sharded ctx: normalizevector / non-scalar weights are not available");
             resident = false;
         }
         if ((p->engine == NMFK_ENGINE_RESIDENT || p->engine == NMFK_ENGINE_RESIDENT_SCALAR) && !resident)
@@ -580,6 +799,11 @@ int32_t nmfk_solve(nmfk_ctx* c, nmfk_batch* const* batches, int32_t nb, const nm
     float ms = 0.f;
     CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->last_solve_ms = ms;
+    if (c->Xn)
+        for (int i = 0; i < nb; ++i) {
+            rc = finish_normalizevector(batches[i], p);
+            if (rc) return rc;
+        }
     return NMFK_OK;
 }
 
@@ -621,8 +845,8 @@ static int32_t residual(nmfk_ctx* c, int k, const void* W, const void* H, int re
         CU(c, cudaMalloc(&c->d_partials, (size_t)nb * 2 * sizeof(double)));
         c->partials_cap = (size_t)nb * 2;
     }
-    CU(c, launch_residual(c->Xp, c->dtype, (int)c->n, (int)c->m, k, W, H, c->lambda, restore, weight, c->d_partials,
-                          c->stream));
+    CU(c, launch_residual(c->Xp, c->dtype, (int)c->n, (int)c->m, k, W, H, c->lambda, restore, weight,
+                          WeightRef{c->wrow, c->wcol, c->wmat}, c->d_partials, c->stream));
     c->launches += 1;
     std::vector<double> h((size_t)nb * 2);
     CU(c, cudaMemcpyAsync(h.data(), c->d_partials, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -650,20 +874,12 @@ int32_t nmfk_batch_objective(nmfk_batch* b, double weight, double* obj_ssq) {
     return NMFK_OK;
 }
 
-int32_t nmfk_batch_cluster(nmfk_batch* b, int32_t clusterWmatrix, int32_t* order_out, int32_t* labels_out,
-                           double* sil_out, double* clustersil_out, double* robustness_out, void* centroids_out,
-                           int32_t* centroid_cols) {
-    if (!b) return fail(nullptr, NMFK_E_INVALID, "nmfk_batch_cluster: NULL batch");
-    nmfk_ctx* c = b->ctx;
-    CU(c, cudaSetDevice(c->device));
-    const int k = b->k, R = b->R;
-    std::vector<UnitState> st;
-    int32_t rc = fetch_state(b, st);
-    if (rc) return rc;
-    // idxsort = sortperm(objvalue) (NMFkExecute.jl:545): stable, ascending, NaN last; objvalue is a Vector{T}
-    std::vector<double> obj((size_t)R);
+// idxsort = sortperm(objvalue) (NMFkExecute.jl:545): stable, ascending, NaN last; objvalue is a Vector{T}
+static void sorted_order(const nmfk_ctx* c, const std::vector<UnitState>& st, std::vector<double>& obj, std::vector<int32_t>& order) {
+    const int R = (int)st.size();
+    obj.resize((size_t)R);
     for (int r = 0; r < R; ++r) obj[r] = c->dtype == NMFK_F32 ? (double)(float)st[r].obj_norm : st[r].obj_norm;
-    std::vector<int32_t> order((size_t)R);
+    order.resize((size_t)R);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
         const double a = obj[x], d = obj[y];
@@ -671,8 +887,72 @@ int32_t nmfk_batch_cluster(nmfk_batch* b, int32_t clusterWmatrix, int32_t* order
         if (d != d) return true;
         return a < d;
     });
+}
+
+int32_t nmfk_batch_select(nmfk_batch* b, double acceptratio, double acceptfactor, int32_t nanaction, int32_t* order_kept,
+                          int32_t* nkept) {
+    if (!b) return fail(nullptr, NMFK_E_INVALID, "nmfk_batch_select: NULL batch");
+    nmfk_ctx* c = b->ctx;
+    if (nanaction != NMFK_NAN_ZEROED && nanaction != NMFK_NAN_REMOVED)
+        return fail(c, NMFK_E_INVALID, "nmfk_batch_select: nanaction must be :zeroed or :removed");
+    CU(c, cudaSetDevice(c->device));
+    const int R = b->R;
+    std::vector<UnitState> st;
+    int32_t rc = fetch_state(b, st);
+    if (rc) return rc;
+    std::vector<double> obj;
+    std::vector<int32_t> order;
+    sorted_order(c, st, obj, order);
+    std::vector<char> keep((size_t)R, 1);
+    if (acceptratio < 1) {  // idxrat = [trues(ccc); falses(nNMF - ccc)] (:552-555)
+        const int ccc = (int)std::ceil((double)R * acceptratio);
+        for (int t = 0; t < R; ++t) keep[t] = keep[t] && (t < ccc);
+    }
+    if (acceptfactor < std::numeric_limits<double>::infinity()) {  // idxcut = objvalue[idxsort] .< cutoff (:559-562)
+        const double cutoff = obj[order[0]] * acceptfactor;
+        for (int t = 0; t < R; ++t) keep[t] = keep[t] && (obj[order[t]] < cutoff);
+    }
+    if (nanaction == NMFK_NAN_REMOVED) {  // idxnan[i] = false for restart NUMBER i (:581-596), ANDed by position like the reference
+        DevBuf flags;
+        CU(c, flags.alloc((size_t)R * sizeof(int32_t)));
+        CU(c, launch_count_nan(b->W, b->H, (int64_t)c->n * b->k, (int64_t)b->k * c->m, R, c->dtype, flags.as<int32_t>(), c->stream));
+        c->launches += 1;
+        std::vector<int32_t> hf((size_t)R);
+        CU(c, cudaMemcpyAsync(hf.data(), flags.p, (size_t)R * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        for (int t = 0; t < R; ++t) keep[t] = keep[t] && !hf[t];
+    }
+    b->sel.clear();
+    for (int t = 0; t < R; ++t)
+        if (keep[t]) b->sel.push_back(order[t]);
+    b->has_sel = true;
+    b->nanaction = nanaction;
+    if (order_kept) std::copy(b->sel.begin(), b->sel.end(), order_kept);
+    if (nkept) *nkept = (int32_t)b->sel.size();
+    return NMFK_OK;
+}
+
+int32_t nmfk_batch_cluster(nmfk_batch* b, int32_t clusterWmatrix, int32_t* order_out, int32_t* labels_out,
+                           double* sil_out, double* clustersil_out, double* robustness_out, void* centroids_out,
+                           int32_t* centroid_cols) {
+    if (!b) return fail(nullptr, NMFK_E_INVALID, "nmfk_batch_cluster: NULL batch");
+    nmfk_ctx* c = b->ctx;
+    CU(c, cudaSetDevice(c->device));
+    const int k = b->k;
+    std::vector<int32_t> order;
+    if (b->has_sel) {
+        order = b->sel;
+    } else {
+        std::vector<UnitState> st;
+        int32_t rc = fetch_state(b, st);
+        if (rc) return rc;
+        std::vector<double> obj;
+        sorted_order(c, st, obj, order);
+    }
+    const int R = (int)order.size();  // solutions that reach clustersolutions / finalize
+    if (R < 1) return fail(c, NMFK_E_INVALID, "nmfk_batch_cluster: no solutions remain after the acceptance filters");
     if (order_out) std::copy(order.begin(), order.end(), order_out);
-    if (k == 1) {  // minsilhouette = 1 when nk == 1 (NMFkExecute.jl:618)
+    if (k == 1) {  // minsilhouette = 1 when nk == 1 (NMFkExecute.jl:618); Wbest / Hbest were copied before the NaN pass (:549-550)
         if (labels_out) std::fill(labels_out, labels_out + R, 1);
         if (sil_out) std::fill(sil_out, sil_out + R, 1.0);
         if (clustersil_out) clustersil_out[0] = 1.0;
@@ -680,56 +960,57 @@ int32_t nmfk_batch_cluster(nmfk_batch* b, int32_t clusterWmatrix, int32_t* order
         if (centroid_cols) *centroid_cols = 0;
         return NMFK_OK;
     }
-    const size_t es = esize(c->dtype);
+    // nanaction = :zeroed (:566-580) touches every stored solution, kept or not
+    if (b->nanaction == NMFK_NAN_ZEROED) {
+        if (b->W) CU(c, launch_zero_nan(b->W, (long long)c->n * k * b->R, c->dtype, c->stream));
+        CU(c, launch_zero_nan(b->H, (long long)k * c->m * b->R, c->dtype, c->stream));
+        c->launches += 2;
+    }
     const int len = clusterWmatrix ? (int)c->n : (int)c->m;
     const int N = R * k, ld = len + 1;
     if (clusterWmatrix && !b->W) return fail(c, NMFK_E_INVALID, "nmfk_batch_cluster: clusterWmatrix on an H-only batch");
-    // nanaction = :zeroed (:566-580)
-    if (b->W) CU(c, launch_zero_nan(b->W, (long long)c->n * k * R, c->dtype, c->stream));
-    CU(c, launch_zero_nan(b->H, (long long)k * c->m * R, c->dtype, c->stream));
-    c->launches += 2;
+    // one persistent scratch arena instead of nine cudaMalloc / cudaFree per call (the N x N distance matrix is 537 MB at
+    // BASELINE C4 k = 32)
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t o_order = 0, o_labels = o_order + up((size_t)R * 4), o_cent = o_labels + up((size_t)N * 4),
+                 o_sil = o_cent + up((size_t)k * ld * 8), o_csil = o_sil + up((size_t)N * 8), o_bias = o_csil + up((size_t)k * 8),
+                 o_vnorm = o_bias + 256, o_V = o_vnorm + up((size_t)N * 8), o_D = o_V + up((size_t)N * ld * 8),
+                 total = o_D + up((size_t)N * N * 8);
+    char* base = nullptr;
+    CU(c, ctx_scratch(c, total, reinterpret_cast<void**>(&base)));
     ClusterArgs a{};
-    int32_t* d_order = nullptr;
-    cudaError_t e = cudaMalloc(&d_order, (size_t)R * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&a.labels, (size_t)N * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&a.cent, (size_t)k * ld * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&a.sil, (size_t)N * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&a.clustersil, (size_t)k * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&a.bias, sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&a.V, (size_t)N * ld * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&a.vnorm, (size_t)N * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&a.Dm, (size_t)N * N * sizeof(double));
+    int32_t* d_order = reinterpret_cast<int32_t*>(base + o_order);
+    a.labels = reinterpret_cast<int32_t*>(base + o_labels);
+    a.cent = reinterpret_cast<double*>(base + o_cent);
+    a.sil = reinterpret_cast<double*>(base + o_sil);
+    a.clustersil = reinterpret_cast<double*>(base + o_csil);
+    a.bias = reinterpret_cast<int32_t*>(base + o_bias);
+    a.vnorm = reinterpret_cast<double*>(base + o_vnorm);
+    a.V = reinterpret_cast<double*>(base + o_V);
+    a.Dm = reinterpret_cast<double*>(base + o_D);
     std::vector<int32_t> labels((size_t)N);
     std::vector<double> sil((size_t)N), csil((size_t)k), cent((size_t)k * ld);
     int32_t bias = 0;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_order, order.data(), (size_t)R * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) {
-        a.F = clusterWmatrix ? b->W : b->H;
-        a.len = len;
-        a.k = k;
-        a.R = R;
-        a.use_W = clusterWmatrix;
-        a.order = d_order;
-        e = launch_cluster(a, c->dtype, c->stream);
-        c->launches += 6;
-    }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(labels.data(), a.labels, labels.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(sil.data(), a.sil, sil.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(csil.data(), a.clustersil, csil.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(cent.data(), a.cent, cent.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&bias, a.bias, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(d_order);
-    cudaFree(a.labels);
-    cudaFree(a.cent);
-    cudaFree(a.sil);
-    cudaFree(a.clustersil);
-    cudaFree(a.bias);
-    cudaFree(a.V);
-    cudaFree(a.vnorm);
-    cudaFree(a.Dm);
-    CU(c, e);
-    (void)es;
+    CU(c, cudaMemcpyAsync(d_order, order.data(), (size_t)R * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    a.F = clusterWmatrix ? b->W : b->H;
+    a.len = len;
+    a.k = k;
+    a.R = R;
+    a.use_W = clusterWmatrix;
+    a.order = d_order;
+    // clusterWmatrix = true: the reference's `newClusterCenters = factors[1]` IS WBig[bestIdx] (no copy is made on this
+    // branch, NMFkCluster.jl:426-428, 453-455), so clustersolutions leaves the centroids (running sums ./ numTrials, :484,
+    // :512) in the best solution's W before finalize / Wbest read it (NMFkExecute.jl:631-637).  Not when the zero-column fix
+    // fired: vcat (:449) made fresh matrices.
+    a.alias_best = clusterWmatrix ? ((char*)b->W + (size_t)order[0] * c->n * k * esize(c->dtype)) : nullptr;
+    CU(c, launch_cluster(a, c->dtype, c->stream));
+    c->launches += 6 + (clusterWmatrix ? 1 : 0);
+    CU(c, cudaMemcpyAsync(labels.data(), a.labels, labels.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(sil.data(), a.sil, sil.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(csil.data(), a.clustersil, csil.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(cent.data(), a.cent, cent.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(&bias, a.bias, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
     if (labels_out) std::copy(labels.begin(), labels.end(), labels_out);
     if (sil_out) std::copy(sil.begin(), sil.end(), sil_out);
     if (clustersil_out) std::copy(csil.begin(), csil.end(), clustersil_out);
@@ -764,17 +1045,13 @@ int32_t nmfk_fit(nmfk_ctx* c, int32_t k, const void* W, const void* H, double* p
     CU(c, cudaSetDevice(c->device));
     const size_t es = esize(c->dtype);
     const size_t wb = (size_t)c->n * k * es, hb = (size_t)k * c->m * es;
-    void *dW = nullptr, *dH = nullptr;
-    CU(c, cudaMalloc(&dW, wb));
-    cudaError_t e = cudaMalloc(&dH, hb);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dW, W, wb, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dH, H, hb, cudaMemcpyHostToDevice, c->stream);
+    DevBuf dW, dH;
+    CU(c, dW.alloc(wb));
+    CU(c, dH.alloc(hb));
+    CU(c, cudaMemcpyAsync(dW.p, W, wb, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(dH.p, H, hb, cudaMemcpyHostToDevice, c->stream));
     double o[2] = {0, 0};
-    int32_t rc = NMFK_OK;
-    if (e == cudaSuccess) rc = residual(c, k, dW, dH, 1, 1.0, o);
-    cudaFree(dW);
-    if (dH) cudaFree(dH);
-    CU(c, e);
+    int32_t rc = residual(c, k, dW.p, dH.p, 1, 1.0, o);
     if (rc) return rc;
     *phi = std::sqrt(o[1]);
     if (c->dtype == NMFK_F32) *phi = (double)(float)*phi;
@@ -789,24 +1066,27 @@ int32_t nmfk_batch_cluster_means(nmfk_batch* b, const int32_t* order, const int3
     if (!b || !order || !labels) return fail(b ? b->ctx : nullptr, NMFK_E_INVALID, "nmfk_batch_cluster_means: NULL argument");
     nmfk_ctx* c = b->ctx;
     CU(c, cudaSetDevice(c->device));
-    const int k = b->k, R = b->R;
+    const int k = b->k, R = b->has_sel ? (int)b->sel.size() : b->R;  // the solutions that reached finalize
     const long long n = c->n, m = c->m;
+    if (R < 1) return fail(c, NMFK_E_INVALID, "nmfk_batch_cluster_means: no solutions selected");
     if ((Wmean || Wvar) && !b->W) return fail(c, NMFK_E_INVALID, "nmfk_batch_cluster_means: W statistics on an H-only batch");
     std::vector<int32_t> amap((size_t)k * R, -1);
     for (int t = 0; t < R; ++t) {
-        if (order[t] < 0 || order[t] >= R) return fail(c, NMFK_E_INVALID, "nmfk_batch_cluster_means: order out of range");
+        if (order[t] < 0 || order[t] >= b->R) return fail(c, NMFK_E_INVALID, "nmfk_batch_cluster_means: order out of range");
         for (int a = 0; a < k; ++a) {
             const int lab = labels[(size_t)t * k + a];
             if (lab >= 1 && lab <= k && amap[(size_t)(lab - 1) * R + t] < 0) amap[(size_t)(lab - 1) * R + t] = a;
         }
     }
     const size_t es = esize(c->dtype);
-    int32_t *d_order = nullptr, *d_amap = nullptr;
-    unsigned char* d_out = nullptr;
+    DevBuf b_order, b_amap, b_out;
     const size_t wbytes = (size_t)n * k * es, hbytes = (size_t)k * m * es;
-    cudaError_t e = cudaMalloc(&d_order, (size_t)R * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&d_amap, amap.size() * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&d_out, 2 * (wbytes + hbytes));
+    cudaError_t e = b_order.alloc((size_t)R * sizeof(int32_t));
+    if (e == cudaSuccess) e = b_amap.alloc(amap.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = b_out.alloc(2 * (wbytes + hbytes));
+    CU(c, e);
+    int32_t *d_order = b_order.as<int32_t>(), *d_amap = b_amap.as<int32_t>();
+    unsigned char* d_out = b_out.as<unsigned char>();
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_order, order, (size_t)R * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_amap, amap.data(), amap.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
     unsigned char *dWm = d_out, *dWv = d_out + wbytes, *dHm = d_out + 2 * wbytes, *dHv = dHm + hbytes;
@@ -823,9 +1103,6 @@ int32_t nmfk_batch_cluster_means(nmfk_batch* b, const int32_t* order, const int3
     if (e == cudaSuccess && Hmean) e = cudaMemcpyAsync(Hmean, dHm, hbytes, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess && Hvar) e = cudaMemcpyAsync(Hvar, dHv, hbytes, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(d_order);
-    cudaFree(d_amap);
-    cudaFree(d_out);
     CU(c, e);
     return NMFK_OK;
 }
@@ -935,6 +1212,25 @@ int32_t nmfk_getk(const int32_t* ks, const double* rob, int32_t nks, double cuto
     return ks[best];
 }
 
+// phi_final = normnan(X - Wa*Ha) with NaN residuals zeroed (NMFkExecute.jl:664-668) and aic (:697-708) of host factors
+static int32_t phi_aic(nmfk_ctx* c, int k, const std::vector<char>& Wb, const std::vector<char>& Hb, double* phi, double* aic) {
+    DevBuf dW, dH;
+    CU(c, dW.alloc(Wb.size()));
+    CU(c, dH.alloc(Hb.size()));
+    CU(c, cudaMemcpyAsync(dW.p, Wb.data(), Wb.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(dH.p, Hb.data(), Hb.size(), cudaMemcpyHostToDevice, c->stream));
+    double o[2] = {0, 0};
+    int32_t rc = residual(c, k, dW.p, dH.p, 1, 1.0, o);
+    if (rc) return rc;
+    double ph = std::sqrt(o[1]);
+    if (c->dtype == NMFK_F32) ph = (double)(float)ph;
+    const double nobs = (double)(c->n * c->m - c->info.nnan);     // sum(.!isnan.(X)) (:697)
+    const double nparam = (double)(c->n * k) + (double)(k * c->m);  // (:698)
+    if (phi) *phi = ph;
+    if (aic) *aic = 2.0 * nparam + nobs * std::log(ph / nobs);  // (:708)
+    return NMFK_OK;
+}
+
 // post-solve part of execute_run for one batch (NMFkExecute.jl:545-711 with the default keywords)
 static int32_t finish_run(nmfk_batch* b, int32_t clusterW, std::vector<char>& Wb, std::vector<char>& Hb, double* phi,
                           double* robustness, double* aic, int64_t* total_iters) {
@@ -959,25 +1255,9 @@ static int32_t finish_run(nmfk_batch* b, int32_t clusterW, std::vector<char>& Wb
                 std::memcpy(Hb.data() + ((size_t)i + (size_t)j * k) * es, H0.data() + ((size_t)ci + (size_t)j * k) * es, es);
         }
     }
-    // phi_final = normnan(X - Wa*Ha) with NaN residuals zeroed (:664-668): computed on the device
-    void *dW = nullptr, *dH = nullptr;
-    CU(c, cudaMalloc(&dW, Wb.size()));
-    cudaError_t e = cudaMalloc(&dH, Hb.size());
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dW, Wb.data(), Wb.size(), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dH, Hb.data(), Hb.size(), cudaMemcpyHostToDevice, c->stream);
-    double o[2] = {0, 0};
-    if (e == cudaSuccess) rc = residual(c, k, dW, dH, 1, 1.0, o);
-    cudaFree(dW);
-    if (dH) cudaFree(dH);
-    CU(c, e);
+    rc = phi_aic(c, k, Wb, Hb, phi, aic);
     if (rc) return rc;
-    double ph = std::sqrt(o[1]);
-    if (c->dtype == NMFK_F32) ph = (double)(float)ph;
-    const double nobs = (double)(c->n * c->m - c->info.nnan);     // sum(.!isnan.(X)) (:697)
-    const double nparam = (double)(c->n * k) + (double)(k * c->m);  // (:698)
-    if (phi) *phi = ph;
     if (robustness) *robustness = rob;
-    if (aic) *aic = 2.0 * nparam + nobs * std::log(ph / nobs);  // (:708)
     if (total_iters) {
         std::vector<UnitState> st;
         rc = fetch_state(b, st);
@@ -992,16 +1272,14 @@ static int32_t finish_run(nmfk_batch* b, int32_t clusterW, std::vector<char>& Wb
 int32_t nmfk_execute_run(nmfk_ctx* c, int32_t k, int32_t R, const void* Winit, const void* Hinit, uint64_t seed0,
                          const nmfk_params* p, void* W_best, void* H_best, double* phi, double* robustness, double* aic,
                          int64_t* total_iters) {
+    if (!c || !p) return fail(c, NMFK_E_INVALID, "nmfk_execute_run: NULL argument");
     nmfk_batch* b = nullptr;
     int32_t rc = nmfk_batch_create(c, k, R, &b);
     if (rc) return rc;
-    if (Winit && Hinit)
-        rc = nmfk_batch_set_init(b, Winit, Hinit);
-    else
-        rc = nmfk_batch_init_random(b, seed0);
+    rc = nmfk_batch_set_init_partial(b, Winit, Hinit, seed0);  // either may be NULL (NMFkMultiplicative.jl:37-55)
     if (!rc) rc = nmfk_solve(c, &b, 1, p);
     std::vector<char> Wb, Hb;
-    if (!rc) rc = finish_run(b, p->normalize == 2, Wb, Hb, phi, robustness, aic, total_iters);
+    if (!rc) rc = finish_run(b, p->clusterWmatrix != 0, Wb, Hb, phi, robustness, aic, total_iters);
     if (!rc) {
         if (W_best) std::memcpy(W_best, Wb.data(), Wb.size());
         if (H_best) std::memcpy(H_best, Hb.data(), Hb.size());
@@ -1010,60 +1288,230 @@ int32_t nmfk_execute_run(nmfk_ctx* c, int32_t k, int32_t R, const void* Winit, c
     return rc;
 }
 
+// signal ordering of execute(X, nk) (NMFkExecute.jl:311-318; skipped with Wfixed / Hfixed, :305-307) + copy to the caller
+static void order_and_store(nmfk_ctx* c, int k, const nmfk_params* p, const std::vector<char>& Wb, const std::vector<char>& Hb,
+                            void* W_out, void* H_out) {
+    const size_t es = esize(c->dtype);
+    std::vector<int32_t> so((size_t)k);
+    std::iota(so.begin(), so.end(), 0);
+    if (!p->Wfixed && !p->Hfixed) nmfk_signalorder(Wb.data(), Hb.data(), c->n, k, c->m, c->dtype, so.data());
+    if (W_out)
+        for (int a = 0; a < k; ++a)
+            std::memcpy((char*)W_out + (size_t)a * c->n * es, Wb.data() + (size_t)so[a] * c->n * es, (size_t)c->n * es);
+    if (H_out)
+        for (int a = 0; a < k; ++a)
+            for (int64_t j = 0; j < c->m; ++j)
+                std::memcpy((char*)H_out + ((size_t)a + (size_t)j * k) * es, Hb.data() + ((size_t)so[a] + (size_t)j * k) * es, es);
+}
+
+// consecutive groups of the sweep's k values whose factor stacks stay within a fixed budget (a constant, so that every
+// rank of a sharded sweep forms the same groups): BASELINE C4 on one GPU would otherwise hold 108 GB of W stacks at once
+static std::vector<std::pair<int, int>> k_groups(const nmfk_ctx* c, const int32_t* ks, int nks, int R) {
+    const double budget = 48.0 * 1073741824.0;
+    const double es = (double)esize(c->dtype);
+    std::vector<std::pair<int, int>> groups;
+    int begin = 0;
+    double used = 0.0;
+    for (int i = 0; i < nks; ++i) {
+        const double bytes = ((double)c->n * ks[i] + (double)ks[i] * c->m) * R * es +
+                             (c->info.nnan > 0 ? (double)R * c->n * c->m * es : 0.0);
+        if (i > begin && used + bytes > budget) {
+            groups.emplace_back(begin, i);
+            begin = i;
+            used = 0.0;
+        }
+        used += bytes;
+    }
+    groups.emplace_back(begin, nks);
+    return groups;
+}
+
+static int32_t kopt_of(const int32_t* ks, int nks, const std::vector<double>& fit, const std::vector<double>& rob, double cutoff) {
+    bool allinf = true;
+    for (double f : fit)
+        if (!std::isinf(f)) allinf = false;
+    return allinf ? 0 : nmfk_getk(ks, rob.data(), nks, cutoff, 1);  // (:206-208, :225)
+}
+
 int32_t nmfk_execute(nmfk_ctx* c, const int32_t* ks, int32_t nks, int32_t R, const void* const* Winit,
                      const void* const* Hinit, uint64_t seed0, const nmfk_params* p, double cutoff, void* const* W_out,
                      void* const* H_out, double* fitquality, double* robustness, double* aic, int32_t* kopt,
                      int64_t* total_iters) {
-    if (!c || !ks || nks < 1 || R < 1) return fail(c, NMFK_E_INVALID, "nmfk_execute: bad arguments");
-    std::vector<nmfk_batch*> bs((size_t)nks, nullptr);
+    if (!c || !ks || !p || nks < 1 || R < 1) return fail(c, NMFK_E_INVALID, "nmfk_execute: bad arguments");
+    if (!c->has_X) return fail(c, NMFK_E_NO_X, "nmfk_set_X has not been called");
     int32_t rc = NMFK_OK;
-    for (int i = 0; i < nks && !rc; ++i) {
-        rc = nmfk_batch_create(c, ks[i], R, &bs[i]);
-        if (rc) break;
-        if (Winit && Hinit && Winit[i] && Hinit[i])
-            rc = nmfk_batch_set_init(bs[i], Winit[i], Hinit[i]);
-        else
-            rc = nmfk_batch_init_random(bs[i], seed0);
-    }
-    if (!rc) rc = nmfk_solve(c, bs.data(), nks, p);
     int64_t tot = 0;
+    double solve_ms = 0.0;
     std::vector<double> rob((size_t)nks, 0.0), fit((size_t)nks, 0.0);
-    const size_t es = esize(c ? c->dtype : NMFK_F64);
-    for (int i = 0; i < nks && !rc; ++i) {
-        std::vector<char> Wb, Hb;
-        double ph = 0, rb = 0, ai = 0;
-        int64_t it = 0;
-        rc = finish_run(bs[i], p->normalize == 2, Wb, Hb, &ph, &rb, &ai, &it);
-        if (rc) break;
-        tot += it;
-        const int k = ks[i];
-        // signal ordering of execute(X, nk) (:311-318) unless Wfixed/Hfixed (:305-307)
-        std::vector<int32_t> so((size_t)k);
-        std::iota(so.begin(), so.end(), 0);
-        if (!p->Wfixed && !p->Hfixed) nmfk_signalorder(Wb.data(), Hb.data(), c->n, k, c->m, c->dtype, so.data());
-        std::vector<char> Wo(Wb.size()), Ho(Hb.size());
-        for (int a = 0; a < k; ++a) {
-            std::memcpy(Wo.data() + (size_t)a * c->n * es, Wb.data() + (size_t)so[a] * c->n * es, (size_t)c->n * es);
-            for (int64_t j = 0; j < c->m; ++j)
-                std::memcpy(Ho.data() + ((size_t)a + (size_t)j * k) * es, Hb.data() + ((size_t)so[a] + (size_t)j * k) * es, es);
+    for (const auto& g : k_groups(c, ks, nks, R)) {
+        const int gn = g.second - g.first;
+        std::vector<nmfk_batch*> bs((size_t)gn, nullptr);
+        for (int q = 0; q < gn && !rc; ++q) {
+            const int i = g.first + q;
+            rc = nmfk_batch_create(c, ks[i], R, &bs[q]);
+            if (!rc) rc = nmfk_batch_set_init_partial(bs[q], Winit ? Winit[i] : nullptr, Hinit ? Hinit[i] : nullptr, seed0);
         }
-        if (W_out && W_out[i]) std::memcpy(W_out[i], Wo.data(), Wo.size());
-        if (H_out && H_out[i]) std::memcpy(H_out[i], Ho.data(), Ho.size());
-        rob[i] = rb;
-        fit[i] = ph;  // execute re-derives fit = normnan(X - W*H) from the returned factors (:212-222)
-        if (fitquality) fitquality[i] = ph;
-        if (robustness) robustness[i] = rb;
-        if (aic) aic[i] = ai;
+        if (!rc) rc = nmfk_solve(c, bs.data(), gn, p);
+        solve_ms += c->last_solve_ms;
+        for (int q = 0; q < gn && !rc; ++q) {
+            const int i = g.first + q;
+            std::vector<char> Wb, Hb;
+            double ph = 0, rb = 0, ai = 0;
+            int64_t it = 0;
+            rc = finish_run(bs[q], p->clusterWmatrix != 0, Wb, Hb, &ph, &rb, &ai, &it);
+            if (rc) break;
+            tot += it;
+            order_and_store(c, ks[i], p, Wb, Hb, W_out ? W_out[i] : nullptr, H_out ? H_out[i] : nullptr);
+            rob[i] = rb;
+            fit[i] = ph;  // execute re-derives fit = normnan(X - W*H) from the returned factors (:212-222)
+            if (fitquality) fitquality[i] = ph;
+            if (robustness) robustness[i] = rb;
+            if (aic) aic[i] = ai;
+        }
+        for (auto b : bs) nmfk_batch_destroy(b);
+        if (rc) return rc;
     }
-    for (auto b : bs) nmfk_batch_destroy(b);
-    if (rc) return rc;
-    if (kopt) {
-        bool allinf = true;
-        for (double f : fit)
-            if (!std::isinf(f)) allinf = false;
-        *kopt = allinf ? 0 : nmfk_getk(ks, rob.data(), nks, cutoff, 1);  // (:206-208, :225)
-    }
+    c->last_solve_ms = solve_ms;
+    if (kopt) *kopt = kopt_of(ks, nks, fit, rob, cutoff);
     if (total_iters) *total_iters = tot;
+    return NMFK_OK;
+}
+
+#define NC(ctx, call)                                                                                           \
+    do {                                                                                                        \
+        ncclResult_t r__ = (call);                                                                              \
+        if (r__ != ncclSuccess) return fail((ctx), NMFK_E_UNSUPPORTED, std::string(#call) + ": " + g_nccl.getErrorString(r__)); \
+    } while (0)
+
+// execute(X, nkrange, nNMF = nranks * R_local) with the restarts sharded over the ranks of the sweep communicator: the
+// reference's `pmap` over restarts (NMFkExecute.jl:511-526).  No collective inside the iteration loop; per k one
+// all-gather of the H stacks (k x m per restart) and of the 64-byte restart states, one broadcast of the best restart's W
+// (n x k) from the rank that solved it; the clustering + silhouettes of the nranks * R_local solutions of a given k run on
+// rank (k index mod nranks) and the robustness values are summed into place at the end.  Every rank returns everything.
+int32_t nmfk_sweep(nmfk_ctx* c, const int32_t* ks, int32_t nks, int32_t R_local, const void* const* Winit,
+                   const void* const* Hinit, uint64_t seed0, const nmfk_params* p, double cutoff, void* const* W_out,
+                   void* const* H_out, double* fitquality, double* robustness, double* aic, int32_t* kopt, int64_t* total_iters,
+                   int64_t* total_iters_local) {
+    if (!c || !ks || !p || nks < 1 || R_local < 1) return fail(c, NMFK_E_INVALID, "nmfk_sweep: bad arguments");
+    if (!c->has_X) return fail(c, NMFK_E_NO_X, "nmfk_set_X has not been called");
+    const int world = c->sweep_nranks, rank = c->sweep_rank;
+    if (world == 1) {
+        int32_t rc = nmfk_execute(c, ks, nks, R_local, Winit, Hinit, seed0, p, cutoff, W_out, H_out, fitquality, robustness, aic,
+                                  kopt, total_iters);
+        if (!rc && total_iters_local && total_iters) *total_iters_local = *total_iters;
+        return rc;
+    }
+    if (c->sharded) return fail(c, NMFK_E_UNSUPPORTED, "nmfk_sweep: the ctx is row-sharded");
+    if (p->clusterWmatrix)
+        return fail(c, NMFK_E_UNSUPPORTED, "nmfk_sweep: clusterWmatrix would gather the W stacks (n x k per restart) - not available "
+                                           "across ranks");
+    CU(c, cudaSetDevice(c->device));
+    ncclComm_t comm = static_cast<ncclComm_t>(c->sweep_comm);
+    const int R_total = world * R_local;
+    const size_t es = esize(c->dtype);
+    const ncclDataType_t nt = c->dtype == NMFK_F64 ? ncclDouble : ncclFloat;
+    int32_t rc = NMFK_OK;
+    int64_t tot_local = 0, tot_global = 0;
+    double solve_ms = 0.0;
+    std::vector<double> rob((size_t)nks, 0.0), fit((size_t)nks, 0.0);
+    struct Guard {  // batches of the current group, destroyed on every exit path
+        std::vector<nmfk_batch*> v;
+        ~Guard() {
+            for (auto b : v) nmfk_batch_destroy(b);
+        }
+    };
+    for (const auto& g : k_groups(c, ks, nks, R_total)) {
+        const int gn = g.second - g.first;
+        Guard bs, hs;
+        bs.v.assign((size_t)gn, nullptr);
+        hs.v.assign((size_t)gn, nullptr);
+        for (int q = 0; q < gn; ++q) {
+            const int i = g.first + q;
+            rc = nmfk_batch_create(c, ks[i], R_local, &bs.v[q]);
+            if (!rc) rc = nmfk_batch_set_init_partial(bs.v[q], Winit ? Winit[i] : nullptr, Hinit ? Hinit[i] : nullptr,
+                                                      seed0 + (uint64_t)rank * (uint64_t)R_local);
+            if (!rc) rc = nmfk_batch_create_hstack(c, ks[i], R_total, &hs.v[q]);
+            if (rc) return rc;
+        }
+        rc = nmfk_solve(c, bs.v.data(), gn, p);
+        if (rc) return rc;
+        solve_ms += c->last_solve_ms;
+        // phase 1: everything the robustness analysis needs crosses NVLink once per k
+        for (int q = 0; q < gn; ++q) {
+            nmfk_batch *b = bs.v[q], *h = hs.v[q];
+            const int k = b->k;
+            NC(c, g_nccl.allGather(b->H, h->H, (size_t)k * c->m * R_local, nt, comm, c->stream));
+            NC(c, g_nccl.allGather(b->st, h->st, (size_t)R_local * sizeof(UnitState), ncclUint8, comm, c->stream));
+            h->inited = true;
+        }
+        CU(c, cudaStreamSynchronize(c->stream));
+        // phase 2: best restart of every k (every rank sorts the same gathered objectives), its W from the rank that solved it
+        DevBuf wtmp;
+        for (int q = 0; q < gn; ++q) {
+            const int i = g.first + q;
+            nmfk_batch *b = bs.v[q], *h = hs.v[q];
+            const int k = b->k;
+            std::vector<UnitState> st;
+            rc = fetch_state(h, st);
+            if (rc) return rc;
+            for (int r = 0; r < R_total; ++r) {
+                tot_global += st[r].it;
+                if (r / R_local == rank) tot_local += st[r].it;
+            }
+            std::vector<double> obj;
+            std::vector<int32_t> order;
+            sorted_order(c, st, obj, order);
+            const int gbest = order[0], br = gbest / R_local, bl = gbest % R_local;
+            const size_t wb = (size_t)c->n * k * es, hb = (size_t)k * c->m * es;
+            if (wtmp.p) {
+                cudaFree(wtmp.p);
+                wtmp.p = nullptr;
+            }
+            CU(c, wtmp.alloc(wb));
+            char* wsrc = (char*)b->W + (size_t)bl * wb;
+            if (k > 1) {  // nanaction = :zeroed before Wbest / Hbest are re-read (:566-580, :631-635)
+                if (rank == br) CU(c, launch_zero_nan(wsrc, (long long)c->n * k, c->dtype, c->stream));
+                CU(c, launch_zero_nan(h->H, (long long)k * c->m * R_total, c->dtype, c->stream));
+                c->launches += 1 + (rank == br);
+            }
+            NC(c, g_nccl.broadcast(rank == br ? (const void*)wsrc : (const void*)wtmp.p, wtmp.p, (size_t)c->n * k, nt, br, comm,
+                                   c->stream));
+            std::vector<char> Wb(wb), Hb(hb);
+            CU(c, cudaMemcpyAsync(Wb.data(), wtmp.p, wb, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaMemcpyAsync(Hb.data(), (const char*)h->H + (size_t)gbest * hb, hb, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+            // labels[:, 1] = 1:k by construction (NMFkCluster.jl:461), so the reordering of :631-635 is the identity
+            double ph = 0, ai = 0;
+            rc = phi_aic(c, k, Wb, Hb, &ph, &ai);
+            if (rc) return rc;
+            order_and_store(c, k, p, Wb, Hb, W_out ? W_out[i] : nullptr, H_out ? H_out[i] : nullptr);
+            fit[i] = ph;
+            if (fitquality) fitquality[i] = ph;
+            if (aic) aic[i] = ai;
+        }
+        // phase 3: clustering + silhouettes of the R_total solutions, one owner per k, no communication
+        for (int q = 0; q < gn; ++q) {
+            const int i = g.first + q;
+            if (i % world != rank) continue;
+            double rb = 1.0;
+            rc = nmfk_batch_cluster(hs.v[q], 0, nullptr, nullptr, nullptr, nullptr, &rb, nullptr, nullptr);
+            if (rc) return rc;
+            rob[i] = rb;
+        }
+    }
+    {  // robustness of every k to every rank: the owners hold the values, the others zero
+        DevBuf d;
+        CU(c, d.alloc((size_t)nks * sizeof(double)));
+        CU(c, cudaMemcpyAsync(d.p, rob.data(), (size_t)nks * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        NC(c, g_nccl.allReduce(d.p, d.p, (size_t)nks, ncclDouble, ncclSum, comm, c->stream));
+        CU(c, cudaMemcpyAsync(rob.data(), d.p, (size_t)nks * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    c->last_solve_ms = solve_ms;
+    if (robustness) std::copy(rob.begin(), rob.end(), robustness);
+    if (kopt) *kopt = kopt_of(ks, nks, fit, rob, cutoff);
+    if (total_iters) *total_iters = tot_global;
+    if (total_iters_local) *total_iters_local = tot_local;
     return NMFK_OK;
 }
 

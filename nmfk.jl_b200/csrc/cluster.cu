@@ -4,6 +4,7 @@
 // Third-party semantics restated: Distances.cosine_dist / pairwise(CosineDist()), Clustering.silhouettes
 // (neither package is vendored in the reference tree; see oracle/nmfk_oracle.py for the same restatement).
 // Everything is Float64 and deterministic: fixed-order reductions, no floating-point atomics.
+#include <algorithm>
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -164,6 +165,23 @@ __global__ void __launch_bounds__(1024) cluster_kernel(double* __restrict__ V, i
     __syncthreads();
     // newClusterCenters ./= numTrials (:512)
     for (int e = tid; e < k * ld; e += NT) cent[e] = cent[e] / (double)R;
+}
+
+// clusterWmatrix = true without the zero-column fix: `centSeeds` / `newClusterCenters` of the reference ARE the best solution's
+// W (NMFkCluster.jl:426-428, 453-455: no copy on this branch), so after clustersolutions that matrix holds the centroids
+// (:484, :512) and finalize / Wbest (NMFkExecute.jl:631-637) read them.  Mirror it: centroids -> the best W (factor type) and
+// -> the gathered copy the silhouettes are computed from.
+template <typename T>
+__global__ void cent_writeback_kernel(const double* __restrict__ cent, int len, int ld, int k, const int* __restrict__ bias,
+                                      T* __restrict__ Wbest, double* __restrict__ V) {
+    if (*bias) return;  // vcat(factors[i], biasRow) made fresh matrices (:449): nothing is aliased
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)k * len;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e / len), j = (int)(e - (long long)c * len);
+        const T v = (T)cent[(long long)c * ld + j];
+        Wbest[e] = v;
+        V[(long long)c * ld + j] = (double)v;
+    }
 }
 
 // zerostoepsilon(vcat(Ha...)) (NMFkFinalize.jl:52, NMFkHelpers.jl:529-543) + row norms
@@ -369,6 +387,14 @@ cudaError_t launch_cluster(const ClusterArgs& a, int dtype, cudaStream_t s) {
     {
         const size_t smem = (size_t)a.k * a.k * sizeof(double) + (size_t)a.k * sizeof(int);
         cluster_kernel<<<1, 1024, smem, s>>>(a.V, a.len, ld, a.k, a.R, a.bias, a.cent, a.labels);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (a.alias_best != nullptr) {
+        const int blocks = (int)std::min<long long>(((long long)a.k * a.len + 255) / 256, 148 * 4);
+        if (dtype == 1)
+            cent_writeback_kernel<double><<<blocks, 256, 0, s>>>(a.cent, a.len, ld, a.k, a.bias, (double*)a.alias_best, a.V);
+        else
+            cent_writeback_kernel<float><<<blocks, 256, 0, s>>>(a.cent, a.len, ld, a.k, a.bias, (float*)a.alias_best, a.V);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     {

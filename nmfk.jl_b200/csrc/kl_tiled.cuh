@@ -250,7 +250,7 @@ template <typename TX, typename TC>
 __global__ void __launch_bounds__(128) tiled_objective_kernel(const TX* __restrict__ X, int n, int m, int k,
                                                               const TC* __restrict__ Wst, const TC* __restrict__ Hst,
                                                               const UnitState* st, TC lambda, int restore,
-                                                              int only_running, double weight,
+                                                              int only_running, double weight, const WeightRef wref,
                                                               double* __restrict__ partials) {
     extern __shared__ unsigned char smraw[];
     TC* Ws = reinterpret_cast<TC*>(smraw);  // [k][128]
@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(128) tiled_objective_kernel(const TX* __restri
     for (int c = 0; c < k; ++c) Ws[c * 128 + tid] = (i < n) ? W[(long long)i + (long long)c * n] : (TC)0;
     __syncthreads();
     double sw = 0.0, s1 = 0.0;
+    const bool wany = wref.any();
     if (i < n) {
         for (int j = 0; j < m; ++j) {
             const TX xr = X[(long long)i + (long long)j * n];
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(128) tiled_objective_kernel(const TX* __restri
             for (int c = 0; c < k; ++c) p = fma(Ws[c * 128 + tid], __ldg(h + c), p);
             const double e = (double)(x - p);
             s1 = fma(e, e, s1);
-            const double ew = e * weight;
+            const double ew = e * (wany ? weight_at<TX>(wref, weight, i, j, n) : weight);
             sw = fma(ew, ew, sw);
         }
     }
@@ -646,6 +647,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     };
     const int SH = slices(nblkH, n), SW = slices(nblkW, m);
     const int nblkObj = (n + 127) / 128;
+    const bool wobj = a.wref.any();  // per-row / per-column / per-entry weights: the scalar objective kernel applies them
 
     // row-sharded X: den and the H-update numerators are contiguous so that one all-reduce moves both
     const ShardComm* sh = a.shard;
@@ -826,14 +828,14 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
                 ++*launches;
             }
             if (it % a.check_every == 0) {
-                if (use_tc) {
+                if (use_tc && !wobj) {
                     NMFK_TRY(launch_tc_objective(obj_args(0, 0), h_active + 1, s));
-                } else if (use_td) {
+                } else if (use_td && !wobj) {
                     NMFK_TRY(launch_tiled_dmma_objective(obj_args(0, 0), s));
                 } else {
                     dim3 g(nblkObj, R);
                     tiled_objective_kernel<TX, TC><<<g, 128, (size_t)k * 128 * sizeof(TC), s>>>(
-                        (const TX*)a.X, n, m, k, (const TC*)a.W, (const TC*)a.H, a.st, (TC)a.lambda, 0, 1, a.weight, objp);
+                        (const TX*)a.X, n, m, k, (const TC*)a.W, (const TC*)a.H, a.st, (TC)a.lambda, 0, 1, a.weight, a.wref, objp);
                 }
                 NMFK_TRY(cudaGetLastError());
                 // per-restart objective sums in block order (and, row-sharded, over all ranks)
@@ -882,14 +884,14 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     }
     {
         // post-run objective on the restored X + normalisation for restarts that stopped in this call
-        if (use_tc) {
+        if (use_tc && !wobj) {
             NMFK_TRY(launch_tc_objective(obj_args(1, 1), h_active + 1, s));
-        } else if (use_td) {
+        } else if (use_td && !wobj) {
             NMFK_TRY(launch_tiled_dmma_objective(obj_args(1, 1), s));
         } else {
             dim3 g(nblkObj, R);
             tiled_objective_kernel<TX, TC><<<g, 128, (size_t)k * 128 * sizeof(TC), s>>>(
-                (const TX*)a.X, n, m, k, (const TC*)a.W, (const TC*)a.H, a.st, (TC)a.lambda, 1, 0, a.weight, objp);
+                (const TX*)a.X, n, m, k, (const TC*)a.W, (const TC*)a.H, a.st, (TC)a.lambda, 1, 0, a.weight, a.wref, objp);
         }
         NMFK_TRY(cudaGetLastError());
         if (sharded) {

@@ -33,6 +33,23 @@ struct ShardComm {
     cudaError_t (*allreduce)(void* comm, void* buf, size_t count, int dtype, cudaStream_t s);
 };
 
+// Non-scalar `weight` keyword (NMFkExecute.jl:484, NMFkMultiplicative.jl:74,125): the residual of entry (i,j) is
+// multiplied by scalar * wrow[i] * wcol[j] * wmat[i + j*n]; a null array counts as 1.  Element type of X.
+struct WeightRef {
+    const void* wrow;
+    const void* wcol;
+    const void* wmat;
+    __host__ __device__ bool any() const { return wrow != nullptr || wcol != nullptr || wmat != nullptr; }
+};
+template <typename T>
+__device__ __forceinline__ double weight_at(const WeightRef& w, double scalar, long long i, long long j, long long n) {
+    double v = scalar;
+    if (w.wrow != nullptr) v *= (double)static_cast<const T*>(w.wrow)[i];
+    if (w.wcol != nullptr) v *= (double)static_cast<const T*>(w.wcol)[j];
+    if (w.wmat != nullptr) v *= (double)static_cast<const T*>(w.wmat)[i + j * n];
+    return v;
+}
+
 // Arguments of one batched KL solve (R restarts at one k).
 struct SolveArgs {
     const void* X;    // n x m column-major, zeros -> lambda, NaN kept
@@ -47,6 +64,7 @@ struct SolveArgs {
     int32_t SH, SW;   // DMMA resident engine: slices of the reduction range per half-update (host heuristic)
     int32_t maxiter, maxbad, maxre, stopconv, check_every, Wfixed, Hfixed, normalize, iter_limit;
     double lambda, tol, tolOF, eps_clamp, weight;
+    WeightRef wref;          // non-scalar weight (tiled engine with the scalar objective kernel only)
     int32_t tiled_tc;        // tiled engine, Float32 without NaN: 1 = tcgen05 kernel (kl_tiled_tc.cu), 0 = scalar-FMA kernel
     const ShardComm* shard;  // non-null: n is the LOCAL row count, the tiled engine all-reduces the k x m partials
 };
@@ -80,7 +98,7 @@ bool resident_fits(int n, int m, int k, size_t sizeofTC);
 // generic residual sums of one (W,H): partials[2*b] = weighted ssq, partials[2*b+1] = plain ssq of CTA b
 int residual_blocks(int n);
 cudaError_t launch_residual(const void* X, int dtype, int n, int m, int k, const void* W, const void* H, double lambda,
-                            int restore, double weight, double* d_partials, cudaStream_t s);
+                            int restore, double weight, const WeightRef& wref, double* d_partials, cudaStream_t s);
 
 // preprocessing (K1): raw X -> Xp, Xpt + statistics
 struct PreStats {
@@ -111,6 +129,8 @@ struct ClusterArgs {
     double* V;            // (R*k) x (len+1) gathered + floored vectors, row-major, sorted order
     double* vnorm;        // R*k
     double* Dm;           // (R*k) x (R*k) cosine distance matrix
+    void* alias_best;     // clusterWmatrix: W of the best solution (n x k, factor type), overwritten with the centroids like
+                          // the reference's aliased newClusterCenters (NMFkCluster.jl:453-455); nullptr otherwise
 };
 cudaError_t launch_cluster(const ClusterArgs& a, int dtype, cudaStream_t s);
 cudaError_t launch_zero_nan(void* p, long long len, int dtype, cudaStream_t s);

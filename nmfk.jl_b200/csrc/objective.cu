@@ -14,7 +14,8 @@ constexpr int kRows = 128;  // rows of X per CTA
 template <typename T>
 __global__ void __launch_bounds__(kRows) residual_kernel(const T* __restrict__ X, int n, int m, int k,
                                                          const T* __restrict__ W, const T* __restrict__ H, T lambda,
-                                                         int restore, double weight, double* __restrict__ partials) {
+                                                         int restore, double weight, const WeightRef wref,
+                                                         double* __restrict__ partials) {
     extern __shared__ unsigned char smraw[];
     T* Ws = reinterpret_cast<T*>(smraw);  // [k][kRows]
     __shared__ double red[2][kRows / 32];
@@ -22,6 +23,7 @@ __global__ void __launch_bounds__(kRows) residual_kernel(const T* __restrict__ X
     for (int a = 0; a < k; ++a) Ws[a * kRows + tid] = (i < n) ? W[(size_t)i + (size_t)a * n] : (T)0;
     __syncthreads();
     double sw = 0.0, s1 = 0.0;
+    const bool wany = wref.any();
     if (i < n) {
         for (int j = 0; j < m; ++j) {
             const T xr = X[(size_t)i + (size_t)j * n];
@@ -33,7 +35,7 @@ __global__ void __launch_bounds__(kRows) residual_kernel(const T* __restrict__ X
             for (int a = 0; a < k; ++a) p = fma(Ws[a * kRows + tid], __ldg(h + a), p);
             const double e = (double)(x - p);
             s1 = fma(e, e, s1);
-            const double ew = e * weight;
+            const double ew = e * (wany ? weight_at<T>(wref, weight, i, j, n) : weight);
             sw = fma(ew, ew, sw);
         }
     }
@@ -62,15 +64,15 @@ __global__ void __launch_bounds__(kRows) residual_kernel(const T* __restrict__ X
 int residual_blocks(int n) { return (n + kRows - 1) / kRows; }
 
 cudaError_t launch_residual(const void* X, int dtype, int n, int m, int k, const void* W, const void* H, double lambda,
-                            int restore, double weight, double* d_partials, cudaStream_t s) {
+                            int restore, double weight, const WeightRef& wref, double* d_partials, cudaStream_t s) {
     const int blocks = residual_blocks(n);
     const size_t smem = (size_t)k * kRows * (dtype == 1 ? 8 : 4);
     if (dtype == 1)
         residual_kernel<double><<<blocks, kRows, smem, s>>>((const double*)X, n, m, k, (const double*)W,
-                                                            (const double*)H, lambda, restore, weight, d_partials);
+                                                            (const double*)H, lambda, restore, weight, wref, d_partials);
     else
         residual_kernel<float><<<blocks, kRows, smem, s>>>((const float*)X, n, m, k, (const float*)W, (const float*)H,
-                                                           (float)lambda, restore, weight, d_partials);
+                                                           (float)lambda, restore, weight, wref, d_partials);
     return cudaGetLastError();
 }
 

@@ -8,6 +8,8 @@
 //        lanes on consecutive addresses,
 // and the statistics the reference derives from X: count of NaN, of entries <= 0, of negative
 // entries (-> the "must be nonnegative" error), all-zero rows / columns (-> its warnings).
+#include <algorithm>
+
 #include "nmfk_internal.h"
 #include "philox.h"
 
@@ -118,11 +120,13 @@ cudaError_t launch_preprocess(const void* Xraw, void* Xp, void* Xpt, int64_t n, 
 // stream element e of restart r = numpy.random.Generator(Philox(key=seed0+r+1)).random(...)[e];
 // the first n*k elements fill W (column-major), the next k*m fill H: W is drawn before H.
 // Row-sharded X: the stream is that of the GLOBAL n x k matrix; this rank keeps rows [row0, row0 + nloc).
+// W == nullptr or H == nullptr: only the other factor is drawn, from the START of the stream (the reference draws W only when
+// Winit is empty and then H only when Hinit is empty, NMFkMultiplicative.jl:37-55).
 template <typename T>
 __global__ void philox_init_kernel(T* __restrict__ W, T* __restrict__ H, long long n, long long row0, long long nloc,
                                    int k, long long km, int R, unsigned long long seed0) {
-    const long long nk = n * k;
-    const long long per = nk + km;
+    const long long nk = W != nullptr ? n * k : 0;
+    const long long per = nk + (H != nullptr ? km : 0);
     const long long blocks4 = (per + 3) / 4;
     const long long total = blocks4 * R;
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
@@ -147,8 +151,9 @@ __global__ void philox_init_kernel(T* __restrict__ W, T* __restrict__ H, long lo
 
 cudaError_t launch_philox_init(void* W, void* H, int64_t n, int64_t row0, int64_t nloc, int k, int64_t m, int R,
                                uint64_t seed0, int dtype, cudaStream_t s) {
-    const long long nk = n * k, km = (long long)k * m;
-    const long long total = ((nk + km + 3) / 4) * R;
+    if (W == nullptr && H == nullptr) return cudaSuccess;
+    const long long nk = W != nullptr ? n * k : 0, km = (long long)k * m;
+    const long long total = ((nk + (H != nullptr ? km : 0) + 3) / 4) * R;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
@@ -156,6 +161,127 @@ cudaError_t launch_philox_init(void* W, void* H, int64_t n, int64_t row0, int64_
         philox_init_kernel<double><<<blocks, 256, 0, s>>>((double*)W, (double*)H, n, row0, nloc, k, km, R, seed0);
     else
         philox_init_kernel<float><<<blocks, 256, 0, s>>>((float*)W, (float*)H, n, row0, nloc, k, km, R, seed0);
+    return cudaGetLastError();
+}
+
+// ---- normalizevector (NMFkMultiplicative.jl:27-31): Xn = Xp ./ nv (rows), and its transpose -----------------------
+template <typename T>
+__global__ void rownormalize_kernel(const T* __restrict__ Xp, T* __restrict__ Xn, T* __restrict__ Xnt, long long n,
+                                    long long m, const T* __restrict__ nv) {
+    __shared__ T tile[32][33];
+    const long long i0 = (long long)blockIdx.x * 32, j0 = (long long)blockIdx.y * 32;
+    for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+        const long long i = i0 + threadIdx.x, j = j0 + jj;
+        if (i < n && j < m) {
+            const T x = Xp[i + j * n] / nv[i];
+            Xn[i + j * n] = x;
+            tile[jj][threadIdx.x] = x;
+        }
+    }
+    __syncthreads();
+    for (int ii = threadIdx.y; ii < 32; ii += blockDim.y) {
+        const long long i = i0 + ii, j = j0 + threadIdx.x;
+        if (i < n && j < m) Xnt[j + i * m] = tile[threadIdx.x][ii];
+    }
+}
+
+cudaError_t launch_rownormalize(const void* Xp, void* Xn, void* Xnt, int64_t n, int64_t m, const void* nv, int dtype,
+                                cudaStream_t s) {
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((m + 31) / 32)), block(32, 8);
+    if (dtype == 1)
+        rownormalize_kernel<double><<<grid, block, 0, s>>>((const double*)Xp, (double*)Xn, (double*)Xnt, n, m, (const double*)nv);
+    else
+        rownormalize_kernel<float><<<grid, block, 0, s>>>((const float*)Xp, (float*)Xn, (float*)Xnt, n, m, (const float*)nv);
+    return cudaGetLastError();
+}
+
+// W .*= normalizevector (NMFkMultiplicative.jl:121) for one restart's n x k factor
+template <typename T>
+__global__ void scale_rows_kernel(T* __restrict__ W, long long n, int k, const T* __restrict__ nv) {
+    const long long total = n * k;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
+        W[e] = W[e] * nv[e % n];
+}
+
+cudaError_t launch_scale_rows(void* W, int64_t n, int k, const void* nv, int dtype, cudaStream_t s) {
+    int blocks = (int)std::min<long long>((n * k + 255) / 256, 148 * 8);
+    if (blocks < 1) blocks = 1;
+    if (dtype == 1)
+        scale_rows_kernel<double><<<blocks, 256, 0, s>>>((double*)W, n, k, (const double*)nv);
+    else
+        scale_rows_kernel<float><<<blocks, 256, 0, s>>>((float*)W, n, k, (const float*)nv);
+    return cudaGetLastError();
+}
+
+// The normalisation of execute_singlerun_compute (NMFkExecute.jl:795-805) for ONE restart, outside the engines (used after
+// the normalizevector epilogue): normalize 1: total = sum(H; dims=2); W .*= total'; H ./= total; 2: total = sum(W; dims=1);
+// W ./= total; H .*= total'.  One CTA; fixed-order sums in Float64 rounded to T like the engines' finish kernels.
+template <typename T>
+__global__ void __launch_bounds__(256) renormalize_kernel(T* __restrict__ W, T* __restrict__ H, long long n, long long m, int k,
+                                                          int normalize) {
+    __shared__ double red[8];
+    __shared__ double tot[32];
+    const int tid = threadIdx.x, NT = blockDim.x;
+    for (int c = 0; c < k; ++c) {
+        double s = 0.0;
+        if (normalize == 1)
+            for (long long j = tid; j < m; j += NT) s += (double)H[j * k + c];
+        else
+            for (long long i = tid; i < n; i += NT) s += (double)W[i + (long long)c * n];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((tid & 31) == 0) red[tid >> 5] = s;
+        __syncthreads();
+        if (tid == 0) {
+            double a = 0.0;
+            for (int w = 0; w < NT / 32; ++w) a += red[w];
+            tot[c] = (double)(T)a;
+        }
+        __syncthreads();
+    }
+    if (normalize == 1) {
+        for (long long e = tid; e < n * k; e += NT) W[e] = W[e] * (T)tot[e / n];
+        for (long long e = tid; e < (long long)k * m; e += NT) H[e] = H[e] / (T)tot[e % k];
+    } else {
+        for (long long e = tid; e < n * k; e += NT) W[e] = W[e] / (T)tot[e / n];
+        for (long long e = tid; e < (long long)k * m; e += NT) H[e] = H[e] * (T)tot[e % k];
+    }
+}
+
+cudaError_t launch_renormalize(void* W, void* H, int64_t n, int64_t m, int k, int normalize, int dtype, cudaStream_t s) {
+    if (normalize != 1 && normalize != 2) return cudaSuccess;
+    if (dtype == 1)
+        renormalize_kernel<double><<<1, 256, 0, s>>>((double*)W, (double*)H, n, m, k, normalize);
+    else
+        renormalize_kernel<float><<<1, 256, 0, s>>>((float*)W, (float*)H, n, m, k, normalize);
+    return cudaGetLastError();
+}
+
+// flags[r] = 1 when restart r's W or H holds a NaN (nanaction == :removed, NMFkExecute.jl:581-596)
+template <typename T>
+__global__ void count_nan_kernel(const T* __restrict__ W, const T* __restrict__ H, long long wlen, long long hlen,
+                                 int32_t* __restrict__ flags) {
+    const int r = blockIdx.y;
+    int found = 0;
+    if (W != nullptr) {
+        const T* w = W + (long long)r * wlen;
+        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < wlen; e += (long long)gridDim.x * blockDim.x)
+            found |= (w[e] != w[e]);
+    }
+    const T* h = H + (long long)r * hlen;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < hlen; e += (long long)gridDim.x * blockDim.x)
+        found |= (h[e] != h[e]);
+    if (__syncthreads_or(found) && threadIdx.x == 0) atomicOr(&flags[r], 1);
+}
+
+cudaError_t launch_count_nan(const void* W, const void* H, int64_t wlen, int64_t hlen, int R, int dtype, int32_t* d_flags,
+                             cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(d_flags, 0, (size_t)R * sizeof(int32_t), s);
+    if (e != cudaSuccess) return e;
+    dim3 g((unsigned)std::min<long long>((std::max(wlen, hlen) + 255) / 256, 64), R);
+    if (dtype == 1)
+        count_nan_kernel<double><<<g, 256, 0, s>>>((const double*)W, (const double*)H, wlen, hlen, d_flags);
+    else
+        count_nan_kernel<float><<<g, 256, 0, s>>>((const float*)W, (const float*)H, wlen, hlen, d_flags);
     return cudaGetLastError();
 }
 

@@ -27,7 +27,8 @@ class Params(C.Structure):
                 ("maxiter", C.c_int32), ("maxbaditers", C.c_int32), ("maxreattempts", C.c_int32),
                 ("stopconv", C.c_int32), ("check_every", C.c_int32), ("Wfixed", C.c_int32), ("Hfixed", C.c_int32),
                 ("normalize", C.c_int32), ("iter_limit", C.c_int32), ("engine", C.c_int32),
-                ("reserved", C.c_int32 * 4)]
+                ("clusterWmatrix", C.c_int32), ("stop_rule", C.c_int32), ("variant", C.c_int32),
+                ("reserved", C.c_int32 * 1)]
 
 
 class XInfo(C.Structure):
@@ -50,10 +51,13 @@ SIGNATURES = {
     "nmfk_ctx_sync": (_i32, [_P]),
     "nmfk_set_X": (_i32, [_P, _P, _i64, _i64, _i32, _dbl, _P, _i32]),
     "nmfk_get_xinfo": (_i32, [_P, C.POINTER(XInfo)]),
+    "nmfk_set_weight": (_i32, [_P, _P, _i64, _i64]),
     "nmfk_batch_create": (_i32, [_P, _i32, _i32, C.POINTER(_P)]),
     "nmfk_batch_destroy": (_i32, [_P]),
     "nmfk_batch_set_init": (_i32, [_P, _P, _P]),
     "nmfk_batch_init_random": (_i32, [_P, _u64]),
+    "nmfk_batch_set_init_partial": (_i32, [_P, _P, _P, _u64]),
+    "nmfk_batch_select": (_i32, [_P, _dbl, _dbl, _i32, _pi32, _pi32]),
     "nmfk_batch_create_hstack": (_i32, [_P, _i32, _i32, C.POINTER(_P)]),
     "nmfk_batch_device_ptrs": (_i32, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "nmfk_batch_import": (_i32, [_P, _P, _P, _pdbl, _pi32, _i32]),
@@ -71,6 +75,9 @@ SIGNATURES = {
     "nmfk_execute_run": (_i32, [_P, _i32, _i32, _P, _P, _u64, C.POINTER(Params), _P, _P, _pdbl, _pdbl, _pdbl, _pi64]),
     "nmfk_execute": (_i32, [_P, _pi32, _i32, _i32, C.POINTER(_P), C.POINTER(_P), _u64, C.POINTER(Params), _dbl,
                             C.POINTER(_P), C.POINTER(_P), _pdbl, _pdbl, _pdbl, _pi32, _pi64]),
+    "nmfk_ctx_sweep_comm_init": (_i32, [_P, _i32, _i32, _P]),
+    "nmfk_sweep": (_i32, [_P, _pi32, _i32, _i32, C.POINTER(_P), C.POINTER(_P), _u64, C.POINTER(Params), _dbl,
+                          C.POINTER(_P), C.POINTER(_P), _pdbl, _pdbl, _pdbl, _pi32, _pi64, _pi64]),
     "nmfk_getk": (_i32, [_pi32, _pdbl, _i32, _dbl, _i32]),
     "nmfk_signalorder": (_i32, [_P, _P, _i64, _i32, _i64, _i32, _pi32]),
     "nmfk_launch_count": (_i64, [_P]),

@@ -65,8 +65,10 @@ class Context:
         except Exception:
             pass
 
-    def set_X(self, X: np.ndarray, lam: float = 1e-32):
-        """NMFpreprocessing! (NMFkMultiplicative.jl:3-22).  The caller's X is never modified."""
+    def set_X(self, X: np.ndarray, lam: float = 1e-32, normalizevector=None):
+        """NMFpreprocessing! (NMFkMultiplicative.jl:3-22).  The caller's X is never modified.
+        normalizevector (length n, :27-31): the solver works on X ./ normalizevector, W is scaled back and the objective is
+        taken against X itself when a restart finishes (:119-125)."""
         X = np.asarray(X)
         if X.ndim != 2:
             raise ValueError("X must be a matrix (N>2 arrays are delegated to tensorfactorization in the reference)")
@@ -76,8 +78,26 @@ class Context:
         self.dtype = _DT[Xf.dtype]
         self.np_dtype = Xf.dtype.type
         self.n, self.m = Xf.shape
-        check(self._lib.nmfk_set_X(self._h, _ptr(Xf), self.n, self.m, self.dtype, lam, None, 0), self._h)
+        nv = None
+        if normalizevector is not None and len(normalizevector) != 0:
+            nv = np.ascontiguousarray(np.asarray(normalizevector, dtype=self.np_dtype).reshape(-1))
+            if nv.shape[0] != self.n:  # :30
+                raise NMFkError(-4, "Length of normalizing vector does not match: %d vs %d" % (nv.shape[0], self.n))
+        check(self._lib.nmfk_set_X(self._h, _ptr(Xf), self.n, self.m, self.dtype, lam, _ptr(nv), 0), self._h)
         return self.xinfo()
+
+    def set_weight(self, weight):
+        """The `weight` keyword when it is an array (NMFkExecute.jl:484): a vector of length n weights the rows, a 1 x m
+        matrix the columns, an n x m matrix the entries of (X - W*H) in the objective (NMFkMultiplicative.jl:74,125).
+        None or a scalar clears it (scalars travel in the solver parameters)."""
+        if weight is None or np.isscalar(weight):
+            check(self._lib.nmfk_set_weight(self._h, None, 0, 0), self._h)
+            return
+        w = np.asarray(weight, dtype=self.np_dtype)
+        if w.ndim == 1:
+            w = w.reshape(-1, 1)  # a Julia Vector broadcasts as a column
+        wf = np.asfortranarray(w)
+        check(self._lib.nmfk_set_weight(self._h, _ptr(wf), wf.shape[0], wf.shape[1]), self._h)
 
     def comm_init(self, nranks: int, rank: int, unique_id: Optional[bytes], row0: int, n_global: int):
         """Row-sharded X (BASELINE C5; NMFmultiplicative(::DArray), NMFkMultiplicative.jl:129-197): this
@@ -154,18 +174,21 @@ class Batch:
         except Exception:
             pass
 
-    def set_init(self, Winit: np.ndarray, Hinit: np.ndarray):
-        """Winit: (R, n, k) or list of n x k; Hinit: (R, k, m).  Sizes are asserted like
-        NMFkMultiplicative.jl:40,50."""
+    def set_init(self, Winit=None, Hinit=None, seed0: int = 0):
+        """Winit: (R, n, k) or list of n x k; Hinit: (R, k, m).  Sizes are asserted like NMFkMultiplicative.jl:40,50.
+        Either may be None: that factor is then drawn on the device from restart r's Philox stream (key seed0 + r + 1),
+        the first numbers of the stream when it is the only one drawn (:37-55)."""
         c = self.ctx
-        W = np.stack([_f(w, c.np_dtype) for w in Winit]) if not isinstance(Winit, np.ndarray) else Winit
-        H = np.stack([_f(h, c.np_dtype) for h in Hinit]) if not isinstance(Hinit, np.ndarray) else Hinit
-        assert W.shape == (self.R, c.n, self.k), "size(Winit) == (n, k)"
-        assert H.shape == (self.R, self.k, c.m), "size(Hinit) == (k, m)"
-        # restart-major stack of column-major matrices
-        Wb = np.ascontiguousarray(np.transpose(W, (0, 2, 1)), dtype=c.np_dtype)
-        Hb = np.ascontiguousarray(np.transpose(H, (0, 2, 1)), dtype=c.np_dtype)
-        check(c._lib.nmfk_batch_set_init(self._h, _ptr(Wb), _ptr(Hb)), c._h)
+        Wb = Hb = None
+        if Winit is not None:
+            W = np.stack([_f(w, c.np_dtype) for w in Winit]) if not isinstance(Winit, np.ndarray) else Winit
+            assert W.shape == (self.R, c.n, self.k), "size(Winit) == (n, k)"
+            Wb = np.ascontiguousarray(np.transpose(W, (0, 2, 1)), dtype=c.np_dtype)  # restart-major stack of column-major matrices
+        if Hinit is not None:
+            H = np.stack([_f(h, c.np_dtype) for h in Hinit]) if not isinstance(Hinit, np.ndarray) else Hinit
+            assert H.shape == (self.R, self.k, c.m), "size(Hinit) == (k, m)"
+            Hb = np.ascontiguousarray(np.transpose(H, (0, 2, 1)), dtype=c.np_dtype)
+        check(c._lib.nmfk_batch_set_init_partial(self._h, _ptr(Wb), _ptr(Hb), int(seed0)), c._h)
 
     def init_random(self, seed0: int):
         check(self.ctx._lib.nmfk_batch_init_random(self._h, int(seed0)), self.ctx._h)
@@ -195,6 +218,18 @@ class Batch:
         check(self.ctx._lib.nmfk_batch_objective(self._h, weight, o.ctypes.data_as(_lib._pdbl)), self.ctx._h)
         return o
 
+    def select(self, acceptratio: float = 1, acceptfactor: float = np.inf, nanaction: str = "zeroed"):
+        """Solution filtering of execute_run (NMFkExecute.jl:551-597): -> sorted restart indices that reach
+        clustersolutions / finalize.  Stored in the batch; `cluster` / `cluster_means` then work on them."""
+        if nanaction not in ("zeroed", "removed"):
+            raise NMFkError(-1, "nanaction must be :zeroed or :removed")
+        order = np.empty(self.R, dtype=np.int32)
+        nk = C.c_int32()
+        check(self.ctx._lib.nmfk_batch_select(self._h, float(acceptratio), float(acceptfactor), int(nanaction == "removed"),
+                                              order.ctypes.data_as(_lib._pi32), C.byref(nk)), self.ctx._h)
+        self.nkept = nk.value
+        return order[:nk.value].copy()
+
     def cluster(self, clusterWmatrix: bool = False):
         """sortperm + clustersolutions + finalize silhouettes (NMFkExecute.jl:545-638,
         NMFkCluster.jl:425-517, NMFkFinalize.jl:36-79).
@@ -212,7 +247,8 @@ class Batch:
         check(c._lib.nmfk_batch_cluster(self._h, int(clusterWmatrix), order.ctypes.data_as(_lib._pi32),
                                         labels.ctypes.data_as(_lib._pi32), sil.ctypes.data_as(_lib._pdbl),
                                         csil.ctypes.data_as(_lib._pdbl), C.byref(rob), _ptr(cent), C.byref(cols)), c._h)
-        return dict(order=order, labels=labels.T, sil=sil.T, clustersil=csil, robustness=rob.value,
+        nk = getattr(self, "nkept", None) or R  # after select(): only the kept solutions were clustered
+        return dict(order=order[:nk], labels=labels[:nk].T, sil=sil[:nk].T, clustersil=csil, robustness=rob.value,
                     centroids=cent[:cols.value].T if cols.value else None)
 
 
@@ -233,167 +269,224 @@ class Batch:
 # ------------------------------------------------------------------------------------------
 # reference-shaped functions
 # ------------------------------------------------------------------------------------------
-def _params_from_kw(kw: dict, **defaults) -> Params:
-    """Map the reference's keyword names onto nmfk_params; unknown keywords are tolerated like the
-    `kw...` sink of NMFkMultiplicative.jl:24."""
-    names = {"tol": "tol", "tolOF": "tolOF", "maxiter": "maxiter", "maxbaditers": "maxbaditers",
-             "maxreattempts": "maxreattempts", "stopconv": "stopconv", "Wfixed": "Wfixed", "Hfixed": "Hfixed",
-             "weight": "weight", "engine": "engine", "iter_limit": "iter_limit", "normalize": "normalize"}
+_PARAM_NAMES = ("tol", "tolOF", "maxiter", "maxbaditers", "maxreattempts", "stopconv", "Wfixed", "Hfixed", "engine", "iter_limit",
+                "normalize", "stop_rule", "variant")
+
+
+def _params_from_kw(kw: dict, ctx: Optional[Context] = None, **defaults) -> Params:
+    """Map the reference's keyword names onto nmfk_params; unknown keywords are tolerated like the `kw...` sink of
+    NMFkMultiplicative.jl:24.  `weight`: a scalar travels in the parameters, an array (vector of length n, 1 x m, n x m;
+    NMFkExecute.jl:484) is installed on the context."""
     vals = dict(defaults)
     for k in list(kw):
-        if k in names:
-            vals[names[k]] = kw.pop(k)
-    if "weight" in vals and not np.isscalar(vals["weight"]):
-        raise NMFkError(-6, "vector/matrix weights are not on the B200 path yet")
+        if k in _PARAM_NAMES:
+            vals[k] = kw.pop(k)
+    weight = kw.pop("weight", vals.pop("weight", 1))
+    if np.isscalar(weight):
+        vals["weight"] = float(weight)
+        if ctx is not None:
+            ctx.set_weight(None)
+    else:
+        if ctx is None:
+            raise NMFkError(-1, "array weights need a context")
+        vals["weight"] = 1.0
+        ctx.set_weight(weight)
     for b in ("Wfixed", "Hfixed"):
         if b in vals:
             vals[b] = int(bool(vals[b]))
     return default_params(**vals)
 
 
-def NMFmultiplicative(X, k: int, *, Winit=None, Hinit=None, seed: int = -1, lam: float = 1e-32, ctx: Context = None,
-                      **kw):
-    """`NMFk.NMFmultiplicative(X, k; ...)` NMFkMultiplicative.jl:24-127 -> (W, H, objvalue) with
-    objvalue the sum of squares of :125.  maxiter defaults to 1000000 as in the direct call.
-    `normalizevector` (length n, :27-31, :119-122): the rows of X are divided by it for the solve, W is scaled back and
-    the objective is taken against the caller's X.  (The reference substitutes lambda for zeros BEFORE dividing, so its
-    substituted entries are lambda / normalizevector[i]; here they are lambda: a 1e-32-scale difference.)"""
+def _seed0(seed) -> int:
+    """restart i (1-based) draws from Philox(key=seed+i): `seed=kwseed+i` of NMFkExecute.jl:536; no seed = the global RNG."""
+    return int(seed) if seed is not None and seed >= 0 else int(np.random.randint(0, 2 ** 31))
+
+
+def _stack(a, R, shape, dt, what):
+    """One n x k (k x m) matrix for all restarts, like the reference's Winit / Hinit keywords, or an explicit (R, ., .) stack."""
+    if a is None or np.size(a) == 0:  # sizeof(Winit) == 0 (NMFkMultiplicative.jl:37,47)
+        return None
+    a = np.asarray(a, dtype=dt)
+    if a.ndim == 2:
+        assert a.shape == shape, "size(%s) == %s" % (what, shape)  # :40,50
+        a = np.broadcast_to(a, (R,) + shape)
+    assert a.shape == (R,) + shape, "size(%s) == %s" % (what, shape)
+    return a
+
+
+def NMFmultiplicative(X, k: int, *, Winit=None, Hinit=None, seed: int = -1, lam: float = 1e-32, normalizevector=None,
+                      ctx: Context = None, **kw):
+    """`NMFk.NMFmultiplicative(X, k; ...)` NMFkMultiplicative.jl:24-127 -> (W, H, objvalue) with objvalue the sum of squares
+    of :125.  maxiter defaults to 1000000 as in the direct call.  Winit and Hinit are independent (:37-55); weight may be a
+    scalar, a vector of length n, a 1 x m or an n x m matrix (:74,125); normalizevector divides the rows of X for the solve
+    (:27-31, :119-122).  (The reference substitutes lambda for zeros BEFORE dividing, so its substituted entries are
+    lambda / normalizevector[i]; NaN entries here start from lambda: a 1e-32-scale difference.)"""
     own = ctx is None
     ctx = ctx or Context()
     try:
-        nv = kw.pop("normalizevector", None)
-        if nv is not None and len(nv) != 0:
-            Xh = np.asarray(X)
-            nv = np.asarray(nv, dtype=Xh.dtype).reshape(-1)
-            if nv.shape[0] != Xh.shape[0]:
-                raise NMFkError(-4, "Length of normalizing vector does not match: %d vs %d" % (nv.shape[0], Xh.shape[0]))
-            W, H, _ = NMFmultiplicative(Xh / nv[:, None], k, Winit=Winit, Hinit=Hinit, seed=seed, lam=lam, ctx=ctx, **kw)
-            W = np.asfortranarray(W * nv[:, None])
-            ctx.set_X(Xh, lam)
-            return W, H, float(ctx.fit(W, H)) ** 2
-        if own or X is not None:
-            ctx.set_X(X, lam)
-        p = _params_from_kw(kw, maxiter=kw.pop("maxiter", 1000000), normalize=0)
+        ctx.set_X(X, lam, normalizevector)
+        p = _params_from_kw(kw, ctx, maxiter=kw.pop("maxiter", 1000000), normalize=0)
         b = ctx.batch(k, 1)
-        if Winit is not None and Hinit is not None:
-            b.set_init(np.asarray(Winit)[None], np.asarray(Hinit)[None])
-        elif Winit is None and Hinit is None:
-            b.init_random(seed - 1 if seed >= 0 else int(np.random.randint(0, 2 ** 31)))
-        else:
-            raise NMFkError(-6, "give both Winit and Hinit or neither")
-        ctx.solve([b], p)
-        r = b.get()
-        b.close()
+        try:
+            b.set_init(_stack(Winit, 1, (ctx.n, k), ctx.np_dtype, "Winit"), _stack(Hinit, 1, (k, ctx.m), ctx.np_dtype, "Hinit"),
+                       _seed0(seed) - 1)
+            ctx.solve([b], p)
+            r = b.get()
+        finally:
+            b.close()
         return np.asfortranarray(r["W"][0]), np.asfortranarray(r["H"][0]), float(r["obj_ssq"][0])
     finally:
         if own:
             ctx.close()
 
 
+def NMFmultiplicative_darray(X, k: int, *, stopconv: int = 10000, **kw):
+    """`NMFk.NMFmultiplicative(X::DArray, k; ...)` NMFkMultiplicative.jl:129-197: the distributed method's own stop rule (no
+    tolOF / baditers / reattempts, no weight, stopconv=10000).  On one GPU this is a flag of the same engines; with the rows
+    of X spread over several GPUs use nmfk_b200.dist.solve_rowsharded(..., params=default_params(stop_rule=1))."""
+    kw.pop("weight", None)
+    return NMFmultiplicative(X, k, stop_rule=1, stopconv=stopconv, **kw)
+
+
 def execute_singlerun(X, nk: int, *, Winit=None, Hinit=None, seed: int = -1, clusterWmatrix: bool = False,
-                      ctx: Context = None, **kw):
-    """`execute_singlerun_compute(X, nk; method=:simple, ...)` NMFkExecute.jl:729-807 ->
-    (W, H, objvalue): objvalue = normnan(X - W*H), rows of H sum to one."""
+                      normalizevector=None, ctx: Context = None, **kw):
+    """`execute_singlerun_compute(X, nk; method=:simple, ...)` NMFkExecute.jl:729-807 -> (W, H, objvalue): objvalue =
+    normnan(X - W*H), rows of H sum to one (columns of W with clusterWmatrix=true, :796-799)."""
     own = ctx is None
     ctx = ctx or Context()
     try:
-        ctx.set_X(X, kw.pop("lam", 1e-32))
-        modify = not ("Wfixed" in kw or "Hfixed" in kw)
-        p = _params_from_kw(kw, normalize=(2 if clusterWmatrix else 1) if modify else 0)
+        ctx.set_X(X, kw.pop("lam", 1e-32), normalizevector)
+        modify = kw.pop("modifymatrices", True)
+        p = _params_from_kw(kw, ctx, normalize=(2 if clusterWmatrix else 1) if modify else 0)
         b = ctx.batch(nk, 1)
-        if Winit is not None and Hinit is not None:
-            b.set_init(np.asarray(Winit)[None], np.asarray(Hinit)[None])
-        else:
-            b.init_random(seed - 1 if seed >= 0 else int(np.random.randint(0, 2 ** 31)))
-        ctx.solve([b], p)
-        r = b.get()
-        b.close()
+        try:
+            b.set_init(_stack(Winit, 1, (ctx.n, nk), ctx.np_dtype, "Winit"), _stack(Hinit, 1, (nk, ctx.m), ctx.np_dtype, "Hinit"),
+                       _seed0(seed) - 1)
+            ctx.solve([b], p)
+            r = b.get()
+        finally:
+            b.close()
         return np.asfortranarray(r["W"][0]), np.asfortranarray(r["H"][0]), ctx.np_dtype(r["obj_norm"][0])
     finally:
         if own:
             ctx.close()
 
 
-def _execute_run_means(ctx, X, nk, nNMF, clusterWmatrix, seed0, inits, p, details):
-    """best=false (NMFkExecute.jl:655-658 not taken): Wa, Ha = the per-cluster means of finalize (:637), phi and aic
-    from them (:664-708).  Same device calls as the best=true path, composed on the host."""
+def _run_inits(ctx, nk, nNMF, inits, Winit, Hinit):
+    """(Winit stack, Hinit stack) from either the harness-style `inits=(W (R,n,k), H (R,k,m))` or the reference's single
+    Winit / Hinit matrices shared by every restart (the kw pass-through of NMFkExecute.jl:536)."""
+    if inits is not None:
+        Winit, Hinit = inits
+    return (_stack(Winit, nNMF, (ctx.n, nk), ctx.np_dtype, "Winit"), _stack(Hinit, nNMF, (nk, ctx.m), ctx.np_dtype, "Hinit"))
+
+
+def execute_run(X, nk: int, nNMF: int, *, clusterWmatrix: bool = False, seed: Optional[int] = None, inits=None, Winit=None,
+                Hinit=None, ctx: Context = None, details: Optional[dict] = None, best: bool = True, acceptratio: float = 1,
+                acceptfactor: float = np.inf, nanaction: str = "zeroed", normalizevector=None, **kw):
+    """`execute_run(X, nk, nNMF; ...)` NMFkExecute.jl:483-711 -> (Wa, Ha, phi, minsilhouette, aic).
+    clusterWmatrix selects the stack that is clustered (:620-624) and is NOT forwarded to the restarts (:516-540).
+    best=False returns the per-cluster means of `finalize` (:637, :646-650) instead of the best restart;
+    acceptratio / acceptfactor / nanaction filter the solutions that reach clustersolutions (:551-597).
+    `seed`: restart i draws from Philox(key=seed+i) (the `seed=kwseed+i` of :536); Winit / Hinit (one matrix for all restarts,
+    independently, like the reference) or `inits=(Winit (R,n,k), Hinit (R,k,m))` inject explicit initialisations.
+    details (dict) receives the fields of the "-all" result file (:650-654)."""
     import math
-    n, m, dt = ctx.n, ctx.m, ctx.np_dtype
-    b = ctx.batch(nk, nNMF)
-    try:
-        if inits is not None:
-            b.set_init(np.asarray(inits[0], dtype=dt), np.asarray(inits[1], dtype=dt))
-        else:
-            b.init_random(seed0)
-        ctx.solve([b], p)
-        cl = b.cluster(clusterWmatrix)
-        st = b.cluster_means(cl["order"], cl["labels"])
-        tot = int(b.get(factors=False)["iters"].sum())
-    finally:
-        b.close()
-    Wa, Ha = np.asfortranarray(st["W"]), np.asfortranarray(st["H"])
-    phi = ctx.fit(Wa, Ha)
-    nobs = int(np.sum(~np.isnan(np.asarray(X))))
-    aic = 2 * (Wa.size + Ha.size) + nobs * math.log(phi / nobs) if phi > 0 else -math.inf
-    if details is not None:
-        details.update(total_iters=tot, solve_ms=ctx.last_solve_ms)
-    return Wa, Ha, dt(phi), dt(cl["robustness"]), aic
-
-
-def execute_run(X, nk: int, nNMF: int, *, clusterWmatrix: bool = False, seed: Optional[int] = None, inits=None,
-                ctx: Context = None, details: Optional[dict] = None, best: bool = True, **kw):
-    """`execute_run(X, nk, nNMF; ...)` NMFkExecute.jl:483-711 (defaults acceptratio=1,
-    acceptfactor=Inf, nanaction=:zeroed, best=true) -> (Wa, Ha, phi, minsilhouette, aic).
-    best=False returns the per-cluster means of `finalize` instead of the best restart (nk > 1).
-    `seed`: restart i draws from Philox(key=seed+i) (the `seed=kwseed+i` of :536);
-    `inits=(Winit (R,n,k), Hinit (R,k,m))` injects explicit initialisations."""
     own = ctx is None
     ctx = ctx or Context()
     try:
-        ctx.set_X(X, kw.pop("lam", 1e-32))
-        modify = not ("Wfixed" in kw or "Hfixed" in kw)
-        p = _params_from_kw(kw, normalize=(2 if clusterWmatrix else 1) if modify else 0)
+        ctx.set_X(X, kw.pop("lam", 1e-32), normalizevector)
+        modify = not ("Wfixed" in kw or "Hfixed" in kw)  # :486-489
+        p = _params_from_kw(kw, ctx, normalize=1 if modify else 0, clusterWmatrix=int(bool(clusterWmatrix)))
         n, m, dt = ctx.n, ctx.m, ctx.np_dtype
-        Wb = np.empty((nk, n), dtype=dt)
-        Hb = np.empty((m, nk), dtype=dt)
-        phi, rob, aic = C.c_double(), C.c_double(), C.c_double()
-        tot = C.c_int64()
-        Wi = Hi = None
-        if inits is not None:
-            Wi = np.ascontiguousarray(np.transpose(np.asarray(inits[0], dtype=dt), (0, 2, 1)))
-            Hi = np.ascontiguousarray(np.transpose(np.asarray(inits[1], dtype=dt), (0, 2, 1)))
-            assert Wi.shape == (nNMF, nk, n) and Hi.shape == (nNMF, m, nk)
-        seed0 = int(seed) if seed is not None else int(np.random.randint(0, 2 ** 31))
-        if not best:
-            if nk == 1:
-                raise NMFkError(-6, "best=false with nk == 1 is not on the B200 path")
-            return _execute_run_means(ctx, X, nk, nNMF, clusterWmatrix, seed0, inits, p, details)
-        check(ctx._lib.nmfk_execute_run(ctx._h, nk, nNMF, _ptr(Wi), _ptr(Hi), seed0, C.byref(p), _ptr(Wb), _ptr(Hb),
-                                        C.byref(phi), C.byref(rob), C.byref(aic), C.byref(tot)), ctx._h)
-        if details is not None:
-            details.update(total_iters=tot.value, solve_ms=ctx.last_solve_ms)
-        return Wb.T, Hb.T, dt(phi.value), (1 if nk == 1 else dt(rob.value)), aic.value
+        Wi, Hi = _run_inits(ctx, nk, nNMF, inits, Winit, Hinit)
+        seed0 = _seed0(seed)
+        defaults = best and acceptratio >= 1 and acceptfactor == np.inf and nanaction == "zeroed" and details is None
+        if defaults:  # the one-call form
+            Wb = np.empty((nk, n), dtype=dt)
+            Hb = np.empty((m, nk), dtype=dt)
+            phi, rob, aic = C.c_double(), C.c_double(), C.c_double()
+            tot = C.c_int64()
+            Ws = None if Wi is None else np.ascontiguousarray(np.transpose(Wi, (0, 2, 1)))
+            Hs = None if Hi is None else np.ascontiguousarray(np.transpose(Hi, (0, 2, 1)))
+            check(ctx._lib.nmfk_execute_run(ctx._h, nk, nNMF, _ptr(Ws), _ptr(Hs), seed0, C.byref(p), _ptr(Wb), _ptr(Hb),
+                                            C.byref(phi), C.byref(rob), C.byref(aic), C.byref(tot)), ctx._h)
+            return Wb.T, Hb.T, dt(phi.value), (1 if nk == 1 else dt(rob.value)), aic.value
+        # every other keyword combination: the same device calls composed here
+        b = ctx.batch(nk, nNMF)
+        try:
+            b.set_init(Wi, Hi, seed0)
+            ctx.solve([b], p)
+            pre = b.get()  # Wbest / Hbest are copies taken BEFORE the NaN pass and the clustering (:549-550)
+            kept = b.select(acceptratio, acceptfactor, nanaction)
+            if len(kept) == 0:
+                raise NMFkError(-1, "no NMF solutions remain after the acceptance filters")
+            cl = b.cluster(clusterWmatrix)
+            sol = b.get()
+            bi = int(np.argsort(np.asarray(pre["obj_norm"], dtype=dt), kind="stable")[0])
+            Wbest, Hbest = np.array(pre["W"][bi], order="F"), np.array(pre["H"][bi], order="F")
+            rob = 1
+            st = None
+            if nk > 1:
+                ci = cl["labels"][:, 0] - 1  # :631-635 reads the stored (NaN-zeroed, possibly centroid-overwritten) best
+                Wbest, Hbest = np.asfortranarray(sol["W"][bi][:, ci]), np.asfortranarray(sol["H"][bi][ci, :])
+                st = b.cluster_means(cl["order"], cl["labels"])
+                rob = dt(cl["robustness"])
+                Wa, Ha = st["W"], st["H"]
+            else:  # :646-650: finalize(WBig[idxsol], HBig[idxsol]) = the first kept restart (mean over its single column / row)
+                order_full = np.argsort(np.asarray(pre["obj_norm"], dtype=dt), kind="stable")
+                first = int(min(np.flatnonzero(np.isin(order_full, kept))))  # idxsol is a POSITIONAL mask applied to WBig itself
+                Wa, Ha = np.asfortranarray(sol["W"][first]), np.asfortranarray(sol["H"][first])
+            if best:
+                Wa, Ha = Wbest, Hbest
+            phi = ctx.fit(Wa, Ha)
+            nobs = int(np.sum(~np.isnan(np.asarray(X))))
+            aic = 2 * (Wa.size + Ha.size) + nobs * math.log(phi / nobs) if phi > 0 else -math.inf
+            if details is not None:
+                details.update(W=sol["W"], H=sol["H"], fit=np.asarray(pre["obj_norm"], dtype=dt), order=cl["order"],
+                               labels=cl["labels"] if nk > 1 else None, clustersil=cl["clustersil"] if nk > 1 else None,
+                               centroids=cl["centroids"], Wmean=None if st is None else st["W"], Hmean=None if st is None else st["H"],
+                               Wvar=None if st is None else st["Wvar"], Hvar=None if st is None else st["Hvar"], Wbest=Wbest,
+                               Hbest=Hbest, iters=pre["iters"], total_iters=int(pre["iters"].sum()), solve_ms=ctx.last_solve_ms)
+            return np.asfortranarray(Wa), np.asfortranarray(Ha), dt(phi), rob, aic
+        finally:
+            b.close()
     finally:
         if own:
             ctx.close()
 
 
-def execute(X, nkrange, nNMF: int = 10, *, cutoff: float = 0.5, seed: Optional[int] = None, inits=None,
-            ctx: Context = None, details: Optional[dict] = None, **kw):
+def execute_k(X, nk: int, nNMF: int = 10, *, ordersignals: bool = True, **kw):
+    """`NMFk.execute(X, nk::Integer, nNMF; ...)` NMFkExecute.jl:236-329 without the file cache (see nmfk_b200.cache for it):
+    -> (W[:, so], H[so, :], fitquality, robustness, aic)."""
+    if np.size(X) == 0:
+        raise NMFkError(-7, "Input array has a zero dimension!")  # :242-244
+    if "Wfixed" in kw or "Hfixed" in kw:  # :305-307
+        ordersignals = False
+    W, H, fit, rob, aic = execute_run(X, nk, nNMF, **kw)
+    so = signalorder(W, H) if ordersignals else np.arange(W.shape[1])  # :311-318
+    return np.asfortranarray(W[:, so]), np.asfortranarray(H[so, :]), fit, rob, aic
+
+
+def execute(X, nkrange, nNMF: int = 10, *, cutoff: float = 0.5, seed: Optional[int] = None, inits=None, Winit=None, Hinit=None,
+            clusterWmatrix: bool = False, normalizevector=None, ctx: Context = None, details: Optional[dict] = None, **kw):
     """`NMFk.execute(X, nkrange, nNMF; cutoff=0.5, method=:simple, ...)` NMFkExecute.jl:178-233 without
     the JLD cache -> (W, H, fitquality, robustness, aic, kopt).  W, H are dicts keyed by k (the
     reference's Vector indexed by k); fitquality/robustness/aic have length maximum(nkrange) with
     fitquality[1]=Inf, robustness[1]=-1 (:200-201); kopt is k, 0 or None (`nothing`).
-    All k of the range are solved concurrently on the device."""
+    All k of the range are solved concurrently on the device.  `inits[k] = (Winit (R,n,k), Hinit (R,k,m))` injects per-restart
+    initial factors (either entry may be None)."""
     if isinstance(nkrange, (int, np.integer)):
-        raise TypeError("use execute_k / execute_run for a single k")
+        return execute_k(X, int(nkrange), nNMF, seed=seed, inits=inits, Winit=Winit, Hinit=Hinit, clusterWmatrix=clusterWmatrix,
+                         normalizevector=normalizevector, ctx=ctx, **kw)
     ks = [int(k) for k in nkrange]
+    if (Winit is not None or Hinit is not None) and len(ks) > 1:
+        raise NMFkError(-4, "Winit / Hinit fix one k: size(Winit) == (n, k) (NMFkMultiplicative.jl:40,50)")
     own = ctx is None
     ctx = ctx or Context()
     try:
-        ctx.set_X(X, kw.pop("lam", 1e-32))
+        ctx.set_X(X, kw.pop("lam", 1e-32), normalizevector)
         modify = not ("Wfixed" in kw or "Hfixed" in kw)
-        p = _params_from_kw(kw, normalize=(2 if kw.pop("clusterWmatrix", False) else 1) if modify else 0)
+        p = _params_from_kw(kw, ctx, normalize=1 if modify else 0, clusterWmatrix=int(bool(clusterWmatrix)))
         n, m, dt = ctx.n, ctx.m, ctx.np_dtype
         nks = len(ks)
         Wo = [np.empty((k, n), dtype=dt) for k in ks]
@@ -402,20 +495,20 @@ def execute(X, nkrange, nNMF: int = 10, *, cutoff: float = 0.5, seed: Optional[i
         Hop = (C.c_void_p * nks)(*[h.ctypes.data for h in Ho])
         Wi_keep, Hi_keep = [], []
         Wip = Hip = None
-        if inits is not None:  # inits[k] = (Winit (R,n,k), Hinit (R,k,m))
+        if inits is not None or Winit is not None or Hinit is not None:
             for k in ks:
-                Wi_keep.append(np.ascontiguousarray(np.transpose(np.asarray(inits[k][0], dtype=dt), (0, 2, 1))))
-                Hi_keep.append(np.ascontiguousarray(np.transpose(np.asarray(inits[k][1], dtype=dt), (0, 2, 1))))
-            Wip = (C.c_void_p * nks)(*[w.ctypes.data for w in Wi_keep])
-            Hip = (C.c_void_p * nks)(*[h.ctypes.data for h in Hi_keep])
+                Wi, Hi = _run_inits(ctx, k, nNMF, None if inits is None else inits[k], Winit, Hinit)
+                Wi_keep.append(None if Wi is None else np.ascontiguousarray(np.transpose(Wi, (0, 2, 1))))
+                Hi_keep.append(None if Hi is None else np.ascontiguousarray(np.transpose(Hi, (0, 2, 1))))
+            Wip = (C.c_void_p * nks)(*[None if w is None else w.ctypes.data for w in Wi_keep])
+            Hip = (C.c_void_p * nks)(*[None if h is None else h.ctypes.data for h in Hi_keep])
         fit = np.empty(nks)
         rob = np.empty(nks)
         aic = np.empty(nks)
         kopt = C.c_int32()
         tot = C.c_int64()
         karr = np.asarray(ks, dtype=np.int32)
-        seed0 = int(seed) if seed is not None else int(np.random.randint(0, 2 ** 31))
-        check(ctx._lib.nmfk_execute(ctx._h, karr.ctypes.data_as(_lib._pi32), nks, nNMF, Wip, Hip, seed0, C.byref(p),
+        check(ctx._lib.nmfk_execute(ctx._h, karr.ctypes.data_as(_lib._pi32), nks, nNMF, Wip, Hip, _seed0(seed), C.byref(p),
                                     cutoff, Wop, Hop, fit.ctypes.data_as(_lib._pdbl), rob.ctypes.data_as(_lib._pdbl),
                                     aic.ctypes.data_as(_lib._pdbl), C.byref(kopt), C.byref(tot)), ctx._h)
         maxk = max(ks)
@@ -467,7 +560,7 @@ def trace(X, k: int, Winit, Hinit, niter: int, *, ctx: Context = None, **kw):
     ctx = ctx or Context()
     try:
         ctx.set_X(X, kw.pop("lam", 1e-32))
-        p = _params_from_kw(kw, normalize=0, maxiter=kw.pop("maxiter", 1000000))
+        p = _params_from_kw(kw, ctx, normalize=0, maxiter=kw.pop("maxiter", 1000000))
         n, m, dt = ctx.n, ctx.m, ctx.np_dtype
         Wi, Hi = _f(Winit, dt), _f(Hinit, dt)
         assert Wi.shape == (n, k) and Hi.shape == (k, m)

@@ -4,13 +4,16 @@
 The reference farms restarts out with `Distributed.pmap` (NMFkExecute.jl:511-526) and gathers the
 (W, H, objvalue) tuples by value.  Here every rank solves its own restarts for every k (X is
 replicated: it is small next to the factor stacks), then only what the robustness analysis needs
-crosses NVLink: the H stacks (k x m per restart), objectives and iteration counts are
-all-gathered, the clustering + silhouettes of the R_total = world * R_local solutions of a given k
-run on the rank that owns that k (k index mod world), and the best restart's W (n x k) is
-broadcast from the rank that solved it.  There is no collective inside the iteration loop.
+crosses NVLink: the H stacks (k x m per restart) and the restart states are all-gathered, the
+clustering + silhouettes of the R_total = world * R_local solutions of a given k run on the rank
+that owns that k (k index mod world), and the best restart's W (n x k) is broadcast from the rank
+that solved it.  There is no collective inside the iteration loop.  All of this lives behind the
+C ABI (nmfk_sweep, library-owned NCCL communicator); torch.distributed only carries the 128-byte
+NCCL id.
 
-The helpers that do not touch the device (`owner_of`, `global_index`, `gather_solutions`,
-`merge_sweep`) are covered by world_size-2 gloo tests on CPU (tests/test_dist_cpu.py)."""
+The helpers that do not touch the device (`row_block`, `owner_of`, `global_index`, `split_global`,
+`gather_solutions`, `merge_sweep`) are covered by world_size-2 gloo tests on CPU
+(tests/test_dist_cpu.py)."""
 from __future__ import annotations
 
 import math
@@ -120,146 +123,58 @@ def merge_sweep(ks: Sequence[int], per_k: Dict[int, dict], cutoff: float = 0.5):
     return fit, rob, aicv, kopt
 
 
-class _DevPtr:
-    """Zero-copy view of library-owned device memory for torch (via __cuda_array_interface__)."""
-
-    def __init__(self, ptr: int, shape, typestr: str):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
-                                         "version": 2, "strides": None}
-
-
-def _h_stack_tensor(batch, ctx):
+def sweep_comm_init(ctx, rank: int, world: int, group=None):
+    """The library's own NCCL communicator for the restart-sharded sweep (nmfk_ctx_sweep_comm_init): the 128-byte id is made on
+    rank 0 and broadcast with torch.distributed (any backend) - the only thing the side channel carries."""
+    if getattr(ctx, "_sweep_world", None) == world:
+        return
+    uid = exchange_unique_id(rank, group) if world > 1 else None
     import ctypes as C
-    import torch
-
-    W, H = C.c_void_p(), C.c_void_p()
-    check(ctx._lib.nmfk_batch_device_ptrs(batch._h, C.byref(W), C.byref(H)), ctx._h)
-    ts = "<f8" if ctx.np_dtype == np.float64 else "<f4"
-    return torch.as_tensor(_DevPtr(H.value, (batch.R, ctx.m, batch.k), ts), device="cuda"), W.value
+    buf = C.create_string_buffer(bytes(uid), 128) if uid is not None else None
+    check(ctx._lib.nmfk_ctx_sweep_comm_init(ctx._h, int(world), int(rank), buf), ctx._h)
+    ctx._sweep_world = world
 
 
 def execute_sharded(ctx, X, ks: Sequence[int], R_local: int, *, inits=None, seed0: Optional[int] = None,
                     stack_layout: bool = False, rank: int = 0, world: int = 1, cutoff: float = 0.5, params=None):
-    """execute(X, ks, nNMF = world * R_local) with the restarts sharded over `world` ranks.
+    """execute(X, ks, nNMF = world * R_local) with the restarts sharded over `world` ranks (one process per GPU): a thin
+    binding of nmfk_sweep - solve, NCCL exchange (the library's own communicator), owner-side clustering and the selection
+    of kopt all happen behind the C ABI, exactly as a Julia host would reach them with `ccall`.
 
-    inits[k] = (Winit, Hinit) for THIS rank's restarts ((R,n,k)/(R,k,m), or with stack_layout=True
-    already (R,k,n)/(R,m,k) C-contiguous == column-major stacks); otherwise device Philox streams
-    seeded seed0 + rank*R_local + i.  Returns a dict; on world == 1 this is exactly nmfk_execute."""
-    ks = [int(k) for k in ks]
-    if world == 1:
-        import ctypes as C
-        from . import _lib
-        ctx.set_X(X)
-        p = params or api.default_params()
-        n, m, dt = ctx.n, ctx.m, ctx.np_dtype
-        nks = len(ks)
-        Wo = [np.empty((k, n), dtype=dt) for k in ks]
-        Ho = [np.empty((m, k), dtype=dt) for k in ks]
-        Wop = (C.c_void_p * nks)(*[w.ctypes.data for w in Wo])
-        Hop = (C.c_void_p * nks)(*[h.ctypes.data for h in Ho])
-        Wip = Hip = None
-        keep = []
-        if inits is not None:
-            for k in ks:
-                Wi, Hi = inits[k]
-                if not stack_layout:
-                    Wi = np.ascontiguousarray(np.transpose(np.asarray(Wi, dtype=dt), (0, 2, 1)))
-                    Hi = np.ascontiguousarray(np.transpose(np.asarray(Hi, dtype=dt), (0, 2, 1)))
-                keep.append((Wi, Hi))
-            Wip = (C.c_void_p * nks)(*[w.ctypes.data for w, _ in keep])
-            Hip = (C.c_void_p * nks)(*[h.ctypes.data for _, h in keep])
-        fit, rob, aicv = np.empty(nks), np.empty(nks), np.empty(nks)
-        kopt, tot = C.c_int32(), C.c_int64()
-        karr = np.asarray(ks, dtype=np.int32)
-        check(ctx._lib.nmfk_execute(ctx._h, karr.ctypes.data_as(_lib._pi32), nks, R_local, Wip, Hip,
-                                    int(seed0 or 0), C.byref(p), cutoff, Wop, Hop, fit.ctypes.data_as(_lib._pdbl),
-                                    rob.ctypes.data_as(_lib._pdbl), aicv.ctypes.data_as(_lib._pdbl), C.byref(kopt),
-                                    C.byref(tot)), ctx._h)
-        d2h = sum(w.nbytes + h.nbytes for w, h in zip(Wo, Ho)) + 3 * 8 * nks + 12
-        return dict(W={k: w.T for k, w in zip(ks, Wo)}, H={k: h.T for k, h in zip(ks, Ho)}, fit=fit, robustness=rob,
-                    aic=aicv, kopt=(None if kopt.value < 0 else kopt.value), total_iters_local=int(tot.value),
-                    d2h_bytes=d2h)
-
+    inits[k] = (Winit, Hinit) for THIS rank's restarts ((R,n,k)/(R,k,m), or with stack_layout=True already (R,k,n)/(R,m,k)
+    C-contiguous == column-major stacks; either may be None); otherwise device Philox streams keyed seed0 + global restart
+    number.  Every rank returns the same dict (W, H by k, fit, robustness, aic, kopt, total_iters, total_iters_local)."""
     import ctypes as C
-    import torch
-    import torch.distributed as td
+    from . import _lib
 
-    xi = ctx.set_X(X)
+    ks = [int(k) for k in ks]
+    ctx.set_X(X)
+    sweep_comm_init(ctx, rank, world)
     p = params or api.default_params()
     n, m, dt = ctx.n, ctx.m, ctx.np_dtype
-    batches = []
-    for k in ks:
-        b = ctx.batch(k, R_local)
-        if inits is not None:
+    nks = len(ks)
+    Wo = [np.empty((k, n), dtype=dt) for k in ks]
+    Ho = [np.empty((m, k), dtype=dt) for k in ks]
+    Wop = (C.c_void_p * nks)(*[w.ctypes.data for w in Wo])
+    Hop = (C.c_void_p * nks)(*[h.ctypes.data for h in Ho])
+    Wip = Hip = None
+    keep = []
+    if inits is not None:
+        for k in ks:
             Wi, Hi = inits[k]
-            if stack_layout:
-                check(ctx._lib.nmfk_batch_set_init(b._h, Wi.ctypes.data_as(C.c_void_p), Hi.ctypes.data_as(C.c_void_p)),
-                      ctx._h)
-            else:
-                b.set_init(Wi, Hi)
-        else:
-            b.init_random(int(seed0 or 0) + rank * R_local)
-        batches.append(b)
-    ctx.solve(batches, p)
-    per_k, d2h, tot_local = {}, 0, 0
-    R_total = world * R_local
-    for i, (k, b) in enumerate(zip(ks, batches)):
-        st = b.get(factors=False)
-        tot_local += int(st["iters"].sum())
-        Hdev, Wptr = _h_stack_tensor(b, ctx)
-        obj = torch.from_numpy(st["obj_norm"]).cuda()
-        its = torch.from_numpy(st["iters"]).cuda()
-        Hall, oall, iall = gather_solutions(Hdev, obj, its)  # NCCL over NVLink
-        own = owner_of(i, world)
-        best = torch.zeros(2, dtype=torch.int64, device="cuda")
-        res = None
-        if rank == own:
-            hb = C.c_void_p()
-            check(ctx._lib.nmfk_batch_create_hstack(ctx._h, k, R_total, C.byref(hb)), ctx._h)
-            oh = oall.cpu().numpy()
-            ih = iall.cpu().numpy().astype(np.int32)
-            Hc = Hall.contiguous()
-            check(ctx._lib.nmfk_batch_import(hb, None, C.c_void_p(Hc.data_ptr()), oh.ctypes.data_as(C.POINTER(C.c_double)),
-                                             ih.ctypes.data_as(C.POINTER(C.c_int32)), 1), ctx._h)
-            hbatch = api.Batch.__new__(api.Batch)
-            hbatch.ctx, hbatch.k, hbatch.R, hbatch._h = ctx, k, R_total, hb
-            cl = hbatch.cluster()
-            g = int(cl["order"][0])
-            br, bl = split_global(g, R_local)
-            best[0], best[1] = br, bl
-            Hbest = Hall[g].cpu().numpy()  # (m, k)
-            res = dict(robustness=(1.0 if k == 1 else cl["robustness"]), labels1=cl["labels"][:, 0].copy(), Hbest=Hbest)
-            hbatch.close()
-        td.broadcast(best, src=own)
-        br, bl = int(best[0]), int(best[1])
-        # the best restart's W travels from the rank that solved it to the owner of k
-        Wbest = torch.empty((k, n), dtype=torch.float64 if dt == np.float64 else torch.float32, device="cuda")
-        if rank == br:
-            ts = "<f8" if dt == np.float64 else "<f4"
-            Wstack = torch.as_tensor(_DevPtr(Wptr, (R_local, k, n), ts), device="cuda")
-            Wbest.copy_(Wstack[bl])
-        td.broadcast(Wbest, src=br)
-        if rank == own:
-            Wb = Wbest.cpu().numpy()  # (k, n) == n x k column-major
-            Hb = res["Hbest"]
-            if k > 1:  # Wbest[:, i] = W[:, labels[i,1]]  (NMFkExecute.jl:631-635)
-                ci = res["labels1"] - 1
-                Wb = np.ascontiguousarray(Wb[ci, :])
-                Hb = np.ascontiguousarray(Hb[:, ci])
-            phi = C.c_double()
-            check(ctx._lib.nmfk_fit(ctx._h, k, Wb.ctypes.data_as(C.c_void_p), Hb.ctypes.data_as(C.c_void_p),
-                                    C.byref(phi)), ctx._h)
-            so = api.signalorder(Wb.T, Hb.T)
-            per_k[k] = dict(fit=phi.value, robustness=res["robustness"], aic=aic(n, m, k, xi.nnan, phi.value),
-                            W=Wb.T[:, so], H=Hb.T[so, :])
-            d2h += Wb.nbytes + Hb.nbytes + 24
-        b.close()
-    # small per-k scalars to every rank for the selection of kopt
-    gathered = [None] * world
-    td.all_gather_object(gathered, {k: {q: v[q] for q in ("fit", "robustness", "aic")} for k, v in per_k.items()})
-    allk = {}
-    for g in gathered:
-        allk.update(g)
-    fit, rob, aicv, kopt = merge_sweep(ks, allk, cutoff)
-    return dict(W={k: v["W"] for k, v in per_k.items()}, H={k: v["H"] for k, v in per_k.items()}, fit=fit,
-                robustness=rob, aic=aicv, kopt=kopt, total_iters_local=tot_local, d2h_bytes=d2h)
+            if not stack_layout:
+                Wi = None if Wi is None else np.ascontiguousarray(np.transpose(np.asarray(Wi, dtype=dt), (0, 2, 1)))
+                Hi = None if Hi is None else np.ascontiguousarray(np.transpose(np.asarray(Hi, dtype=dt), (0, 2, 1)))
+            keep.append((Wi, Hi))
+        Wip = (C.c_void_p * nks)(*[None if w is None else w.ctypes.data for w, _ in keep])
+        Hip = (C.c_void_p * nks)(*[None if h is None else h.ctypes.data for _, h in keep])
+    fit, rob, aicv = np.empty(nks), np.empty(nks), np.empty(nks)
+    kopt, tot, tot_local = C.c_int32(), C.c_int64(), C.c_int64()
+    karr = np.asarray(ks, dtype=np.int32)
+    check(ctx._lib.nmfk_sweep(ctx._h, karr.ctypes.data_as(_lib._pi32), nks, R_local, Wip, Hip, int(seed0 or 0), C.byref(p),
+                              cutoff, Wop, Hop, fit.ctypes.data_as(_lib._pdbl), rob.ctypes.data_as(_lib._pdbl),
+                              aicv.ctypes.data_as(_lib._pdbl), C.byref(kopt), C.byref(tot), C.byref(tot_local)), ctx._h)
+    d2h = sum(w.nbytes + h.nbytes for w, h in zip(Wo, Ho)) + 3 * 8 * nks + 12
+    return dict(W={k: w.T for k, w in zip(ks, Wo)}, H={k: h.T for k, h in zip(ks, Ho)}, fit=fit, robustness=rob,
+                aic=aicv, kopt=(None if kopt.value < 0 else kopt.value), total_iters=int(tot.value),
+                total_iters_local=int(tot_local.value), d2h_bytes=d2h)

@@ -84,6 +84,20 @@ def nmf_preprocessing(X: np.ndarray, lam: float = 1e-32):
     return inan, izero
 
 
+def _julia_weight(weight, n: int, m: int):
+    """`(X - W*H) .* weight` under Julia's broadcasting: a Vector of length n is an n x 1 column (one weight per ROW),
+    a 1 x m matrix weights the columns, an n x m matrix weights entries (the shapes execute_run asserts,
+    src/NMFkExecute.jl:484).  NumPy would broadcast a 1-D array along the last axis, hence this helper."""
+    if np.isscalar(weight):
+        return weight
+    w = np.asarray(weight)
+    if w.ndim == 1:
+        assert w.shape[0] == n, "length(weight) == size(X, 1)"
+        return w.reshape(n, 1)
+    assert w.shape in ((n, 1), (1, m), (n, m))
+    return w
+
+
 def _canon_partition(index: np.ndarray) -> np.ndarray:
     """Canonical form of the co-clustering matrix `cons` (NMFkMultiplicative.jl:105):
     cons[i,j] = (index[i]==index[j]) is determined by, for every column, the first column
@@ -127,6 +141,7 @@ def nmf_multiplicative(
     """
     inan, izero = nmf_preprocessing(X, lam)  # :25
     n, m = X.shape
+    weight = _julia_weight(weight, n, m)
     if normalizevector is not None and len(normalizevector) == n:  # :27-31
         X /= np.asarray(normalizevector).reshape(n, 1)
     elif normalizevector is not None and len(normalizevector) != 0:
@@ -216,6 +231,59 @@ def nmf_multiplicative(
     objvalue = float(np.sum((((X - W @ H) * weight)[~inan]) ** 2))  # :125
     if info is not None:
         info.update(iters=iters, stop_reason=stop_reason, baditers=baditers, reattempts=reattempts)
+    return W, H, objvalue
+
+
+def nmf_multiplicative_darray(
+    X: np.ndarray,
+    k: int,
+    *,
+    tol: float = 1e-19,
+    lam: float = 1e-32,
+    maxiter: int = 1000000,
+    stopconv: int = 10000,
+    Winit: Optional[np.ndarray] = None,
+    Hinit: Optional[np.ndarray] = None,
+    rng: Optional[np.random.Generator] = None,
+    info: Optional[dict] = None,
+):
+    """`NMFmultiplicative(X::DArray, k)` src/NMFkMultiplicative.jl:129-197: the same two updates on distributed arrays, but NO
+    tolOF / baditers / reattempts logic, no weight, no NaN imputation; the loop ends on objvalue < tol (:170-173), on
+    inc > stopconv (default 10000, :186-189) or after maxiter iterations.  The distribution itself (collect / distribute of
+    the k-vectors and of H', :160-167) does not change the arithmetic, so this is a dense restatement."""
+    inan, izero = nmf_preprocessing(X, lam)  # :130
+    n, m = X.shape
+    if rng is None:
+        rng = np.random.default_rng()
+    W = rng.random(n * k).reshape((n, k), order="F") if Winit is None or Winit.size == 0 else Winit  # :136-144
+    H = rng.random(k * m).reshape((k, m), order="F") if Hinit is None or Hinit.size == 0 else Hinit  # :146-154
+    if np.isnan(W).any():
+        raise ValueError("Initial values for the W matrix entries include NaNs!")
+    if np.isnan(H).any():
+        raise ValueError("Initial values for the H matrix entries include NaNs!")
+    consold, inc, iters, stop_reason = None, 0, 0, "maxiter"
+    for i in range(1, maxiter + 1):  # :159
+        iters = i
+        H = H * (W.T @ (X / (W @ H))) / np.sum(W, axis=0).reshape(k, 1)  # :160-162
+        W = W * ((X / (W @ H)) @ H.T) / np.sum(H, axis=1).reshape(1, k)  # :163-167
+        if i % 10 == 0:  # :168
+            objvalue = float(np.sum((X - W @ H) ** 2))  # :169
+            if objvalue < tol:  # :170-173
+                stop_reason = "tol"
+                break
+            H = np.maximum(H, EPS64)  # :174
+            W = np.maximum(W, EPS64)  # :175
+            cons = _canon_partition(np.argmin(H, axis=0))  # :176-179
+            inc = inc + 1 if (consold is not None and np.array_equal(cons, consold)) else 0  # :180-185
+            if inc > stopconv:  # :186-189
+                stop_reason = "consistency"
+                break
+            consold = cons  # :190
+    X[izero] = 0  # :193
+    X[inan] = np.nan  # :194
+    objvalue = float(np.sum((X - W @ H) ** 2))  # :195
+    if info is not None:
+        info.update(iters=iters, stop_reason=stop_reason)
     return W, H, objvalue
 
 
@@ -329,9 +397,11 @@ def clustersolutions(factors: Sequence[np.ndarray], clusterWmatrix: bool = False
     """`clustersolutions(factors, clusterWmatrix=false)` src/NMFkCluster.jl:425-517.
     Returns (labels k x R, 1-based; centroids)."""
     if not clusterWmatrix:
-        factors = [np.array(f.T, copy=True) for f in factors]  # :427
+        factors = [np.array(f.T, copy=True) for f in factors]  # :427 permutedims makes copies
     else:
-        factors = [np.array(f, copy=True) for f in factors]
+        # NO copy on this branch (:426-428): factors[1] below IS the caller's best W, which the running-sum
+        # centroids then overwrite in place (:453-455, :484, :512) - execute_run reads it afterwards (:631-637)
+        factors = list(factors)
     numTrials = len(factors)
     r, k = factors[0].shape
     for w in factors:
@@ -364,8 +434,8 @@ def clustersolutions(factors: Sequence[np.ndarray], clusterWmatrix: bool = False
             labels[:, trial] = np.arange(1, k + 1)
         else:
             labels[idx, trial] = idx + 1
-    cent = cent / numTrials  # :512
-    return labels, cent.T  # :516
+    cent /= numTrials  # :512 `newClusterCenters ./= numTrials` (in place: the aliased best W ends up holding the centroids)
+    return labels, cent.T.copy()  # :516
 
 
 # --------------------------------------------------------------------------------------
@@ -457,11 +527,14 @@ def execute_run(
     init_fn: Optional[Callable[[int, int, int, int], tuple]] = None,
     details: Optional[dict] = None,
     best: bool = True,
+    acceptratio: float = 1,
+    acceptfactor: float = np.inf,
+    nanaction: str = "zeroed",
     **kw,
 ):
-    """`execute_run(X::AbstractMatrix, nk, nNMF; ...)` src/NMFkExecute.jl:483-711 with the
-    defaults acceptratio=1, acceptfactor=Inf, nanaction=:zeroed, serial; best=false returns the
-    per-cluster means of finalize (:637, :655-658) instead of the best restart (nk > 1 only).
+    """`execute_run(X::AbstractMatrix, nk, nNMF; ...)` src/NMFkExecute.jl:483-711 (serial branch); best=false returns
+    the per-cluster means of finalize (:637, :655-658) instead of the best restart; acceptratio / acceptfactor /
+    nanaction filter the solutions that reach clustersolutions / finalize (:551-597).
 
     Initialisations: the reference draws from Julia's RNG (seed+i per restart when `seed` is
     given, :532-537).  Here `inits[i] = (Winit, Hinit)` or `init_fn(i, n, nk, m)` (i is the
@@ -480,37 +553,56 @@ def execute_run(
         elif seed is not None:
             kwi["rng"] = np.random.Generator(np.random.Philox(key=seed + i))
         inf = {}
-        W, H, of = execute_singlerun_compute(X, nk, modifymatrices=modifymatrices, clusterWmatrix=clusterWmatrix,
-                                             weight=weight, info=inf, **kwi)
-        WBig.append(np.asarray(W, dtype=T))  # stored into Vector{Matrix{T}}, :529-536
-        HBig.append(np.asarray(H, dtype=T))
+        # clusterWmatrix is a named keyword of execute_run and is NOT forwarded (:516-540): every restart is normalised
+        # with the default branch (rows of H sum to one, :800-804)
+        W, H, of = execute_singlerun_compute(X, nk, modifymatrices=modifymatrices, weight=weight, info=inf, **kwi)
+        WBig.append(np.array(W, dtype=T))  # stored into Vector{Matrix{T}}, :529-536
+        HBig.append(np.array(H, dtype=T))
         objvalue[i - 1] = of
         iters.append(inf.get("iters", 0))
     idxsort = np.argsort(objvalue, kind="stable")  # :545 sortperm
     bestIdx = int(idxsort[0])
-    Wbest = WBig[bestIdx].copy()
+    Wbest = WBig[bestIdx].copy()  # :549-550
     Hbest = HBig[bestIdx].copy()
-    for i in idxsort:  # nanaction == :zeroed, :566-580
-        WBig[i][np.isnan(WBig[i])] = 0
-        HBig[i][np.isnan(HBig[i])] = 0
+    if acceptratio < 1:  # :552-558
+        ccc = int(math.ceil(nNMF * acceptratio))
+        idxrat = np.array([True] * ccc + [False] * (nNMF - ccc))
+    else:
+        idxrat = np.ones(nNMF, dtype=bool)
+    if acceptfactor < np.inf:  # :559-565
+        idxcut = objvalue[idxsort] < objvalue[bestIdx] * acceptfactor
+    else:
+        idxcut = np.ones(nNMF, dtype=bool)
+    idxnan = np.ones(nNMF, dtype=bool)
+    if nanaction == "zeroed":  # :566-580
+        for i in idxsort:
+            WBig[i][np.isnan(WBig[i])] = 0
+            HBig[i][np.isnan(HBig[i])] = 0
+    elif nanaction == "removed":  # :581-596 (idxnan is indexed by restart NUMBER, the other two by sorted position)
+        for i in idxsort:
+            if np.isnan(WBig[i]).any() or np.isnan(HBig[i]).any():
+                idxnan[i] = False
+    idxsol = idxrat & idxcut & idxnan  # :597
     minsilhouette = 1
     labels = None
     clustersil = None
+    centroids = None
+    Wv = Hv = np.nan
+    Ws = [WBig[i] for i in idxsort[idxsol]]  # WBig[idxsort][idxsol]
+    Hs = [HBig[i] for i in idxsort[idxsol]]
     if nk > 1:  # :618-645
-        Ws = [WBig[i] for i in idxsort]
-        Hs = [HBig[i] for i in idxsort]
         labels, centroids = clustersolutions(Ws if clusterWmatrix else Hs, clusterWmatrix)  # :620-624
         ci = labels[:, 0]
-        for i, c in enumerate(ci):  # :631-635
+        for i, c in enumerate(ci):  # :631-635 (reads WBig[bestIdx] AFTER clustersolutions may have overwritten it)
             Wbest[:, i] = WBig[bestIdx][:, c - 1]
             Hbest[i, :] = HBig[bestIdx][c - 1, :]
-        Wmean, Hmean, clustersil, _, _ = finalize(Ws, Hs, labels, clusterWmatrix)  # :637
+        Wmean, Hmean, clustersil, Wv, Hv = finalize(Ws, Hs, labels, clusterWmatrix)  # :637
         minsilhouette = T.type(np.min(clustersil))  # :638
-    Wa, Ha = Wbest, Hbest  # best == true, :655-658
-    if not best:
-        if nk == 1:
-            raise NotImplementedError("best=false with nk == 1 uses finalize(WBig, HBig) (:648), not restated")
-        Wa, Ha = Wmean, Hmean
+    else:  # :646-650: finalize(WBig[idxsol], HBig[idxsol]) -> mean over the single column / row of the FIRST kept restart
+        keep = [i for i in range(nNMF) if idxsol[i]]
+        Wmean = np.mean(WBig[keep[0]], axis=1, keepdims=True)
+        Hmean = np.mean(HBig[keep[0]], axis=0, keepdims=True)
+    Wa, Ha = (Wbest, Hbest) if best else (Wmean, Hmean)  # :655-658
     E = X - Wa @ Ha  # :664
     E[np.isnan(E)] = 0  # :667
     phi_final = normnan(E)  # :668
@@ -518,9 +610,10 @@ def execute_run(
     numparameters = Wa.size + Ha.size  # :698
     with np.errstate(divide="ignore"):
         aic = 2 * numparameters + numobservations * math.log(phi_final / numobservations) if phi_final > 0 else -math.inf  # :708
-    if details is not None:
-        details.update(objvalue=objvalue, idxsort=idxsort, labels=labels, clustersil=clustersil, iters=np.asarray(iters),
-                       WBig=WBig, HBig=HBig)
+    if details is not None:  # the fields of the "-all" result file (:650-654) and what the tests compare
+        details.update(objvalue=objvalue, idxsort=idxsort, idxsol=idxsol, labels=labels, clustersil=clustersil,
+                       centroids=centroids, iters=np.asarray(iters), WBig=WBig, HBig=HBig, Wmean=Wmean, Hmean=Hmean, Wvar=Wv,
+                       Hvar=Hv, Wbest=Wbest, Hbest=Hbest)
     return Wa, Ha, T.type(phi_final), minsilhouette, aic
 
 

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "missing export " + name
     assert declared == set(_lib.SIGNATURES), "python binding and header disagree"
-    assert lib.nmfk_abi_version() == 1
+    assert lib.nmfk_abi_version() == 2
 
 
 def test_no_gpu_fails_loudly():
