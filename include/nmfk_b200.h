@@ -283,11 +283,17 @@ int32_t nmfk_signalorder(const void* W, const void* H, int64_t n, int32_t k, int
 /* ---- measurement helpers (bench only) --------------------------------------------------- */
 /* kernel launches issued by this ctx since creation (for bench.py's gpu_launches) */
 int64_t nmfk_launch_count(const nmfk_ctx* ctx);
+/* Per-launch device time of the dominant kernels of the tiled engine (the two half-update pass kernels: tc_pass_kernel for
+ * Float32, tiled_dmma_pass_kernel / tiled_pass_kernel for Float64), measured with CUDA events on the launching stream while
+ * nmfk_solve runs: enable (resets the counters), solve, then read the summed duration and the number of launches. */
+int32_t nmfk_profile_enable(nmfk_ctx* ctx, int32_t on);
+int32_t nmfk_profile_get(const nmfk_ctx* ctx, double* pass_ms, int64_t* pass_launches);
 /* device time (ms, CUDA events on the ctx streams) of the last nmfk_solve */
 double nmfk_last_solve_ms(const nmfk_ctx* ctx);
 /* micro-benchmarks that give the roofline denominators MEASURED_PEAKS.json does not hold:
  * which: 0 = FP64 DFMA TFLOP/s, 1 = FP64 DMMA (mma.sync m8n8k4) TFLOP/s, 2 = FP32 FFMA TFLOP/s,
- *        3 = device-to-device copy GB/s (read+write bytes) */
+ *        3 = device-to-device copy GB/s (read+write bytes), 13 = dense tcgen05.mma kind::tf32 TFLOP/s (M = 128, N = 256,
+ *        K = 8 from shared memory on every SM; the 3-term split of the Float32 kernels runs at a third of it) */
 int32_t nmfk_measure_peak(nmfk_ctx* ctx, int32_t which, double* value);
 /* Device self-test of the tcgen05 / tensor-memory building blocks of the Float32 tiled engine (no reference
  * counterpart): U 128x16, V 64x16 row-major; mode bits: 1 P=UV' (A,B shared), 2 P (A tensor memory),

@@ -75,6 +75,7 @@ struct nmfk_ctx {
     bool sharded = false;
     int64_t row0 = 0, n_global = 0;
     // restart-sharded sweep (nmfk_ctx_sweep_comm_init): the library's own communicator over the ranks that share the restarts
+    PassProfile prof;            // nmfk_profile_enable: device time of the tiled engine's pass kernels
     void* sweep_comm = nullptr;  // ncclComm_t
     int sweep_nranks = 1, sweep_rank = 0;
 };
@@ -341,6 +342,7 @@ int32_t nmfk_ctx_destroy(nmfk_ctx* c) {
     cudaDeviceSynchronize();
     nmfk_ctx_comm_destroy(c);
     free_X(c);
+    c->prof.destroy();
     if (c->scratch) cudaFree(c->scratch);
     if (c->d_partials) cudaFree(c->d_partials);
     for (auto s : c->pool) cudaStreamDestroy(s);
@@ -676,6 +678,7 @@ static void fill_args(const nmfk_batch* b, const nmfk_params* p, SolveArgs& a) {
     if (c->Xn) a.normalize = 0;  // the normalizevector epilogue (finish_normalizevector) rescales W first, then normalises
     a.tiled_tc = p->engine != NMFK_ENGINE_TILED_SCALAR;
     a.shard = c->sharded ? &c->shard : nullptr;
+    a.prof = c->prof.enabled ? const_cast<PassProfile*>(&c->prof) : nullptr;
 }
 
 // tiled engine (kl_tiled.cu): host-driven, for factors that do not fit in shared memory
@@ -1516,6 +1519,20 @@ int32_t nmfk_sweep(nmfk_ctx* c, const int32_t* ks, int32_t nks, int32_t R_local,
 }
 
 int64_t nmfk_launch_count(const nmfk_ctx* c) { return c ? c->launches : 0; }
+
+int32_t nmfk_profile_enable(nmfk_ctx* c, int32_t on) {
+    if (!c) return fail(nullptr, NMFK_E_INVALID, "ctx is NULL");
+    c->prof.enabled = on != 0;
+    c->prof.reset();
+    return NMFK_OK;
+}
+
+int32_t nmfk_profile_get(const nmfk_ctx* c, double* pass_ms, int64_t* pass_launches) {
+    if (!c) return fail(nullptr, NMFK_E_INVALID, "ctx is NULL");
+    if (pass_ms) *pass_ms = c->prof.ms;
+    if (pass_launches) *pass_launches = c->prof.launches;
+    return NMFK_OK;
+}
 
 double nmfk_last_solve_ms(const nmfk_ctx* c) { return c ? c->last_solve_ms : 0.0; }
 

@@ -576,15 +576,20 @@ cudaError_t dispatch_tiled_combine(const TiledPassArgs& a, void* red, cudaStream
 // use_td: Float64 without NaN, k >= 4 -> the DMMA kernel of kl_tiled_dmma.cu (a.nblocks counts 128-index blocks, a.D is
 // the step-contiguous copy of the data)
 template <typename TX, typename TC>
-cudaError_t dispatch_tiled_pass(const TiledPassArgs& a, void* red, cudaStream_t s, bool use_tc, int* errflag, bool use_td = false) {
+cudaError_t dispatch_tiled_pass(const TiledPassArgs& a, void* red, cudaStream_t s, bool use_tc, int* errflag, bool use_td = false,
+                                PassProfile* prof = nullptr) {
     const int kt = resident_template_k(a.k);
     if (use_tc) {
+        if (prof) prof->begin(s);
         cudaError_t e = launch_tc_pass(a, errflag, s);
+        if (prof) prof->end(s);
         if (e != cudaSuccess || a.partial == nullptr) return e;
         return dispatch_tiled_combine<TX, TC>(a, red, s);
     }
     if (use_td) {
+        if (prof) prof->begin(s);
         cudaError_t e = launch_tiled_dmma_pass(a, s);
+        if (prof) prof->end(s);
         if (e != cudaSuccess || a.partial == nullptr) return e;
         return dispatch_tiled_combine<TX, TC>(a, red, s);
     }
@@ -785,6 +790,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
                 ++*launches;
                 NMFK_TRY(cudaMemcpyAsync(h_active, d_active, sizeof(int), cudaMemcpyDeviceToHost, s));
                 NMFK_TRY(cudaStreamSynchronize(s));
+                if (a.prof) a.prof->harvest();
                 if (*h_active == 0) break;
                 need_guard = false;
             }
@@ -793,7 +799,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
             if (!a.Hfixed) {
                 tiled_sums_kernel<TC><<<dim3(k, R), 256, 0, s>>>(a.W, (long long)n * k, 1, n, n, a.st, den);
                 NMFK_TRY(cudaGetLastError());
-                NMFK_TRY((dispatch_tiled_pass<TX, TC>(ph, red, s, use_tc, h_active + 1, use_td)));
+                NMFK_TRY((dispatch_tiled_pass<TX, TC>(ph, red, s, use_tc, h_active + 1, use_td, a.prof)));
                 *launches += 2 + (SH > 1 || sharded);
                 if (d_trace != nullptr) {
                     std::vector<long long> ht(3 * 64 * 8);
@@ -817,7 +823,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
             if (!a.Wfixed) {
                 tiled_sums_kernel<TC><<<dim3(k, R), 256, 0, s>>>(a.H, (long long)k * m, k, 1, m, a.st, den);
                 NMFK_TRY(cudaGetLastError());
-                NMFK_TRY((dispatch_tiled_pass<TX, TC>(pw, nullptr, s, use_tc, h_active + 1, use_td)));
+                NMFK_TRY((dispatch_tiled_pass<TX, TC>(pw, nullptr, s, use_tc, h_active + 1, use_td, a.prof)));
                 *launches += 2 + (SW > 1);
             }
             if (a.has_nan) {
@@ -905,6 +911,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
         NMFK_TRY(cudaGetLastError());
         *launches += 2;
         NMFK_TRY(cudaStreamSynchronize(s));
+        if (a.prof) a.prof->harvest();
     }
 done:
     if (h_active && h_active[1] != 0)

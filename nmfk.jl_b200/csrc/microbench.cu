@@ -278,6 +278,7 @@ cudaError_t measure_peak(int which, double* value, cudaStream_t s) {
         *value = flops / (ms * 1e-3) / 1e12;
         return cudaSuccess;
     }
+    if (which == 13) return umma_peak(value, s);  // dense tcgen05.mma kind::tf32 TFLOP/s (tc_selftest.cu)
     return cudaErrorInvalidValue;
 }
 

@@ -3,6 +3,8 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <vector>
+
 #include <cuda_runtime.h>
 
 namespace nmfk {
@@ -50,6 +52,55 @@ __device__ __forceinline__ double weight_at(const WeightRef& w, double scalar, l
     return v;
 }
 
+// Device time of the dominant kernels of the tiled engine (the two half-update passes), measured with CUDA events on the
+// launching stream while a solve runs (bench.py's roofline.achieved): begin/end bracket one launch, harvest() is called after
+// a stream synchronisation.
+struct PassProfile {
+    bool enabled = false;
+    double ms = 0.0;
+    long long launches = 0;
+    std::vector<cudaEvent_t> idle, pending;  // pending holds (start, stop) pairs
+    cudaEvent_t get() {
+        if (!idle.empty()) {
+            cudaEvent_t e = idle.back();
+            idle.pop_back();
+            return e;
+        }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void begin(cudaStream_t s) {
+        if (!enabled) return;
+        cudaEvent_t e = get();
+        cudaEventRecord(e, s);
+        pending.push_back(e);
+    }
+    void end(cudaStream_t s) { begin(s); }
+    void harvest() {
+        for (size_t i = 0; i + 1 < pending.size(); i += 2) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, pending[i], pending[i + 1]) == cudaSuccess) {
+                ms += t;
+                ++launches;
+            }
+            idle.push_back(pending[i]);
+            idle.push_back(pending[i + 1]);
+        }
+        pending.clear();
+    }
+    void reset() {
+        ms = 0.0;
+        launches = 0;
+    }
+    void destroy() {
+        for (auto e : idle) cudaEventDestroy(e);
+        for (auto e : pending) cudaEventDestroy(e);
+        idle.clear();
+        pending.clear();
+    }
+};
+
 // Arguments of one batched KL solve (R restarts at one k).
 struct SolveArgs {
     const void* X;    // n x m column-major, zeros -> lambda, NaN kept
@@ -67,6 +118,7 @@ struct SolveArgs {
     WeightRef wref;          // non-scalar weight (tiled engine with the scalar objective kernel only)
     int32_t tiled_tc;        // tiled engine, Float32 without NaN: 1 = tcgen05 kernel (kl_tiled_tc.cu), 0 = scalar-FMA kernel
     const ShardComm* shard;  // non-null: n is the LOCAL row count, the tiled engine all-reduces the k x m partials
+    PassProfile* prof;       // non-null: time the pass-kernel launches of the tiled engine
 };
 
 // threads per restart-CTA of the resident engine: 512 (<=128 registers) while u/acc fit, 256 beyond
@@ -140,6 +192,8 @@ cudaError_t launch_cluster_means(const void* F, int len, int k, int R, int use_W
 
 // micro-benchmarks
 cudaError_t measure_peak(int which, double* value, cudaStream_t s);
+// dense tcgen05.mma kind::tf32 throughput, TFLOP/s (tc_selftest.cu)
+cudaError_t umma_peak(double* tflops, cudaStream_t s);
 // tcgen05 building-block self-test (tc_selftest.cu)
 cudaError_t umma_timing(const float* U, const float* V, int reps, long long* out8, float* bias, cudaStream_t s);
 cudaError_t umma_selftest(const float* U, const float* V, int mode, float* Pss, float* Pts, float* ACCa, float* ACCb, int* err,

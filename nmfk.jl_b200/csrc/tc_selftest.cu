@@ -277,7 +277,80 @@ __global__ void __launch_bounds__(128) umma_timing_kernel(const float* __restric
     if (warp == 0) tc::tmem_dealloc<512>(tbase);
 }
 
+// Dense tcgen05.mma kind::tf32 throughput (the denominator of the Float32 tensor-core kernels): every SM runs one CTA whose
+// elected thread issues `iters` back-to-back M = 128, N = 256, K = 8 instructions with both operands in shared memory
+// (un-swizzled K-major tiles: 4 KB + 8 KB read per instruction = 96 B/clk, below the shared-memory bandwidth) into two
+// alternating tensor-memory accumulators, then one commit.
+__global__ void __launch_bounds__(128) umma_peak_kernel(int iters, int* errflag) {
+    __shared__ __align__(128) float As[128 * 8];
+    __shared__ __align__(128) float Bs[256 * 8];
+    __shared__ __align__(8) uint64_t bar[1];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < 128 * 8; e += 128) As[e] = 0.f;
+    for (int e = tid; e < 256 * 8; e += 128) Bs[e] = 0.f;
+    if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
+    if (tid == 0) {
+        tc::mbar_init(&bar[0], 1);
+        tc::mbar_fence_init();
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tbase = tmem_slot;
+    if (warp == 0) {
+        const uint32_t id = tc::idesc_tf32(128, 256, 0);
+        const uint64_t da = tc::smem_desc(tc::smem_u32(As), 128, 256), db = tc::smem_desc(tc::smem_u32(Bs), 128, 256);
+        if (tc::elect_one()) {
+            for (int i0 = 0; i0 < iters; i0 += 8) {
+#pragma unroll
+                for (int ii = 0; ii < 8; ++ii) tc::mma_tf32_ss(tbase + ((ii & 1) ? 256 : 0), da, db, id, (i0 | (ii >> 1)) != 0);
+            }
+            tc::mma_commit(&bar[0]);
+        }
+        __syncwarp();
+    }
+    tc::mbar_wait(&bar[0], 0, errflag, 9);
+    tc::tc_fence_after_sync();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<512>(tbase);
+}
+
 }  // namespace
+
+// TFLOP/s of dense tcgen05.mma kind::tf32 (2 * 128 * 256 * 8 flops per instruction) over all SMs, best of 5 launches
+cudaError_t umma_peak(double* tflops, cudaStream_t s) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int* derr = nullptr;
+    cudaError_t e = cudaMalloc(&derr, sizeof(int));
+    if (e != cudaSuccess) return e;
+    cudaMemsetAsync(derr, 0, sizeof(int), s);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 1 << 15;
+    float best = 1e30f;
+    for (int rep = 0; rep < 7 && e == cudaSuccess; ++rep) {
+        cudaEventRecord(e0, s);
+        umma_peak_kernel<<<sms, 128, 0, s>>>(iters, derr);
+        cudaEventRecord(e1, s);
+        e = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep >= 2 && ms < best) best = ms;
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(derr);
+    if (e != cudaSuccess) return e;
+    *tflops = 2.0 * 128.0 * 256.0 * 8.0 * (double)iters * sms / (best * 1e-3) / 1e12;
+    return cudaSuccess;
+}
 
 // U: 128 x 16 row-major, V: 64 x 16 row-major (host); outputs row-major 128 x 64 / 128 x 16 (host)
 cudaError_t umma_selftest(const float* U, const float* V, int mode, float* Pss, float* Pts, float* ACCa, float* ACCb, int* err,

@@ -82,6 +82,8 @@ SIGNATURES = {
     "nmfk_signalorder": (_i32, [_P, _P, _i64, _i32, _i64, _i32, _pi32]),
     "nmfk_launch_count": (_i64, [_P]),
     "nmfk_last_solve_ms": (_dbl, [_P]),
+    "nmfk_profile_enable": (_i32, [_P, _i32]),
+    "nmfk_profile_get": (_i32, [_P, _pdbl, _pi64]),
     "nmfk_measure_peak": (_i32, [_P, _i32, _pdbl]),
     "nmfk_umma_timing": (_i32, [_P, _P, _P, _i32, _P, _P]),
     "nmfk_umma_selftest": (_i32, [_P, _P, _P, _i32, _P, _P, _P, _P, _pi32]),

@@ -118,6 +118,29 @@ class Context:
     def batch(self, k: int, R: int) -> "Batch":
         return Batch(self, k, R)
 
+    def import_solutions(self, H: np.ndarray, obj_norm, W: Optional[np.ndarray] = None, iters=None) -> "Batch":
+        """A batch made of finished solutions (nmfk_batch_create_hstack / nmfk_batch_create + nmfk_batch_import): H (R, k, m),
+        optional W (R, n, k), objective values (NMFkExecute.jl:792) - the input of `Batch.cluster` without a solve, e.g.
+        solutions gathered from other ranks or loaded from a result file."""
+        H = np.asarray(H, dtype=self.np_dtype)
+        R, k, m = H.shape
+        assert m == self.m
+        b = Batch.__new__(Batch)
+        b.ctx, b.k, b.R = self, int(k), int(R)
+        h = C.c_void_p()
+        if W is None:
+            check(self._lib.nmfk_batch_create_hstack(self._h, b.k, b.R, C.byref(h)), self._h)
+        else:
+            check(self._lib.nmfk_batch_create(self._h, b.k, b.R, C.byref(h)), self._h)
+        b._h = h
+        Hs = np.ascontiguousarray(np.transpose(H, (0, 2, 1)))
+        Ws = None if W is None else np.ascontiguousarray(np.transpose(np.asarray(W, dtype=self.np_dtype), (0, 2, 1)))
+        ob = np.ascontiguousarray(obj_norm, dtype=np.float64)
+        it = np.zeros(R, dtype=np.int32) if iters is None else np.ascontiguousarray(iters, dtype=np.int32)
+        check(self._lib.nmfk_batch_import(h, _ptr(Ws), _ptr(Hs), ob.ctypes.data_as(_lib._pdbl), it.ctypes.data_as(_lib._pi32), 0),
+              self._h)
+        return b
+
     def solve(self, batches: Sequence["Batch"], params: Optional[Params] = None):
         """The restart loop of execute_run for all batches at once (NMFkExecute.jl:510-544)."""
         p = params or default_params()
@@ -131,6 +154,16 @@ class Context:
     @property
     def last_solve_ms(self) -> float:
         return float(self._lib.nmfk_last_solve_ms(self._h))
+
+    def profile(self, on: bool = True):
+        """Time the pass-kernel launches of the tiled engine with CUDA events (nmfk_profile_enable; resets the counters)."""
+        check(self._lib.nmfk_profile_enable(self._h, int(on)), self._h)
+
+    def profile_get(self):
+        """-> (summed device ms of the pass-kernel launches, number of launches) since `profile()`."""
+        ms, cnt = C.c_double(), C.c_int64()
+        check(self._lib.nmfk_profile_get(self._h, C.byref(ms), C.byref(cnt)), self._h)
+        return ms.value, cnt.value
 
     def fit(self, W: np.ndarray, H: np.ndarray) -> float:
         """normnan(X - W*H) with NaN residuals zeroed (NMFkExecute.jl:664-668, :212-222) for host factors W (n,k), H (k,m)."""

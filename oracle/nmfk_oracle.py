@@ -543,7 +543,7 @@ def execute_run(
     T = X.dtype
     n, m = X.shape
     modifymatrices = not ("Wfixed" in kw or "Hfixed" in kw)  # :486-489
-    WBig, HBig, objvalue, iters = [], [], np.empty(nNMF, dtype=T), []
+    WBig, HBig, objvalue, iters, stops = [], [], np.empty(nNMF, dtype=T), [], []
     for i in range(1, nNMF + 1):  # :534-542
         kwi = dict(kw)
         if inits is not None:
@@ -560,6 +560,7 @@ def execute_run(
         HBig.append(np.array(H, dtype=T))
         objvalue[i - 1] = of
         iters.append(inf.get("iters", 0))
+        stops.append(inf.get("stop_reason", ""))
     idxsort = np.argsort(objvalue, kind="stable")  # :545 sortperm
     bestIdx = int(idxsort[0])
     Wbest = WBig[bestIdx].copy()  # :549-550
@@ -612,7 +613,7 @@ def execute_run(
         aic = 2 * numparameters + numobservations * math.log(phi_final / numobservations) if phi_final > 0 else -math.inf  # :708
     if details is not None:  # the fields of the "-all" result file (:650-654) and what the tests compare
         details.update(objvalue=objvalue, idxsort=idxsort, idxsol=idxsol, labels=labels, clustersil=clustersil,
-                       centroids=centroids, iters=np.asarray(iters), WBig=WBig, HBig=HBig, Wmean=Wmean, Hmean=Hmean, Wvar=Wv,
+                       centroids=centroids, iters=np.asarray(iters), stop_reasons=stops, WBig=WBig, HBig=HBig, Wmean=Wmean, Hmean=Hmean, Wvar=Wv,
                        Hvar=Hv, Wbest=Wbest, Hbest=Hbest)
     return Wa, Ha, T.type(phi_final), minsilhouette, aic
 

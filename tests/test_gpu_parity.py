@@ -370,6 +370,23 @@ def test_rowsharded_two_gpus_torchrun():
     assert "ROWSHARD OK" in r.stdout
 
 
+def test_restart_sharded_sweep_two_gpus_torchrun():
+    """nmfk_sweep over NCCL on two GPUs against the oracle's execute with nNMF = 2 * R_local (skipped on a one-GPU box; the
+    log of the builder's 2-GPU run is committed under profiles/)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613",
+                        os.path.join(root, "tests", "multigpu", "sweep_ranks.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "SWEEP OK" in r.stdout
+
+
 # ---------------------------------------------------------------------------------------------
 # Float32 tiled engine on the 5th-generation tensor cores (kl_tiled_tc.cu): tcgen05.mma kind::tf32 with the
 # 3-term split, tensor-memory operands, per-unit accumulators drained in FP32.  engine=2 takes this path for
