@@ -1,36 +1,43 @@
 #!/usr/bin/env python3
 """bench.py - NMF restart-iterations/sec of the B200-native NMFk hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config auto|C2|C3|C4|C5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], "C2"): synthetic nonnegative mixture X = W0*H0, 1000 x 200
-Float64 (k0 = 5), NMFk.execute(X, 2:10, 100; method=:simple) with the reference's stop rule
-(maxiter=10000, tolOF=1e-3, ...).  One step = one such execute over one X: 900 restarts
-(9 values of k x 100), all solved concurrently on the device.
-
-value  = restart-iterations / second of the solver phase with X and the initial factors already
-         resident in HBM (device time, CUDA events on the library's launching stream).
-e2e    = the same metric through the public API (nmfk_b200.execute == the C-ABI nmfk_execute)
-         with HOST buffers: X and all initial factors are copied from pinned host memory and
-         the per-k best factors / fit / robustness / aic / kopt are read back inside the timed
-         region, which also contains clustering, silhouettes and selection.
-N > 1  : restarts are sharded (weak scaling: every rank solves 100 restarts per k with its own
-         seeds); H stacks and objectives are all-gathered over NCCL for the clustering of the
-         R = 100*N solutions per k, which is split by k across ranks.
-
---impl reference times the CPU restatement of the reference (oracle/nmfk_oracle.py: NumPy +
-OpenBLAS, the operation sequence of NMFkMultiplicative.jl) on the host cores - Julia itself is
-not installed here or on the GPU box.
+Workloads (BASELINE.json `configs`; synthetic nonnegative mixtures X = W0*H0, seed 2015):
+  N = 1 (default)  C3: 10000 x 10000 Float32, k = 16, nNMF = 64 - the largest single-GPU configuration.  One step = ITERS
+                   iterations of all 64 restarts (fixed iteration budget, every restart active) through the tiled engine
+                   (tcgen05 kind::tf32 3-term split).  X (400 MB) is larger than the 126 MB L2, so every iteration streams it.
+  N > 1            C4: 100000 x 2000 Float64, k = 2:32, nNMF = 256, restarts sharded over the N GPUs (STRONG scaling: 256 / N
+                   restarts of every k per GPU), fixed iteration budget, through nmfk_sweep (library-owned NCCL communicator;
+                   no collective inside the iteration loop, one all-gather of H stacks + states and one W broadcast per k).
+  --config C5      2,000,000 x 1000 Float32, k = 24, nNMF = 32, rows of X sharded over the N GPUs, one NCCL all-reduce of the
+                   k x m x R numerators per iteration.          --config C2: 1000 x 200 Float64, execute(X, 2:10, 100), full stop rule.
+value  = restart-iterations / second of the solver phase with X and the initial factors resident in HBM (device time, CUDA
+         events on the library's launching stream, max over ranks).
+e2e    = the same metric through the public call (C ABI: nmfk_set_X + nmfk_execute_run / nmfk_sweep) with HOST buffers: X and
+         the initial factors are copied from pinned host memory, the best factors / fit / robustness / aic come back, and
+         clustering + silhouettes + selection are inside the timed region.
+--impl reference times the CPU restatement of the reference (oracle/nmfk_oracle.py: NumPy + OpenBLAS with the thread count SET
+below, the literal operation sequence of NMFkMultiplicative.jl) on the SAME configuration; Julia itself is not installed here or
+on the GPU box.  Under torchrun rank 0 alone runs it.
 """
-import argparse
-import json
 import os
-import statistics
-import subprocess
-import sys
-import threading
-import time
+
+# BLAS threads of the CPU arm: set explicitly BEFORE NumPy loads OpenBLAS, identical in both arms, and not left to torchrun's
+# OMP_NUM_THREADS=1 (546 vs 996 restart-iterations/s for the same function inside one run)
+BLAS_THREADS = int(os.environ.get("NMFK_BENCH_BLAS_THREADS", os.cpu_count() or 1))
+os.environ["OPENBLAS_NUM_THREADS"] = str(BLAS_THREADS)
+os.environ["OMP_NUM_THREADS"] = str(BLAS_THREADS)
+os.environ["MKL_NUM_THREADS"] = str(BLAS_THREADS)
+
+import argparse  # noqa: E402
+import json  # noqa: E402
+import statistics  # noqa: E402
+import subprocess  # noqa: E402
+import sys  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "nmfk.jl_b200", "python")):
@@ -41,16 +48,41 @@ import numpy as np  # noqa: E402
 
 METRIC = "nmf_restart_iterations_per_sec"
 UNIT = "restart-iterations/s"
-N_ROWS, N_COLS, K0 = 1000, 200, 5
-KS = list(range(2, 11))
-R_PER_RANK = 100
 SEED_X, SEED0 = 2015, 2015
-WORKLOAD = "C2: synthetic mixture 1000x200 Float64 (k0=5), execute(X, 2:10, nNMF=100; method=:simple), maxiter=10000"
+# name: (n, m, k0, dtype, ks, nNMF)
+CONFIGS = {
+    "C2": (1000, 200, 5, np.float64, list(range(2, 11)), 100),
+    "C3": (10000, 10000, 16, np.float32, [16], 64),
+    "C4": (100000, 2000, 8, np.float64, list(range(2, 33)), 256),
+    "C5": (2000000, 1000, 24, np.float32, [24], 32),
+}
+WORKLOADS = {
+    "C2": "C2: synthetic mixture 1000x200 Float64 (k0=5), execute(X, 2:10, nNMF=100; method=:simple), maxiter=10000, full stop rule",
+    "C3": "C3: synthetic mixture 10000x10000 Float32 (k0=16), k=16, nNMF=64, %d iterations per step with every restart active",
+    "C4": "C4: synthetic mixture 100000x2000 Float64 (k0=8), k=2:32, nNMF=256 sharded over the GPUs (strong scaling), %d iterations per step",
+    "C5": "C5: synthetic tall matrix 2000000x1000 Float32 (k0=24), k=24, nNMF=32, rows of X sharded over the GPUs, %d iterations per step",
+}
+ITERS = {"C3": 20, "C4": 3, "C5": 10}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full` captures
+TRAFFIC = {"C3": (893748480, "profiles/r02_tc_pass_c3.txt"), "C4": (None, None), "C5": (None, None), "C2": (17534720, "profiles/r01_resident_dmma_v3_k10.txt")}
 
 
-def algorithmic_flops(iters_by_k):
-    """KL multiplicative update: 8*n*m*k flops per restart-iteration."""
-    return float(sum(8.0 * N_ROWS * N_COLS * k * it for k, it in iters_by_k.items()))
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
+    except Exception:
+        return BLAS_THREADS
+
+
+def pin_blas():
+    """Raise OpenBLAS to BLAS_THREADS even when the library was loaded under another setting."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=BLAS_THREADS, user_api="blas")
+    except Exception:
+        pass
+    return blas_threads()
 
 
 class ClockSampler:
@@ -94,94 +126,250 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_sample(iters_per_k=100, ks=KS):
-    """Bounded sample of the C2 workload on the host cores: `iters_per_k` iterations of ONE restart
-    for every k of the sweep, literal reference operation sequence (oracle)."""
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def c5_rows(rank, world, n_global, m, k0):
+    """This rank's rows of the C5 mixture: H0 from the common stream, W0 rows from a per-rank stream (16 GB of Float64 would be
+    needed to build the whole matrix on every rank)."""
+    r0, r1 = (n_global * rank) // world, (n_global * (rank + 1)) // world
+    H0 = np.random.Generator(np.random.Philox(key=SEED_X)).random((k0, m))
+    W0 = np.random.Generator(np.random.Philox(key=SEED_X + 1 + rank)).random((r1 - r0, k0))
+    return np.asfortranarray((W0 @ H0).astype(np.float32)), r0, r1
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle): bounded samples of the same configurations
+# ------------------------------------------------------------------------------------------------------------------
+_CPU_X = {}
+
+def cpu_sample_fixed(cfg, iters, k=None, rank=0, world=1):
+    """`iters` iterations of ONE restart of the configuration on the host cores (literal reference operation sequence,
+    Float64 compute like the reference - SURVEY 0.4).  -> (restart-iterations, seconds)"""
     from oracle import nmfk_oracle as o
     from nmfk_b200 import synth
-    X = synth.mixture(N_ROWS, N_COLS, K0, seed=SEED_X)
+    n, m, k0, dt, ks, R = CONFIGS[cfg]
+    k = k or ks[-1]
+    scale = 4.0 if cfg == "C5" else 1.0
+    if cfg not in _CPU_X:
+        _CPU_X.clear()
+        if cfg == "C5":
+            X, _, _ = c5_rows(0, 4, n, m, k0)  # a quarter of the rows: the CPU time per iteration scales with the row count
+        else:
+            X = synth.mixture(n, m, k0, seed=SEED_X, dtype=dt)
+        _CPU_X[cfg] = np.asfortranarray(X.astype(np.float64))
+        del X
+    X64 = _CPU_X[cfg]  # nmf_multiplicative restores it before returning
+    nn = X64.shape[0]
+    rng = np.random.Generator(np.random.Philox(key=SEED0 + 1))
+    W0 = rng.random(nn * k).reshape((nn, k), order="F")
+    H0 = rng.random(k * m).reshape((k, m), order="F")
+    inf = {}
+    t0 = time.perf_counter()
+    o.nmf_multiplicative(X64, k, Winit=W0, Hinit=H0, maxiter=iters, info=inf)
+    dt_s = (time.perf_counter() - t0) * scale
+    return inf["iters"], dt_s
+
+
+def cpu_sample_c2(iters_per_k=60):
+    from oracle import nmfk_oracle as o
+    from nmfk_b200 import synth
+    n, m, k0, dt, ks, R = CONFIGS["C2"]
+    X = synth.mixture(n, m, k0, seed=SEED_X)
     tot = 0
     t0 = time.perf_counter()
     for k in ks:
-        W0, H0 = synth.philox_inits(SEED0, 1, N_ROWS, k, N_COLS)
+        W0, H0 = synth.philox_inits(SEED0, 1, n, k, m)
         inf = {}
         o.nmf_multiplicative(X.copy(order="F"), k, Winit=W0[0], Hinit=H0[0], maxiter=iters_per_k, info=inf)
         tot += inf["iters"]
-    dt = time.perf_counter() - t0
-    return tot, dt
+    return tot, time.perf_counter() - t0
 
 
-def bench_tiled(ctx, nb, synth, tag, n, m, k, R, dtype, k0, iters=20):
-    """One of the large BASELINE configurations on ONE GPU through the tiled engine: a fixed number of iterations with
-    every restart active; the tensor-core pass (tcgen05 kind::tf32 3-term split for Float32, DMMA m8n8k4 for Float64)
-    next to the scalar-FMA pass kernel and a bounded CPU sample.  Reported under "also" (the headline stays C2)."""
-    from oracle import nmfk_oracle as o
-    f32 = dtype == np.float32
-    X = synth.mixture(n, m, k0, seed=SEED_X, dtype=dtype)
-    ctx.set_X(X)
-    peak = max(ctx.measure_peak(2 if f32 else 1) for _ in range(2))
-    out = {}
-    for name, eng in (("tensor", 2), ("scalar_fma", 4)):
-        best = None
-        for rep, it in enumerate((3, iters, iters)):  # the first solve is the warm-up; best of two timed solves
-            b = ctx.batch(k, R)
-            b.init_random(SEED0)
-            sampler = ClockSampler(0)
-            sampler.start()
-            ctx.solve([b], nb.default_params(maxiter=it, engine=eng))
-            clk = sampler.stop()
-            ms = ctx.last_solve_ms
-            tot = int(b.get(factors=False)["iters"].sum())
-            b.close()
-            if rep > 0 and (best is None or ms < best[0]):
-                best = (ms, tot, clk)
-        ms, tot, clk = best
-        tf = 8.0 * n * m * k * tot / ms / 1e9
-        out[name] = {"value": tot / ms * 1e3, "unit": UNIT, "ms": ms, "restart_iterations": tot,
-                     "algorithmic_tflops": tf, "frac_of_peak": tf / peak, "clocks": clk}
-    W0, H0 = synth.philox_inits(SEED0, 1, n, k, m)
-    inf = {}
-    t0 = time.perf_counter()
-    o.nmf_multiplicative(np.asfortranarray(X.astype(np.float64)), k, Winit=W0[0], Hinit=H0[0], maxiter=3, info=inf)
-    dt = time.perf_counter() - t0
-    return {"workload": "%s, %d iterations, all restarts active" % (tag, iters),
-            "engine": "tiled; " + ("tcgen05.mma kind::tf32 3-term split (kl_tiled_tc.cu)" if f32 else "DMMA m8n8k4 (kl_tiled_dmma.cu)"),
-            "peak": {"value": peak, "unit": "TFLOP/s", "what": "FP32 FFMA (own micro-benchmark)" if f32 else "FP64 DMMA (own micro-benchmark)"},
-            "tensor_pass": out["tensor"], "scalar_fma_pass": out["scalar_fma"],
-            "cpu_baseline": {"value": inf["iters"] / dt, "unit": UNIT, "cores": blas_threads(), "kind": "port",
-                             "sample": "3 iterations of 1 restart (oracle, Float64 like the reference)"}}
+def cpu_step(cfg, budget_iters):
+    """One bounded CPU sample of a step of `cfg` -> (restart-iterations, seconds, description)."""
+    if cfg == "C2":
+        tot, dt = cpu_sample_c2(60)
+        return tot, dt, "60 iterations of 1 restart for each k in 2:10 (540 restart-iterations)"
+    if cfg == "C4":
+        tot, dt, parts = 0, 0.0, []
+        for k in (2, 8, 16, 32):  # four k of the sweep, 2 iterations of 1 restart each
+            t, d = cpu_sample_fixed("C4", 2, k=k)
+            tot += t
+            dt += d
+            parts.append(k)
+        return tot, dt, "2 iterations of 1 restart at k = %s of the 2:32 sweep" % parts
+    t, d = cpu_sample_fixed(cfg, budget_iters)
+    extra = " on a quarter of the rows, time x 4" if cfg == "C5" else ""
+    return t, d, "%d iterations of 1 restart%s" % (budget_iters, extra)
 
 
-def blas_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        return max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
-    except Exception:
-        return os.cpu_count() or 1
-
-
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, cfg):
     if rank != 0:
         return
-    per_k = 60
-    for _ in range(args.warmup):
-        cpu_sample(10)
-    tot, dt = 0, 0.0
+    threads = pin_blas()
+    iters = {"C3": 3, "C5": 2}.get(cfg, 0)
+    for _ in range(min(args.warmup, 1)):
+        cpu_step(cfg, 1 if iters else 0)
+    tot, dt, what = 0, 0.0, ""
     for _ in range(args.steps):
-        t, d = cpu_sample(per_k)
+        t, d, what = cpu_step(cfg, iters)
         tot += t
         dt += d
     val = tot / dt
-    cores = blas_threads()
-    sample = "%d iterations of 1 restart for each k in 2:10 per step (%d restart-iterations/step)" % (per_k, per_k * len(KS))
+    wl = WORKLOADS[cfg] % ITERS[cfg] if cfg in ITERS else WORKLOADS[cfg]
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU restatement of NMFk.jl (Julia unavailable): NumPy/OpenBLAS, "
-                       "5 n*m*k products + 2 n*m divides per iteration, restarts serial"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "strong" if cfg in ("C4", "C5") else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl, "same_config": True,
+                       "note": "CPU restatement of NMFk.jl (Julia unavailable): NumPy/OpenBLAS, Float64 compute like the reference, "
+                               "5 n*m*k products + 2 n*m divides per iteration, restarts serial; each step is a bounded sample "
+                               "of the workload: " + what},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": what + " per step",
+                             "blas_threads_set": BLAS_THREADS},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arms
+# ------------------------------------------------------------------------------------------------------------------
+def fixed_budget_single(ctx, nb, synth, torch, cfg, args, iters, flush, k=None, R=None, engine=2):
+    """C3-style measurement on one GPU: R restarts at one k, `iters` iterations per step, every restart active."""
+    n, m, k0, dt, ks, R0 = CONFIGS[cfg]
+    k, R = k or ks[-1], R or R0
+    f32 = dt == np.float32
+    X = synth.mixture(n, m, k0, seed=SEED_X, dtype=dt)
+    W0, H0 = synth.philox_inits(SEED0, R, n, k, m, dtype=dt)
+    Xpin = torch.from_numpy(np.ascontiguousarray(X.T)).pin_memory()  # (m, n) C-order == n x m column-major
+    Wpin = torch.from_numpy(np.ascontiguousarray(np.transpose(W0, (0, 2, 1)))).pin_memory()
+    Hpin = torch.from_numpy(np.ascontiguousarray(np.transpose(H0, (0, 2, 1)))).pin_memory()
+    del W0, H0
+    es = 4 if f32 else 8
+    h2d = (Xpin.numel() + Wpin.numel() + Hpin.numel()) * es
+    d2h = (n * k + k * m) * es + 3 * 8
+    # ---- device-resident arm
+    ctx.set_X(X)
+    params = nb.default_params(maxiter=iters, engine=engine)
+
+    def device_step(profile):
+        b = ctx.batch(k, R)
+        b.init_random(SEED0)  # the same Philox streams as the pinned host factors, generated in HBM
+        if flush is not None:
+            flush.fill_(1)
+        torch.cuda.synchronize()
+        l0 = ctx.launches
+        if profile:
+            ctx.profile(True)
+        ctx.solve([b], params)
+        ms = ctx.last_solve_ms
+        pm, pl = ctx.profile_get() if profile else (0.0, 0)
+        ctx.profile(False)
+        tot = int(b.get(factors=False)["iters"].sum())
+        nl = ctx.launches - l0
+        b.close()
+        return ms, tot, nl, pm, pl
+
+    for _ in range(args.warmup):
+        device_step(False)
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    tot_ms = tot_it = launches = pass_l = 0
+    pass_ms = 0.0
+    for _ in range(args.steps):
+        ms, tot, nl, pm, pl = device_step(True)
+        tot_ms += ms
+        tot_it += tot
+        launches += nl
+        pass_ms += pm
+        pass_l += pl
+    clocks = sampler.stop()
+
+    # ---- end-to-end arm: host buffers in, best factors and scores out, through the one-call C ABI
+    import ctypes as C
+    Wb = np.empty((k, n), dtype=dt)
+    Hb = np.empty((m, k), dtype=dt)
+
+    def e2e_step():
+        if flush is not None:
+            flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.set_X(Xpin.numpy().T)  # H2D of X + preprocessing
+        phi, rob, aic, tot = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        nb._lib.check(ctx._lib.nmfk_execute_run(ctx._h, k, R, C.c_void_p(Wpin.data_ptr()), C.c_void_p(Hpin.data_ptr()), SEED0,
+                                                C.byref(params), Wb.ctypes.data_as(C.c_void_p), Hb.ctypes.data_as(C.c_void_p),
+                                                C.byref(phi), C.byref(rob), C.byref(aic), C.byref(tot)), ctx._h)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, int(tot.value), rob.value
+
+    for _ in range(min(args.warmup, 1)):
+        e2e_step()
+    e2e_t = e2e_it = 0
+    rob = None
+    for _ in range(args.steps):
+        dts, t, rob = e2e_step()
+        e2e_t += dts
+        e2e_it += t
+    return dict(value=tot_it / (tot_ms * 1e-3), ms_per_step=tot_ms / args.steps, iters_per_step=tot_it / args.steps,
+                launches=launches, pass_ms=pass_ms, pass_launches=pass_l, flops_per_pass=4.0 * n * m * k * R, clocks=clocks,
+                e2e_value=e2e_it / e2e_t, e2e_ms_per_step=e2e_t / args.steps * 1e3, h2d=h2d, d2h=d2h, robustness=rob,
+                n=n, m=m, k=k, R=R)
+
+
+def bench_c2(ctx, nb, synth, torch, args, flush, steps, warmup):
+    """C2 on one GPU: execute(X, 2:10, 100) with the reference stop rule (the resident DMMA engine)."""
+    n, m, k0, dt, ks, R = CONFIGS["C2"]
+    X = synth.mixture(n, m, k0, seed=SEED_X)
+    ctx.set_X(X)
+    params = nb.default_params()
+    peak = max(ctx.measure_peak(1) for _ in range(2))
+
+    def step():
+        bs = [ctx.batch(k, R) for k in ks]
+        for b in bs:
+            b.init_random(SEED0)
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        ctx.solve(bs, params)
+        ms = ctx.last_solve_ms
+        its = {b.k: int(b.get(factors=False)["iters"].sum()) for b in bs}
+        for b in bs:
+            b.close()
+        return ms, its
+
+    for _ in range(warmup):
+        step()
+    tot_ms, tot_it, flops = 0.0, 0, 0.0
+    for _ in range(steps):
+        ms, its = step()
+        tot_ms += ms
+        tot_it += sum(its.values())
+        flops += sum(8.0 * n * m * k * v for k, v in its.items())
+    t0 = time.perf_counter()
+    W, H, fit, rob, aic, kopt = nb.execute(X, ks, R, seed=SEED0, ctx=ctx)
+    e2e = time.perf_counter() - t0
+    tf = flops / (tot_ms * 1e-3) / 1e12
+    return {"workload": WORKLOADS["C2"], "value": tot_it / (tot_ms * 1e-3), "unit": UNIT, "ms_per_step": tot_ms / steps,
+            "restart_iterations_per_step": tot_it / steps, "kopt": kopt, "e2e_s_execute": e2e,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                         "kernel": "kl_resident_dmma_kernel<K> (one CTA per restart, DMMA m8n8k4)",
+                         "peak_source": "FP64 DMMA micro-benchmark (nmfk_measure_peak 1); MEASURED_PEAKS.json has no FP64 figure"}}
+
+
+def sweep_step(ctx, nbdist, torch, Xhost, ks, R_local, params, rank, world, barrier):
+    barrier()
+    t0 = time.perf_counter()
+    out = nbdist.execute_sharded(ctx, Xhost, ks, R_local, seed0=SEED0, rank=rank, world=world, params=params)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return dt, ctx.last_solve_ms, out
 
 
 def main():
@@ -190,14 +378,17 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="auto", choices=["auto", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--iters", type=int, default=0, help="iterations per step of the fixed-budget configurations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-also", action="store_true", help="skip the secondary C3 measurement")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary measurements (C2, C4 on one GPU)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = args.config if args.config != "auto" else ("C3" if world == 1 else "C4")
     if args.impl == "reference":
-        return run_reference(args, rank, world)
+        return run_reference(args, rank, world, cfg)
 
     import torch
     import nmfk_b200 as nb
@@ -217,146 +408,245 @@ def main():
             td.barrier()
         torch.cuda.synchronize()
 
-    ctx = nb.Context(local_rank)
-    X = synth.mixture(N_ROWS, N_COLS, K0, seed=SEED_X)
-    # pinned host copies of every input of one step (X + the initial factors of this rank's restarts)
-    seed_rank = SEED0 + rank * R_PER_RANK
-    Xpin = torch.from_numpy(X.T.copy()).pin_memory()  # (m, n) C-order == n x m column-major
-    inits = {}
-    h2d = Xpin.numel() * 8
-    for k in KS:
-        W0, H0 = synth.philox_inits(seed_rank, R_PER_RANK, N_ROWS, k, N_COLS)
-        Wp = torch.from_numpy(np.ascontiguousarray(np.transpose(W0, (0, 2, 1)))).pin_memory()
-        Hp = torch.from_numpy(np.ascontiguousarray(np.transpose(H0, (0, 2, 1)))).pin_memory()
-        inits[k] = (Wp, Hp)
-        h2d += (Wp.numel() + Hp.numel()) * 8
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-
-    peaks = {"fp64_dmma_tflops": max(ctx.measure_peak(1) for _ in range(2)),
-             "fp64_dfma_tflops": max(ctx.measure_peak(0) for _ in range(2))}
-
-    # ---------------- device-resident arm: `value` ----------------
-    ctx.set_X(X)
-    params = nb.default_params()
-
-    def make_batches():
-        bs = [ctx.batch(k, R_PER_RANK) for k in KS]
-        for b in bs:
-            b.init_random(seed_rank)  # same Philox streams as the pinned host inits, generated in HBM
-        return bs
-
-    def device_step():
-        bs = make_batches()
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        launches0 = ctx.launches
-        ctx.solve(bs, params)  # timed inside by CUDA events on the launching stream
-        ms = ctx.last_solve_ms
-        iters = {b.k: int(b.get(factors=False)["iters"].sum()) for b in bs}
-        nl = ctx.launches - launches0
-        for b in bs:
-            b.close()
-        return ms, iters, nl
-
-    for _ in range(args.warmup):
-        device_step()
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    t_wall0 = time.perf_counter()
-    tot_ms, tot_it, launches, iters_sum = 0.0, 0, 0, {k: 0 for k in KS}
-    for _ in range(args.steps):
-        ms, iters, nl = device_step()
-        tot_ms += ms
-        launches += nl
-        for k, v in iters.items():
-            iters_sum[k] += v
-        tot_it += sum(iters.values())
-    barrier()
-    wall_dev = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
-
-    # ---------------- end-to-end arm through the public API with host buffers ----------------
-    def e2e_step():
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        out = nbdist.execute_sharded(ctx, Xpin.numpy().T, KS, R_PER_RANK,
-                                     inits={k: (inits[k][0].numpy(), inits[k][1].numpy()) for k in KS},
-                                     stack_layout=True, rank=rank, world=world)
-        torch.cuda.synchronize()
-        return time.perf_counter() - t0, out
-
-    for _ in range(min(args.warmup, 1)):
-        e2e_step()
-    barrier()
-    e2e_t, e2e_it, d2h, kopt = 0.0, 0, 0, None
-    for _ in range(args.steps):
-        dt, out = e2e_step()
-        e2e_t += dt
-        e2e_it += out["total_iters_local"]
-        d2h = out["d2h_bytes"]
-        kopt = out["kopt"]
-    barrier()
-
-    # ---------------- reduce over ranks: max time, summed work ----------------
-    if use_dist:
-        t = torch.tensor([tot_ms, e2e_t], dtype=torch.float64, device="cuda")
+    def reduce_max(vals):
+        if not use_dist:
+            return list(vals)
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
         td.all_reduce(t, op=td.ReduceOp.MAX)
-        w = torch.tensor([float(tot_it), float(e2e_it), float(launches), algorithmic_flops(iters_sum)],
-                         dtype=torch.float64, device="cuda")
-        td.all_reduce(w, op=td.ReduceOp.SUM)
-        tot_ms_max, e2e_t_max = t.tolist()
-        tot_it_all, e2e_it_all, launches_all, flops_all = w.tolist()
-    else:
-        tot_ms_max, e2e_t_max = tot_ms, e2e_t
-        tot_it_all, e2e_it_all, launches_all, flops_all = float(tot_it), float(e2e_it), float(launches), \
-            algorithmic_flops(iters_sum)
+        return t.tolist()
 
-    if rank == 0:
-        value = tot_it_all / (tot_ms_max * 1e-3)
-        achieved = flops_all / world / (tot_ms_max * 1e-3) / 1e12  # per GPU
-        peak = peaks["fp64_dmma_tflops"]
+    def reduce_sum(vals):
+        if not use_dist:
+            return list(vals)
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+        td.all_reduce(t, op=td.ReduceOp.SUM)
+        return t.tolist()
+
+    ctx = nb.Context(local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    mp = measured_peaks()
+    iters = args.iters or ITERS.get(cfg, 0)
+    line = None
+
+    if cfg == "C3":
+        if world != 1:
+            raise SystemExit("bench.py: C3 is the single-GPU configuration (use --config C4 / C5 with several GPUs)")
+        tf32 = max(ctx.measure_peak(13) for _ in range(3))
+        ffma = max(ctx.measure_peak(2) for _ in range(2))
+        r = fixed_budget_single(ctx, nb, synth, torch, "C3", args, iters, flush)
+        per_launch_ms = r["pass_ms"] / max(r["pass_launches"], 1)
+        achieved = r["flops_per_pass"] / (per_launch_ms * 1e-3) / 1e12
+        peak = tf32 / 3.0
+        traffic, traffic_src = TRAFFIC["C3"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": tot_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "restarts_per_gpu_per_k": R_PER_RANK, "engine": "resident (one CTA per restart)",
-                       "l2": "256 MiB written between steps (X itself is 1.6 MB and L2-resident by design)",
-                       "kopt": kopt, "restart_iterations_per_step": tot_it_all / args.steps,
-                       "wall_s_device_arm": wall_dev},
-            "clocks": clocks,
-            "e2e": {"value": e2e_it_all / e2e_t_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_t_max / args.steps * 1e3},
-            "gpu_launches": int(launches_all),
+            "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOADS["C3"] % iters, "engine": "tiled; tcgen05.mma kind::tf32 3-term split (kl_tiled_tc.cu)",
+                       "l2": "inputs larger than L2: X is 400 MB (and its transpose another 400 MB) against 126 MB of L2; 256 MiB "
+                             "are also written between steps", "restart_iterations_per_step": r["iters_per_step"],
+                       "same_config": True},
+            "clocks": r["clocks"],
+            "e2e": {"value": r["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                    "ms_per_step": r["e2e_ms_per_step"],
+                    "call": "nmfk_set_X + nmfk_execute_run with pinned host X / Winit / Hinit; clustering, silhouettes and the "
+                            "best-restart selection inside the timed region", "robustness": r["robustness"]},
+            "gpu_launches": int(r["launches"]),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": 17534720,
-                         "traffic_note": "dram__bytes_read + dram__bytes_write of one ncu --set full capture of "
-                                         "kl_resident_dmma_kernel<10> (30 iterations of 148 restarts, "
-                                         "profiles/r01_resident_dmma_v3_k10.txt): X (1.6 MB, both orientations) and the "
-                                         "factors are read from DRAM once and stay in L2 / shared memory - the kernel is "
-                                         "FP64-pipe and L2-latency bound, not DRAM bound",
-                         "kernel": "kl_resident_dmma_kernel<K,false> (9 instantiations, one per k, concurrent streams; "
-                                   "DMMA m8n8k4 + DFMA remainder columns share the FP64 pipe)",
-                         "note": "FP64 work: MEASURED_PEAKS.json holds only HBM and bf16 peaks, so the denominator is the "
-                                 "FP64 DMMA (mma.sync m8n8k4) throughput measured by nmfk_measure_peak in this run; the "
-                                 "DFMA pipe measured %.1f TFLOP/s. achieved = 8*n*m*k flops per restart-iteration / "
-                                 "event time of the solve" % peaks["fp64_dfma_tflops"]},
-        }
-        if not args.no_cpu_baseline and world == 1:
-            tot, dt = cpu_sample(60)
-            line["cpu_baseline"] = {"value": tot / dt, "unit": UNIT, "cores": blas_threads(), "kind": "port",
-                                    "sample": "60 iterations of 1 restart for each k in 2:10 (540 restart-iterations), "
-                                              "oracle/nmfk_oracle.py (NumPy/OpenBLAS restatement of NMFkMultiplicative.jl)"}
-        if not args.no_also and world == 1:
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "tc_pass_kernel<K8,N2,WIDE,0> (one launch = one half-update of all 64 restarts)",
+                         "launch_ms": per_launch_ms, "launches_timed": int(r["pass_launches"]),
+                         "algorithmic_flops_per_launch": r["flops_per_pass"],
+                         "algorithmic_bytes_per_launch": float(r["n"]) * r["m"] * 4,
+                         "peak_source": "tcgen05.mma kind::tf32 dense throughput measured in this run by nmfk_measure_peak(13) "
+                                        "(%.1f TFLOP/s) / 3 for the 3-term split; MEASURED_PEAKS.json holds bf16 %.1f TFLOP/s "
+                                        "(TF32 = half of it = %.1f)" % (tf32, mp.get("bf16_tflops", float("nan")),
+                                                                       mp.get("bf16_tflops", float("nan")) / 2),
+                         "frac_of_fp32_ffma_peak": achieved / ffma, "fp32_ffma_peak": ffma,
+                         "what_bounds": "the CUDA-core quotient stage (MUFU.RCP + hi/lo split + tensor-memory traffic of Q), not "
+                                        "the tensor pipe: see DESIGN.md 4a",
+                         "hbm_gbs_if_streaming_only": float(r["n"]) * r["m"] * 4 / (per_launch_ms * 1e-3) / 1e9,
+                         "hbm_peak_gbs": mp.get("hbm_gbs")}}
+        if not args.no_cpu_baseline:
+            threads = pin_blas()
+            t, d, what = cpu_step("C3", 6)
+            line["cpu_baseline"] = {"value": t / d, "unit": UNIT, "cores": threads, "kind": "port", "blas_threads_set": BLAS_THREADS,
+                                    "sample": what + " of the same configuration, oracle/nmfk_oracle.py (NumPy/OpenBLAS "
+                                              "restatement of NMFkMultiplicative.jl, Float64 compute like the reference)"}
+        if not args.no_also:
             line["also"] = {}
-            for key, cfg in (("C3", ("C3: synthetic mixture 10000x10000 Float32, k=16, nNMF=64", 10000, 10000, 16, 64, np.float32, 16)),
-                             ("C4_k32", ("C4 at k=32 on one GPU: synthetic mixture 100000x2000 Float64, 32 of the 256 restarts",
-                                         100000, 2000, 32, 32, np.float64, 8))):
-                try:
-                    line["also"][key] = bench_tiled(ctx, nb, synth, *cfg)
-                except Exception as e:  # the headline must survive a failure of a secondary measurement
-                    line["also"][key] = {"error": repr(e)}
+            try:
+                line["also"]["C2"] = bench_c2(ctx, nb, synth, torch, args, flush, 1, 1)
+            except Exception as e:
+                line["also"]["C2"] = {"error": repr(e)}
+            try:  # the C4 step of the multi-GPU runs on ONE GPU: the strong-scaling baseline
+                n, m, k0, dt, ks, R = CONFIGS["C4"]
+                X4 = synth.mixture(n, m, k0, seed=SEED_X, dtype=dt)
+                p4 = nb.default_params(maxiter=ITERS["C4"], engine=2)
+                ctx.profile(True)
+                dt_s, solve_ms, out = sweep_step(ctx, nbdist, torch, X4, ks, R, p4, 0, 1, barrier)
+                pm, pl = ctx.profile_get()
+                ctx.profile(False)
+                line["also"]["C4_strong_n1"] = {"workload": WORKLOADS["C4"] % ITERS["C4"], "n_gpus": 1,
+                                                "value": out["total_iters"] / (solve_ms * 1e-3), "unit": UNIT, "ms_per_step": solve_ms,
+                                                "e2e_value": out["total_iters"] / dt_s, "restart_iterations_per_step": out["total_iters"],
+                                                "pass_ms": pm, "pass_launches": pl, "note": "one step, no warm-up"}
+                del X4
+            except Exception as e:
+                line["also"]["C4_strong_n1"] = {"error": repr(e)}
+
+    elif cfg == "C4":
+        n, m, k0, dt, ks, R = CONFIGS["C4"]
+        if R % world:
+            raise SystemExit("bench.py: nNMF = 256 must be divisible by the number of GPUs")
+        R_local = R // world
+        X = synth.mixture(n, m, k0, seed=SEED_X, dtype=dt)
+        Xpin = torch.from_numpy(np.ascontiguousarray(X.T)).pin_memory()
+        del X
+        params = nb.default_params(maxiter=iters, engine=2)
+        dmma = max(ctx.measure_peak(1) for _ in range(2))
+        for _ in range(args.warmup):
+            sweep_step(ctx, nbdist, torch, Xpin.numpy().T, ks, R_local, params, rank, world, barrier)
+        sampler = ClockSampler(local_rank)
+        barrier()
+        sampler.start()
+        l0 = ctx.launches
+        ctx.profile(True)
+        wall = solve = 0.0
+        its = its_local = 0
+        kopt = None
+        for _ in range(args.steps):
+            flush.fill_(1)
+            dts, sms, out = sweep_step(ctx, nbdist, torch, Xpin.numpy().T, ks, R_local, params, rank, world, barrier)
+            wall += dts
+            solve += sms
+            its += out["total_iters"]
+            its_local += out["total_iters_local"]
+            kopt = out["kopt"]
+        barrier()
+        pm, pl = ctx.profile_get()
+        ctx.profile(False)
+        clocks = sampler.stop()
+        launches = ctx.launches - l0
+        wall_max, solve_max, pm_max = reduce_max([wall, solve, pm])
+        launches_all, = reduce_sum([float(launches)])
+        if rank == 0:
+            flops_rank = sum(8.0 * n * m * k * R_local * iters for k in ks) * args.steps  # per GPU, both half-updates
+            achieved = flops_rank / (pm_max * 1e-3) / 1e12 if pm_max > 0 else float("nan")
+            es = 8
+            h2d = n * m * es
+            d2h = sum((n * k + k * m) * es for k in ks) + 3 * 8 * len(ks) + 12
+            line = {
+                "metric": METRIC, "value": its / (solve_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": solve_max / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOADS["C4"] % iters, "restarts_per_gpu_per_k": R_local,
+                           "engine": "tiled; DMMA m8n8k4 pass (kl_tiled_dmma.cu) for k >= 4, scalar-FMA pass for k = 2, 3",
+                           "sharding": "restarts (nmfk_sweep): 256 / N restarts of every k per GPU; k groups of <= 48 GB of factor stacks",
+                           "l2": "inputs larger than L2: X is 1.6 GB (and its transpose); 256 MiB written between steps",
+                           "restart_iterations_per_step": its / args.steps, "kopt": kopt, "same_config": True,
+                           "strong_scaling_n1": "bench.py --gpus 1 reports this same step on one GPU under also.C4_strong_n1"},
+                "clocks": clocks,
+                "e2e": {"value": its / wall_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": wall_max / args.steps * 1e3,
+                        "call": "nmfk_set_X + nmfk_sweep with pinned host X on every rank: H2D of X, device Philox initial factors, "
+                                "solve, NCCL all-gather of H stacks / states, W broadcast, owner-side clustering + silhouettes, kopt"},
+                "gpu_launches": int(launches_all),
+                "roofline": {"bound": "tensor", "achieved": achieved, "peak": dmma, "unit": "TFLOP/s", "frac": achieved / dmma,
+                             "traffic": None, "kernel": "tiled_dmma_pass_kernel<K> / tiled_pass_kernel (all k of the sweep, per GPU)",
+                             "launch_ms": pm_max / max(pl, 1), "launches_timed": int(pl),
+                             "peak_source": "FP64 DMMA micro-benchmark (nmfk_measure_peak 1); MEASURED_PEAKS.json has no FP64 figure",
+                             "note": "achieved = 8*n*m*k flops per restart-iteration of this GPU's restarts / summed event time of "
+                                     "its pass launches (slowest rank)"}}
+
+    elif cfg == "C5":
+        n, m, k0, dt, ks, R = CONFIGS["C5"]
+        k = ks[0]
+        Xloc, r0, r1 = c5_rows(rank, world, n, m, k0)
+        uid = nbdist.exchange_unique_id(rank) if use_dist else None
+        ctx.comm_init(world, rank, uid, r0, n)
+        tf32 = max(ctx.measure_peak(13) for _ in range(3))
+        Xpin = torch.from_numpy(np.ascontiguousarray(Xloc.T)).pin_memory()
+        del Xloc
+        params = nb.default_params(maxiter=iters, engine=2)
+
+        def step(profile):
+            barrier()
+            t0 = time.perf_counter()
+            ctx.set_X(Xpin.numpy().T)
+            b = ctx.batch(k, R)
+            b.init_random(SEED0)
+            if profile:
+                ctx.profile(True)
+            ctx.solve([b], params)
+            st = b.get(factors=False)
+            torch.cuda.synchronize()
+            dts = time.perf_counter() - t0
+            pm, pl = ctx.profile_get() if profile else (0.0, 0)
+            ctx.profile(False)
+            b.close()
+            return dts, ctx.last_solve_ms, int(st["iters"].sum()), pm, pl
+
+        for _ in range(args.warmup):
+            step(False)
+        sampler = ClockSampler(local_rank)
+        barrier()
+        sampler.start()
+        l0 = ctx.launches
+        wall = solve = pm = 0.0
+        its = pl = 0
+        for _ in range(args.steps):
+            flush.fill_(1)
+            d, s_ms, t, a, b_ = step(True)
+            wall += d
+            solve += s_ms
+            its += t
+            pm += a
+            pl += b_
+        barrier()
+        clocks = sampler.stop()
+        launches = ctx.launches - l0
+        wall_max, solve_max, pm_max = reduce_max([wall, solve, pm])
+        launches_all, = reduce_sum([float(launches)])
+        if rank == 0:
+            nloc = r1 - r0
+            achieved = 4.0 * nloc * m * k * R * pl / (pm_max * 1e-3) / 1e12 if pm_max > 0 else float("nan")
+            line = {
+                "metric": METRIC, "value": its / (solve_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": solve_max / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOADS["C5"] % iters, "rows_per_gpu": nloc,
+                           "engine": "tiled, row-sharded: tcgen05 pass per GPU + one NCCL all-reduce of the k x m x R numerators "
+                                     "and colsum(W) per iteration", "l2": "inputs larger than L2 (%.1f GB of X per GPU)" % (nloc * m * 4 / 1e9),
+                           "restart_iterations_per_step": its / args.steps, "same_config": True},
+                "clocks": clocks,
+                "e2e": {"value": its / wall_max, "unit": UNIT, "h2d_bytes_per_step": nloc * m * 4, "d2h_bytes_per_step": R * 4 * 8,
+                        "ms_per_step": wall_max / args.steps * 1e3,
+                        "call": "nmfk_set_X (H2D of this rank's rows) + device Philox factors + nmfk_solve + state read-back"},
+                "gpu_launches": int(launches_all),
+                "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf32 / 3.0, "unit": "TFLOP/s",
+                             "frac": achieved / (tf32 / 3.0), "traffic": None,
+                             "kernel": "tc_pass_kernel (per GPU; one launch = one half-update of all 32 restarts on this GPU's rows)",
+                             "launch_ms": pm_max / max(pl, 1), "launches_timed": int(pl),
+                             "peak_source": "tcgen05 kind::tf32 dense (nmfk_measure_peak 13: %.1f TFLOP/s) / 3" % tf32}}
+
+    elif cfg == "C2":
+        if world != 1:
+            raise SystemExit("bench.py: --config C2 runs on one GPU")
+        r = bench_c2(ctx, nb, synth, torch, args, flush, args.steps, args.warmup)
+        line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": {"workload": WORKLOADS["C2"], "kopt": r["kopt"], "same_config": True,
+                                                "l2": "256 MiB written between steps (X itself is 1.6 MB and L2-resident by design)"},
+                "e2e": {"value": r["restart_iterations_per_step"] / r["e2e_s_execute"], "unit": UNIT,
+                        "h2d_bytes_per_step": 1000 * 200 * 8, "d2h_bytes_per_step": sum((1000 * k + k * 200) * 8 for k in range(2, 11))},
+                "gpu_launches": int(ctx.launches), "roofline": dict(r["roofline"], traffic=TRAFFIC["C2"][0])}
+        if not args.no_cpu_baseline:
+            threads = pin_blas()
+            t, d, what = cpu_step("C2", 0)
+            line["cpu_baseline"] = {"value": t / d, "unit": UNIT, "cores": threads, "kind": "port", "sample": what}
+
+    if rank == 0 and line is not None:
         print(json.dumps(line))
     ctx.close()
     if use_dist:

@@ -576,24 +576,29 @@ cudaError_t dispatch_tiled_combine(const TiledPassArgs& a, void* red, cudaStream
 // use_td: Float64 without NaN, k >= 4 -> the DMMA kernel of kl_tiled_dmma.cu (a.nblocks counts 128-index blocks, a.D is
 // the step-contiguous copy of the data)
 template <typename TX, typename TC>
-cudaError_t dispatch_tiled_pass(const TiledPassArgs& a, void* red, cudaStream_t s, bool use_tc, int* errflag, bool use_td = false,
-                                PassProfile* prof = nullptr) {
+cudaError_t dispatch_tiled_pass(const TiledPassArgs& a, void* red, cudaStream_t s, bool use_tc, int* errflag, bool use_td = false) {
     const int kt = resident_template_k(a.k);
     if (use_tc) {
-        if (prof) prof->begin(s);
         cudaError_t e = launch_tc_pass(a, errflag, s);
-        if (prof) prof->end(s);
         if (e != cudaSuccess || a.partial == nullptr) return e;
         return dispatch_tiled_combine<TX, TC>(a, red, s);
     }
     if (use_td) {
-        if (prof) prof->begin(s);
         cudaError_t e = launch_tiled_dmma_pass(a, s);
-        if (prof) prof->end(s);
         if (e != cudaSuccess || a.partial == nullptr) return e;
         return dispatch_tiled_combine<TX, TC>(a, red, s);
     }
     NMFK_DISPATCH_K(launch_tiled_pass_k, TX, TC, kt, a, red, s)
+}
+// the same, bracketed by the profile events (one "launch" = the pass kernel, plus the small slice-combine kernel when the
+// reduction range is sliced)
+template <typename TX, typename TC>
+cudaError_t timed_tiled_pass(const TiledPassArgs& a, void* red, cudaStream_t s, bool use_tc, int* errflag, bool use_td,
+                             PassProfile* prof) {
+    if (prof) prof->begin(s);
+    const cudaError_t e = dispatch_tiled_pass<TX, TC>(a, red, s, use_tc, errflag, use_td);
+    if (prof) prof->end(s);
+    return e;
 }
 template <typename TX, typename TC>
 cudaError_t dispatch_tiled_apply(const TiledPassArgs& a, void* red, cudaStream_t s) {
@@ -799,7 +804,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
             if (!a.Hfixed) {
                 tiled_sums_kernel<TC><<<dim3(k, R), 256, 0, s>>>(a.W, (long long)n * k, 1, n, n, a.st, den);
                 NMFK_TRY(cudaGetLastError());
-                NMFK_TRY((dispatch_tiled_pass<TX, TC>(ph, red, s, use_tc, h_active + 1, use_td, a.prof)));
+                NMFK_TRY((timed_tiled_pass<TX, TC>(ph, red, s, use_tc, h_active + 1, use_td, a.prof)));
                 *launches += 2 + (SH > 1 || sharded);
                 if (d_trace != nullptr) {
                     std::vector<long long> ht(3 * 64 * 8);
@@ -823,7 +828,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
             if (!a.Wfixed) {
                 tiled_sums_kernel<TC><<<dim3(k, R), 256, 0, s>>>(a.H, (long long)k * m, k, 1, m, a.st, den);
                 NMFK_TRY(cudaGetLastError());
-                NMFK_TRY((dispatch_tiled_pass<TX, TC>(pw, nullptr, s, use_tc, h_active + 1, use_td, a.prof)));
+                NMFK_TRY((timed_tiled_pass<TX, TC>(pw, nullptr, s, use_tc, h_active + 1, use_td, a.prof)));
                 *launches += 2 + (SW > 1);
             }
             if (a.has_nan) {
