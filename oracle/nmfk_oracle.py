@@ -288,6 +288,73 @@ def nmf_multiplicative_darray(
 
 
 # --------------------------------------------------------------------------------------
+# Variant FRO: method=:nmf, algorithm=:multdiv (src/NMFkExecute.jl:763-766) -> NMF.MultUpdate(obj=:mse)
+# --------------------------------------------------------------------------------------
+def nmf_multupdate_mse(
+    X: np.ndarray,
+    k: int,
+    *,
+    Winit: np.ndarray,
+    Hinit: np.ndarray,
+    maxiter: int = 10000,
+    tol: float = 1e-19,
+    lambda_w: float = 0.0,
+    lambda_h: float = 0.0,
+    delta: Optional[float] = None,
+    trace: Optional[Callable[[int, np.ndarray, np.ndarray], None]] = None,
+    info: Optional[dict] = None,
+):
+    """The Frobenius ("mse") multiplicative update of the third-party package NMF.jl (compat "0.4-1", Project.toml:85; NOT
+    vendored under /root/reference - restated from the published source `src/multupd.jl` + `src/common.jl`, unpinned), which
+    the reference reaches at src/NMFkExecute.jl:763-766 (`NMF.solve!(NMF.MultUpdate{T}(obj=:mse, maxiter, tol), X, W, H)`; the
+    reference's keyword for it is algorithm=:multdiv).  It is the update BASELINE.json's north star writes out:
+        H <- H .* (W'X)  ./ (W'W*H  + lambda_h + delta)        delta = sqrt(eps(T))
+        W <- W .* (X*H') ./ (W*H*H' + lambda_w + delta)        (with the new H)
+    until every column of W and every row of H moved by less than `tol` relative (NMF.jl `stop_condition`:
+    sqrt(sum((new-old)^2)) <= tol * sqrt(sum((new+old)^2)) for all of them) or `maxiter` iterations.  In the reference the
+    initial factors come from NMF.randinit; here they are injected.  Computes in the dtype of the inputs (pass Float64 copies
+    for a Float64 oracle of Float32 data; `delta` then still has to be sqrt(eps(Float32)), hence the argument).
+    Returns (W, H, objvalue = sum((X - W*H)^2), the package's `sqL2dist`)."""
+    W = np.array(Winit, copy=True)
+    H = np.array(Hinit, copy=True)
+    if delta is None:
+        delta = float(np.sqrt(np.finfo(X.dtype).eps))
+    iters, converged = 0, False
+    while not converged and iters < maxiter:
+        iters += 1
+        preW, preH = W.copy(), H.copy()
+        WtX = W.T @ X
+        WtWH = (W.T @ W) @ H
+        H *= WtX / (WtWH + (lambda_h + delta))
+        XHt = X @ H.T
+        WHHt = W @ (H @ H.T)
+        W *= XHt / (WHHt + (lambda_w + delta))
+        dw = np.sqrt(np.sum((W - preW) ** 2, axis=0))
+        sw = np.sqrt(np.sum((W + preW) ** 2, axis=0))
+        dh = np.sqrt(np.sum((H - preH) ** 2, axis=1))
+        sh = np.sqrt(np.sum((H + preH) ** 2, axis=1))
+        converged = not (np.any(dw > tol * sw) or np.any(dh > tol * sh))
+        if trace is not None:
+            trace(iters, W, H)
+    if info is not None:
+        info.update(iters=iters, converged=converged, stop_reason="tol" if converged else "maxiter")
+    return W, H, float(np.sum((X - W @ H) ** 2))
+
+
+def execute_singlerun_nmf(X: np.ndarray, nk: int, *, Winit, Hinit, maxiter: int = 10000, tol: float = 1e-19,
+                          modifymatrices: bool = True, info: Optional[dict] = None, delta: Optional[float] = None):
+    """`execute_singlerun_compute(X, nk; method=:nmf, algorithm=:multdiv)` src/NMFkExecute.jl:763-775, 787-805: the solver
+    above, then objvalue = normnan(X - W*H) and the H-row normalisation like every other method."""
+    W, H, _ = nmf_multupdate_mse(X, nk, Winit=Winit, Hinit=Hinit, maxiter=maxiter, tol=tol, delta=delta, info=info)
+    objvalue = normnan(X - W @ H)
+    if modifymatrices:
+        total = np.sum(H, axis=1, keepdims=True)
+        W = W * total.T
+        H = H / total
+    return W, H, objvalue
+
+
+# --------------------------------------------------------------------------------------
 # One restart as reached from execute: src/NMFkExecute.jl:729-807
 # --------------------------------------------------------------------------------------
 def execute_singlerun_compute(
