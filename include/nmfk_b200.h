@@ -274,6 +274,22 @@ int32_t nmfk_sweep(nmfk_ctx* ctx, const int32_t* ks, int32_t nks, int32_t R_loca
                    void* const* H_out, double* fitquality, double* robustness, double* aic, int32_t* kopt, int64_t* total_iters,
                    int64_t* total_iters_local);
 
+/* ---- robustkmeans(X, k, repeats; maxiter=1000, tol=1e-32, distance=CosineDist(), compute_silhouettes_flag)
+ *      (NMFkCluster.jl:172-246; the k-means + silhouette step postprocess runs on W[kopt], H[kopt]) ------------------------------
+ * X: d x N column-major Float64, the POINTS ARE THE COLUMNS (Clustering.kmeans convention).  `repeats` runs of Lloyd k-means with
+ * cosine distance execute concurrently on the device (Clustering.jl `kmeans` restated; see csrc/kmeans.cu); the first run with
+ * the smallest total cost is kept (:219-225), its silhouettes are Clustering.silhouettes on pairwise(CosineDist(),
+ * zerostoepsilon(X)) (:195-218), and the result is relabelled by sortclustering (:264-289: clusters ranked by size).
+ * seeds: k x repeats 0-based point indices - the k-means++ seeding draws from Julia's RNG in the reference and is the caller's
+ * job here (the host mirrors implement it).  Outputs (any may be NULL): assignments N (1-based, sorted labels), centers d x k,
+ * costs N, counts k, totalcost, iterations, converged of the best run; best_silhouettes N; *best_repeat (0-based);
+ * *empty_cluster_repeats = runs in which a cluster lost all its points (the package re-draws such a centre at random; here it
+ * keeps its position). */
+int32_t nmfk_robustkmeans(nmfk_ctx* ctx, const double* X, int32_t d, int32_t N, int32_t k, int32_t repeats, const int32_t* seeds,
+                          int32_t maxiter, double tol, int32_t compute_silhouettes, int32_t* assignments, double* centers, double* costs,
+                          int32_t* counts, double* totalcost, int32_t* iterations, int32_t* converged, double* best_silhouettes,
+                          int32_t* best_repeat, int32_t* empty_cluster_repeats);
+
 /* getk (NMFkPostprocess.jl:7-41): returns k, 0 (all NaN) or -1 (nothing). */
 int32_t nmfk_getk(const int32_t* ks, const double* robustness, int32_t nks, double cutoff, int32_t strict);
 /* signalorder (NMFkPostprocess.jl:148-158) on host buffers; order is 0-based. */
@@ -295,6 +311,11 @@ double nmfk_last_solve_ms(const nmfk_ctx* ctx);
  *        3 = device-to-device copy GB/s (read+write bytes), 13 = dense tcgen05.mma kind::tf32 TFLOP/s (M = 128, N = 256,
  *        K = 8 from shared memory on every SM; the 3-term split of the Float32 kernels runs at a third of it) */
 int32_t nmfk_measure_peak(nmfk_ctx* ctx, int32_t which, double* value);
+/* The stacked-restart GEMM of Variant FRO on its own (test / measurement hook; no reference counterpart beyond BLAS gemm):
+ * C[M x N] = A[M x K] * B[N x K]^T, all row-major host buffers.  Float32: tcgen05.mma kind::tf32 with the 3-term split, operands
+ * staged by TMA tensor maps (N and K multiples of 4); Float64: DMMA.  *ms: average device time of `reps` launches. */
+int32_t nmfk_gemm_nt(nmfk_ctx* ctx, int32_t dtype, const void* A, const void* B, int32_t M, int32_t N, int32_t K, void* C,
+                     int32_t reps, double* ms);
 /* Device self-test of the tcgen05 / tensor-memory building blocks of the Float32 tiled engine (no reference
  * counterpart): U 128x16, V 64x16 row-major; mode bits: 1 P=UV' (A,B shared), 2 P (A tensor memory),
  * 4 / 8 ACC = 0.5 P V with the 2-term TF32 split of the A operand (B K-major copy / B MN-major alias). */

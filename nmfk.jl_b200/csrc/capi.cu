@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/nmfk_b200.h"
+#include "fro.h"
 #include "nmfk_internal.h"
 #include "philox.h"
 
@@ -57,6 +58,9 @@ struct nmfk_ctx {
     void* wrow = nullptr;
     void* wcol = nullptr;
     void* wmat = nullptr;
+    // Variant FRO, Float32: lo images (x - tf32(x)) of Xp / Xpt for the 3-term split, built at the first FRO solve
+    void* Xlo = nullptr;
+    void* Xtlo = nullptr;
     // persistent device scratch of the clustering phase (grown on demand, never shrunk)
     void* scratch = nullptr;
     size_t scratch_cap = 0;
@@ -136,7 +140,7 @@ struct DevBuf {
 };
 
 void free_X(nmfk_ctx* c) {
-    for (void** q : {&c->Xp, &c->Xpt, &c->Xn, &c->Xnt, &c->nv, &c->wrow, &c->wcol, &c->wmat}) {
+    for (void** q : {&c->Xp, &c->Xpt, &c->Xn, &c->Xnt, &c->nv, &c->wrow, &c->wcol, &c->wmat, &c->Xlo, &c->Xtlo}) {
         if (*q) cudaFree(*q);
         *q = nullptr;
     }
@@ -718,6 +722,40 @@ static int32_t finish_normalizevector(nmfk_batch* b, const nmfk_params* p) {
     return NMFK_OK;
 }
 
+// Variant FRO (method=:nmf, algorithm=:multdiv; NMFkExecute.jl:763-766): stacked-restart GEMMs, one batch after the other
+static int32_t solve_fro_batches(nmfk_ctx* c, nmfk_batch* const* batches, int32_t nb, const nmfk_params* p) {
+    if (c->info.nnan > 0) return fail(c, NMFK_E_UNSUPPORTED, "variant FRO: X holds NaN (NMF.jl's MultUpdate has no missing-data handling)");
+    if (c->sharded || c->Xn || c->wrow || c->wcol || c->wmat)
+        return fail(c, NMFK_E_UNSUPPORTED, "variant FRO: row-sharded X, normalizevector and array weights are not available");
+    if (p->stop_rule != 0) return fail(c, NMFK_E_UNSUPPORTED, "variant FRO has its own stop rule (NMF.jl stop_condition)");
+    if (c->dtype == NMFK_F32) {
+        if (!fro_gemm_supported(c->m, c->n) || !fro_gemm_supported(c->n, c->m))
+            return fail(c, NMFK_E_UNSUPPORTED, "variant FRO (Float32): row and column counts must be multiples of 4 (TMA strides) and "
+                                               "the driver must provide cuTensorMapEncodeTiled");
+        if (!c->Xlo) {
+            const size_t bytes = (size_t)c->n * c->m * sizeof(float);
+            CU(c, cudaMalloc(&c->Xlo, bytes));
+            CU(c, cudaMalloc(&c->Xtlo, bytes));
+            CU(c, launch_split_lo((const float*)c->Xp, (float*)c->Xlo, (long long)c->n * c->m, c->stream));
+            CU(c, launch_split_lo((const float*)c->Xpt, (float*)c->Xtlo, (long long)c->n * c->m, c->stream));
+            c->launches += 2;
+        }
+    }
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < nb; ++i) {
+        if (batches[i]->k > 32) return fail(c, NMFK_E_UNSUPPORTED, "variant FRO: k > 32 is not supported");
+        SolveArgs a;
+        fill_args(batches[i], p, a);
+        CU(c, solve_fro(a, c->dtype, c->Xlo, c->Xtlo, c->stream, &c->launches));
+    }
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    CU(c, cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_solve_ms = ms;
+    return NMFK_OK;
+}
+
 int32_t nmfk_solve(nmfk_ctx* c, nmfk_batch* const* batches, int32_t nb, const nmfk_params* p) {
     if (!c || !batches || nb < 1) return fail(c, NMFK_E_INVALID, "nmfk_solve: bad arguments");
     int32_t rc = check_params(c, p);
@@ -728,6 +766,7 @@ int32_t nmfk_solve(nmfk_ctx* c, nmfk_batch* const* batches, int32_t nb, const nm
         if (!batches[i]->inited) return fail(c, NMFK_E_INVALID, "nmfk_solve: batch has no initialisation");
         if (!batches[i]->W || !batches[i]->canon) return fail(c, NMFK_E_INVALID, "nmfk_solve: H-only batch");
     }
+    if (p->variant == NMFK_VARIANT_FRO) return solve_fro_batches(c, batches, nb, p);
     while ((int)c->pool.size() < nb) {
         cudaStream_t s;
         cudaEvent_t ev;
@@ -1540,6 +1579,155 @@ int32_t nmfk_measure_peak(nmfk_ctx* c, int32_t which, double* value) {
     if (!c || !value) return fail(c, NMFK_E_INVALID, "nmfk_measure_peak: NULL argument");
     CU(c, cudaSetDevice(c->device));
     CU(c, measure_peak(which, value, c->stream));
+    return NMFK_OK;
+}
+
+// robustkmeans(X, k, repeats; ...) (NMFkCluster.jl:172-246): the repeats run concurrently on the device, the host keeps the
+// first repeat with the smallest total cost (:219-225), computes its silhouettes and applies sortclustering (:264-289).
+int32_t nmfk_robustkmeans(nmfk_ctx* c, const double* X, int32_t d, int32_t N, int32_t k, int32_t repeats, const int32_t* seeds,
+                          int32_t maxiter, double tol, int32_t compute_silhouettes, int32_t* assignments, double* centers, double* costs,
+                          int32_t* counts, double* totalcost, int32_t* iterations, int32_t* converged, double* best_silhouettes,
+                          int32_t* best_repeat, int32_t* empty_cluster_repeats) {
+    if (!c || !X || !seeds || d < 1 || N < 1 || k < 1 || repeats < 1 || maxiter < 0)
+        return fail(c, NMFK_E_INVALID, "nmfk_robustkmeans: bad arguments");
+    if (k >= N) return fail(c, NMFK_E_INVALID, "nmfk_robustkmeans: k must be smaller than the number of points (NMFkCluster.jl:139-142)");
+    for (long long e = 0; e < (long long)k * repeats; ++e)
+        if (seeds[e] < 0 || seeds[e] >= N) return fail(c, NMFK_E_INVALID, "nmfk_robustkmeans: seed index out of range");
+    CU(c, cudaSetDevice(c->device));
+    DevBuf dX, dxn, dseeds, dassign, dcosts, dcounts, dcent, dtc, dit, dfl;
+    CU(c, dX.alloc((size_t)d * N * 8));
+    CU(c, dxn.alloc((size_t)N * 8));
+    CU(c, dseeds.alloc((size_t)k * repeats * 4));
+    CU(c, dassign.alloc((size_t)repeats * N * 4));
+    CU(c, dcosts.alloc((size_t)repeats * N * 8));
+    CU(c, dcounts.alloc((size_t)repeats * k * 4));
+    CU(c, dcent.alloc((size_t)repeats * d * k * 8));
+    CU(c, dtc.alloc((size_t)repeats * 8));
+    CU(c, dit.alloc((size_t)repeats * 4));
+    CU(c, dfl.alloc((size_t)repeats * 4));
+    CU(c, cudaMemcpyAsync(dX.p, X, (size_t)d * N * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(dseeds.p, seeds, (size_t)k * repeats * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, launch_kmeans(dX.as<double>(), dxn.as<double>(), d, N, k, repeats, dseeds.as<int>(), maxiter, tol, dassign.as<int>(),
+                        dcosts.as<double>(), dcounts.as<int>(), dcent.as<double>(), dtc.as<double>(), dit.as<int>(), dfl.as<int>(),
+                        c->stream));
+    c->launches += 2;
+    std::vector<double> tc((size_t)repeats);
+    std::vector<int32_t> its((size_t)repeats), fl((size_t)repeats);
+    CU(c, cudaMemcpyAsync(tc.data(), dtc.p, (size_t)repeats * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(its.data(), dit.p, (size_t)repeats * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(fl.data(), dfl.p, (size_t)repeats * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    int best = 0, nempty = 0;
+    for (int i = 0; i < repeats; ++i) {  // `if i == 1 || c_new.totalcost < best_totalcost` (:219)
+        if (i > 0 && tc[i] < tc[best]) best = i;
+        nempty += (fl[i] >> 1) & 1;
+    }
+    std::vector<int32_t> as((size_t)N), cnt((size_t)k);
+    std::vector<double> cst((size_t)N), cen((size_t)d * k), sil((size_t)N, 0.0);
+    CU(c, cudaMemcpyAsync(as.data(), dassign.as<int>() + (size_t)best * N, (size_t)N * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(cst.data(), dcosts.as<double>() + (size_t)best * N, (size_t)N * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(cnt.data(), dcounts.as<int>() + (size_t)best * k, (size_t)k * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(cen.data(), dcent.as<double>() + (size_t)best * d * k, (size_t)d * k * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (compute_silhouettes && best_silhouettes) {
+        int maxa = 0;
+        for (int v : as) maxa = std::max(maxa, v);
+        if (maxa > 1) {  // `if maximum(c_new.assignments) > 1` (:208-214); otherwise the silhouettes stay zero
+            // Xn = zerostoepsilon(X); Xd = pairwise(CosineDist(), Xn; dims=2); silhouettes(c_new, Xd)
+            const int ld = d + 1;
+            DevBuf dV, dvn, dD, dsil;
+            CU(c, dV.alloc((size_t)N * ld * 8));
+            CU(c, dvn.alloc((size_t)N * 8));
+            CU(c, dD.alloc((size_t)N * N * 8));
+            CU(c, dsil.alloc((size_t)N * 8));
+            CU(c, cudaMemcpy2DAsync(dV.p, (size_t)ld * 8, dX.p, (size_t)d * 8, (size_t)d * 8, (size_t)N, cudaMemcpyDeviceToDevice, c->stream));
+            const double eps = 2.220446049250313e-16;
+            CU(c, launch_point_silhouettes(dV.as<double>(), d, ld, N, k, dassign.as<int>() + (size_t)best * N, eps * eps, dvn.as<double>(),
+                                           dD.as<double>(), dsil.as<double>(), c->stream));
+            c->launches += 3;
+            CU(c, cudaMemcpyAsync(sil.data(), dsil.p, (size_t)N * 8, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+        }
+        std::copy(sil.begin(), sil.end(), best_silhouettes);
+    }
+    // sortclustering(c::KmeansResult) (:264-289): clusters relabelled by first appearance, then ranked by size (stable, descending)
+    std::vector<int> first;  // j = unique(c.assignments)
+    std::vector<int> pos((size_t)k + 1, -1);
+    for (int v : as)
+        if (pos[v] < 0) {
+            pos[v] = (int)first.size();
+            first.push_back(v);
+        }
+    std::vector<int> rank(first.size());
+    std::iota(rank.begin(), rank.end(), 0);
+    std::stable_sort(rank.begin(), rank.end(), [&](int x, int y) { return cnt[first[x] - 1] > cnt[first[y] - 1]; });
+    std::vector<int> newlabel(first.size());
+    for (size_t q = 0; q < rank.size(); ++q) newlabel[rank[q]] = (int)q + 1;
+    if (assignments)
+        for (int j = 0; j < N; ++j) assignments[j] = newlabel[pos[as[j]]];
+    // centers[:, r], counts[r] with r = j[i]: only the clusters that appear (the reference drops empty ones here)
+    if (counts) std::fill(counts, counts + k, 0);
+    if (centers) std::fill(centers, centers + (size_t)d * k, 0.0);
+    for (size_t q = 0; q < rank.size(); ++q) {
+        const int old = first[rank[q]] - 1;
+        if (counts) counts[q] = cnt[old];
+        if (centers) std::copy(cen.begin() + (size_t)old * d, cen.begin() + (size_t)(old + 1) * d, centers + q * d);
+    }
+    if (costs) std::copy(cst.begin(), cst.end(), costs);
+    if (totalcost) *totalcost = tc[best];
+    if (iterations) *iterations = its[best];
+    if (converged) *converged = fl[best] & 1;
+    if (best_repeat) *best_repeat = best;
+    if (empty_cluster_repeats) *empty_cluster_repeats = nempty;
+    return NMFK_OK;
+}
+
+// The stacked-restart GEMM of Variant FRO on its own (test / measurement hook): C[M x N] = A[M x K] B[N x K]^T, row-major host
+// buffers; Float32 = tcgen05 kind::tf32 with the 3-term split (TMA tensor maps), Float64 = DMMA.  *ms = average device time of
+// `reps` launches (CUDA events on the ctx stream).
+int32_t nmfk_gemm_nt(nmfk_ctx* c, int32_t dtype, const void* A, const void* B, int32_t M, int32_t N, int32_t K, void* Cout,
+                     int32_t reps, double* ms) {
+    if (!c || !A || !B || !Cout || M < 1 || N < 1 || K < 1 || reps < 1) return fail(c, NMFK_E_INVALID, "nmfk_gemm_nt: bad arguments");
+    if (dtype != NMFK_F32 && dtype != NMFK_F64) return fail(c, NMFK_E_INVALID, "nmfk_gemm_nt: bad dtype");
+    if (dtype == NMFK_F32 && !fro_gemm_supported(N, K)) return fail(c, NMFK_E_UNSUPPORTED, "nmfk_gemm_nt (Float32): N and K must be multiples of 4");
+    CU(c, cudaSetDevice(c->device));
+    const size_t es = esize(dtype);
+    DevBuf dA, dB, dC, dAlo, dBlo, derr;
+    CU(c, dA.alloc((size_t)M * K * es));
+    CU(c, dB.alloc((size_t)N * K * es));
+    const int S = dtype == NMFK_F32 ? fro_gemm_slices(M, N, K) : 1;  // split-K partial products side by side, summed in order
+    CU(c, dC.alloc((size_t)S * M * N * es));
+    CU(c, derr.alloc(sizeof(int)));
+    CU(c, cudaMemsetAsync(derr.p, 0, sizeof(int), c->stream));
+    CU(c, cudaMemcpyAsync(dA.p, A, (size_t)M * K * es, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(dB.p, B, (size_t)N * K * es, cudaMemcpyHostToDevice, c->stream));
+    if (dtype == NMFK_F32) {
+        CU(c, dAlo.alloc((size_t)M * K * es));
+        CU(c, dBlo.alloc((size_t)N * K * es));
+        CU(c, launch_split_lo(dA.as<float>(), dAlo.as<float>(), (long long)M * K, c->stream));
+        CU(c, launch_split_lo(dB.as<float>(), dBlo.as<float>(), (long long)N * K, c->stream));
+    }
+    auto launch = [&]() -> cudaError_t {
+        if (dtype == NMFK_F32) {
+            cudaError_t e = launch_fro_gemm(dA.as<float>(), dAlo.as<float>(), K, dB.as<float>(), dBlo.as<float>(), K, dC.as<float>(), N, M, N,
+                                            K, S, (long long)M * N, derr.as<int>(), c->stream);
+            return e != cudaSuccess ? e : launch_sum_slices(dC.as<float>(), S, (long long)M * N, (long long)M * N, c->stream);
+        }
+        return launch_fro_gemm_f64(dA.as<double>(), K, dB.as<double>(), K, dC.as<double>(), N, M, N, K, c->stream);
+    };
+    CU(c, launch());  // warm-up (and the launch whose result is returned when reps == 1)
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; ++i) CU(c, launch());
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    CU(c, cudaEventSynchronize(c->ev1));
+    float t = 0.f;
+    CU(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
+    c->launches += reps + 1;
+    if (ms) *ms = (double)t / reps;
+    int herr = 0;
+    CU(c, cudaMemcpy(&herr, derr.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (herr) return fail(c, NMFK_E_INVALID, "nmfk_gemm_nt: barrier time-out inside fro_gemm_kernel (site " + std::to_string(herr) + ")");
+    CU(c, cudaMemcpy(Cout, dC.p, (size_t)M * N * es, cudaMemcpyDeviceToHost));
     return NMFK_OK;
 }
 

@@ -369,6 +369,22 @@ cudaError_t launch_cluster_means(const void* F, int len, int k, int R, int use_W
     return cudaGetLastError();
 }
 
+// silhouettes of N labelled points (robustkmeans, NMFkCluster.jl:195-218): V = the points as rows (N x ld doubles, floored in
+// place like zerostoepsilon), Dm = pairwise cosine distances, sil = Clustering.silhouettes(labels, Dm)
+cudaError_t launch_point_silhouettes(double* V, int len, int ld, int N, int k, const int* labels, double floorv, double* vnorm, double* Dm,
+                                     double* sil, cudaStream_t s) {
+    cudaError_t e;
+    floor_norm_kernel<<<(N + 7) / 8, 256, 0, s>>>(V, len, ld, N, floorv, vnorm);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    dim3 grid((N + 63) / 64, (N + 63) / 64);
+    cosine_gram_kernel<<<grid, 256, 0, s>>>(V, len, ld, N, vnorm, Dm);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    const int NT = 128;
+    const size_t smem = (size_t)k * NT * sizeof(double) + (size_t)k * sizeof(int);
+    silhouette_kernel<<<(N + NT - 1) / NT, NT, smem, s>>>(Dm, N, k, labels, sil);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_cluster(const ClusterArgs& a, int dtype, cudaStream_t s) {
     const int N = a.R * a.k, ld = a.len + 1;
     cudaError_t e;

@@ -27,6 +27,8 @@
 // The element-wise halves of the update (Gram matrices, H .*= N1 ./ (G*H + d), convergence sums) are fro_solve.cu.
 #include <cuda.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
@@ -115,7 +117,7 @@ template <int CLUSTER>
 __global__ void __launch_bounds__(THREADS, 1)
     fro_gemm_kernel(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
                     const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo, float* __restrict__ Cout,
-                    int M, int N, int K, long long ldc, int* errflag) {
+                    int M, int N, int K, long long ldc, int S, long long pstride, int* errflag) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
@@ -154,20 +156,29 @@ __global__ void __launch_bounds__(THREADS, 1)
     const uint32_t tbase = *tmem_slot;
 
     const int mtiles = (M + BM - 1) / BM, ntiles = (N + BN - 1) / BN;
-    const int kblocks = (K + BK - 1) / BK;
-    const int nchunks = (kblocks + CHUNK - 1) / CHUNK;
-    // tiles: M index fastest, so that the CTAs running at the same time read the same rows of B (= X) through L2; a cluster
-    // takes CLUSTER neighbouring M tiles of one N tile
+    const int kblocks_all = (K + BK - 1) / BK;
+    // work item = (M tile group, K slice, N tile), M index fastest: the CTAs running at the same time read the same rows and
+    // the same K range of B (= X) through L2; a cluster takes CLUSTER neighbouring M tiles.  The K range is cut in S slices
+    // (split-K) when the tiles alone cannot fill the SMs evenly; slice s writes its partial product to Cout + s * pstride and
+    // the consumer (fro_apply_kernel) adds the slices in order.
     const int mgroups = (mtiles + CLUSTER - 1) / CLUSTER;
-    const int ngroupsTotal = mgroups * ntiles;
+    const int ngroupsTotal = mgroups * S * ntiles;
     const int cluster_id = blockIdx.x / CLUSTER, nclusters = gridDim.x / CLUSTER;
+    auto item = [&](int g, int& m0, int& n0, int& kb0, int& kb1, int& sl) {
+        m0 = ((g % mgroups) * CLUSTER + (int)crank) * BM;
+        sl = (g / mgroups) % S;
+        n0 = (g / (mgroups * S)) * BN;
+        kb0 = (int)((long long)kblocks_all * sl / S);
+        kb1 = (int)((long long)kblocks_all * (sl + 1) / S);
+    };
 
     if (warp == 0) {
         // ===== TMA producer =====
         uint32_t it = 0;
         for (int g = cluster_id; g < ngroupsTotal; g += nclusters) {
-            const int m0 = ((g % mgroups) * CLUSTER + (int)crank) * BM, n0 = (g / mgroups) * BN;
-            for (int kb = 0; kb < kblocks; ++kb, ++it) {
+            int m0, n0, kb0, kb1, sl;
+            item(g, m0, n0, kb0, kb1, sl);
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 tc::mbar_wait(&empty[s], ph ^ 1, errflag, 1);
@@ -194,12 +205,15 @@ __global__ void __launch_bounds__(THREADS, 1)
         const uint32_t idesc = tc::idesc_tf32(BM, BN, 0);
         uint32_t it = 0, chunk_no = 0;
         for (int g = cluster_id; g < ngroupsTotal; g += nclusters) {
+            int m0, n0, kb0, kb1, sl;
+            item(g, m0, n0, kb0, kb1, sl);
+            const int nchunks = (kb1 - kb0 + CHUNK - 1) / CHUNK;
             for (int c = 0; c < nchunks; ++c, ++chunk_no) {
                 const int buf = chunk_no & 1;
                 tc::mbar_wait(&acc_empty[buf], ((chunk_no >> 1) & 1) ^ 1, errflag, 2);
                 tc::tc_fence_after_sync();
-                const int kb_end = min(kblocks, (c + 1) * CHUNK);
-                for (int kb = c * CHUNK; kb < kb_end; ++kb, ++it) {
+                const int kb_begin = kb0 + c * CHUNK, kb_end = min(kb1, kb_begin + CHUNK);
+                for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
                     const int s = it % STAGES;
                     tc::mbar_wait(&full[s], (it / STAGES) & 1, errflag, 3);
                     tc::tc_fence_after_sync();
@@ -211,7 +225,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
                         for (int kk = 0; kk < BK / 8; ++kk) {
                             const uint64_t off = (uint64_t)(kk * 2);  // 8 floats = 32 bytes along K inside the swizzle row
-                            tc::mma_tf32_ss(d, alo + off, bhi + off, idesc, (kb > c * CHUNK || kk > 0) ? 1u : 0u);
+                            tc::mma_tf32_ss(d, alo + off, bhi + off, idesc, (kb > kb_begin || kk > 0) ? 1u : 0u);
                             tc::mma_tf32_ss(d, ahi + off, blo + off, idesc, 1u);
                             tc::mma_tf32_ss(d, ahi + off, bhi + off, idesc, 1u);
                         }
@@ -234,7 +248,9 @@ __global__ void __launch_bounds__(THREADS, 1)
         float acc[BN / 2];
         uint32_t chunk_no = 0;
         for (int g = cluster_id; g < ngroupsTotal; g += nclusters) {
-            const int m0 = ((g % mgroups) * CLUSTER + (int)crank) * BM, n0 = (g / mgroups) * BN;
+            int m0, n0, kb0, kb1, sl;
+            item(g, m0, n0, kb0, kb1, sl);
+            const int nchunks = (kb1 - kb0 + CHUNK - 1) / CHUNK;
 #pragma unroll
             for (int j = 0; j < BN / 2; ++j) acc[j] = 0.f;
             for (int c = 0; c < nchunks; ++c, ++chunk_no) {
@@ -255,7 +271,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             }
             const int row = m0 + quarter * 32 + lane;
             if (row < M) {
-                float* dst = Cout + (long long)row * ldc + n0 + half * (BN / 2);
+                float* dst = Cout + (long long)sl * pstride + (long long)row * ldc + n0 + half * (BN / 2);
                 const int ncols = min(BN / 2, N - (n0 + half * (BN / 2)));
                 if (ncols == BN / 2 && (ldc & 3) == 0) {
 #pragma unroll
@@ -280,23 +296,53 @@ __global__ void __launch_bounds__(THREADS, 1)
 
 bool fro_gemm_supported(long long N, long long K) { return encode_fn() != nullptr && (K % 4) == 0 && (N % 4) == 0 && K >= 4; }
 
+static int fro_cluster(int M) {
+    static int cluster_env = -1;
+    if (cluster_env < 0) cluster_env = getenv("NMFK_FRO_CLUSTER") ? atoi(getenv("NMFK_FRO_CLUSTER")) : 2;
+    return (cluster_env == 2 && (M + BM - 1) / BM >= 2) ? 2 : 1;
+}
+
+// K slices (split-K) of the stacked GEMM: the tile count alone rarely fills the 148 SMs evenly (C3: 8 x 40 tiles = 2.16 waves,
+// 72 % of the last wave idle; C5's H-update: 6 x 4 tiles for 148 SMs) while K is long.  Picks the slice count with the best
+// wave efficiency, charging 1.5 % per extra slice for the partial products the consumer has to add.
+int fro_gemm_slices(int M, int N, int K) {
+    if (getenv("NMFK_FRO_SLICES")) return std::max(1, atoi(getenv("NMFK_FRO_SLICES")));
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int cluster = fro_cluster(M);
+    const int mtiles = (M + BM - 1) / BM, ntiles = (N + BN - 1) / BN, kblocks = (K + BK - 1) / BK;
+    const double groups = (double)((mtiles + cluster - 1) / cluster) * ntiles, slots = (double)(sms / cluster);
+    int best = 1;
+    double best_score = -1.0;
+    for (int S = 1; S <= 64 && kblocks / S >= 2 * CHUNK; ++S) {
+        const double x = groups * S / slots;
+        const double score = x / std::ceil(x) - 0.015 * (S - 1);
+        if (score > best_score + 1e-9) {
+            best_score = score;
+            best = S;
+        }
+    }
+    return best;
+}
+
 // C[M x N] (row-major, leading dimension ldc) = A[M x K] B[N x K]^T with the 3-term TF32 split; A / B row-major with
 // leading dimensions lda / ldb (floats, multiples of 4), *lo = the x - tf32(x) images.
+// S > 1: slice s of the K range writes its partial product to C + s * pstride (floats); the consumer adds them in order.
 cudaError_t launch_fro_gemm(const float* Ahi, const float* Alo, long long lda, const float* Bhi, const float* Blo, long long ldb, float* C,
-                            long long ldc, int M, int N, int K, int* d_errflag, cudaStream_t s) {
-    static int cluster_env = -1;
-    if (cluster_env < 0) cluster_env = getenv("NMFK_FRO_CLUSTER") ? atoi(getenv("NMFK_FRO_CLUSTER")) : 1;
+                            long long ldc, int M, int N, int K, int S, long long pstride, int* d_errflag, cudaStream_t s) {
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int mtiles = (M + BM - 1) / BM, ntiles = (N + BN - 1) / BN;
-    const int cluster = (cluster_env == 2 && mtiles >= 2) ? 2 : 1;
+    const int cluster = fro_cluster(M);
+    if (S < 1) S = 1;
     CUtensorMap mAhi, mAlo, mBhi, mBlo;
     if (!make_map(&mAhi, Ahi, M, K, lda, BM) || !make_map(&mAlo, Alo, M, K, lda, BM) || !make_map(&mBhi, Bhi, N, K, ldb, BN / cluster) ||
         !make_map(&mBlo, Blo, N, K, ldb, BN / cluster))
         return cudaErrorInvalidValue;
     cudaError_t e;
-    const int groups = ((mtiles + cluster - 1) / cluster) * ntiles;
+    const int groups = ((mtiles + cluster - 1) / cluster) * ntiles * S;
     int grid = std::min(groups * cluster, sms / cluster * cluster);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
@@ -312,10 +358,10 @@ cudaError_t launch_fro_gemm(const float* Ahi, const float* Alo, long long lda, c
     cfg.numAttrs = 1;
     if (cluster == 2) {
         if ((e = cudaFuncSetAttribute(fro_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess) return e;
-        return cudaLaunchKernelEx(&cfg, fro_gemm_kernel<2>, mAhi, mAlo, mBhi, mBlo, C, M, N, K, ldc, d_errflag);
+        return cudaLaunchKernelEx(&cfg, fro_gemm_kernel<2>, mAhi, mAlo, mBhi, mBlo, C, M, N, K, ldc, S, pstride, d_errflag);
     }
     if ((e = cudaFuncSetAttribute(fro_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)) != cudaSuccess) return e;
-    return cudaLaunchKernelEx(&cfg, fro_gemm_kernel<1>, mAhi, mAlo, mBhi, mBlo, C, M, N, K, ldc, d_errflag);
+    return cudaLaunchKernelEx(&cfg, fro_gemm_kernel<1>, mAhi, mAlo, mBhi, mBlo, C, M, N, K, ldc, S, pstride, d_errflag);
 }
 
 }  // namespace nmfk

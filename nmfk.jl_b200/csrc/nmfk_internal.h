@@ -190,6 +190,13 @@ cudaError_t launch_zero_nan(void* p, long long len, int dtype, cudaStream_t s);
 cudaError_t launch_cluster_means(const void* F, int len, int k, int R, int use_W, const int32_t* d_order, const int32_t* d_amap,
                                  void* mean_out, void* var_out, int dtype, cudaStream_t s);
 
+cudaError_t launch_point_silhouettes(double* V, int len, int ld, int N, int k, const int* labels, double floorv, double* vnorm, double* Dm,
+                                     double* sil, cudaStream_t s);
+// robustkmeans: `repeats` Lloyd runs with cosine distance, one CTA each (kmeans.cu)
+cudaError_t launch_kmeans(const double* X, double* xnorm, int d, int N, int k, int repeats, const int* seeds, int maxiter, double tol,
+                          int* assign, double* costs, int* counts, double* centers, double* totalcost, int* iters, int* flags,
+                          cudaStream_t s);
+
 // micro-benchmarks
 cudaError_t measure_peak(int which, double* value, cudaStream_t s);
 // dense tcgen05.mma kind::tf32 throughput, TFLOP/s (tc_selftest.cu)

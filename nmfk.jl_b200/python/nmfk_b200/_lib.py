@@ -78,6 +78,8 @@ SIGNATURES = {
     "nmfk_ctx_sweep_comm_init": (_i32, [_P, _i32, _i32, _P]),
     "nmfk_sweep": (_i32, [_P, _pi32, _i32, _i32, C.POINTER(_P), C.POINTER(_P), _u64, C.POINTER(Params), _dbl,
                           C.POINTER(_P), C.POINTER(_P), _pdbl, _pdbl, _pdbl, _pi32, _pi64, _pi64]),
+    "nmfk_robustkmeans": (_i32, [_P, _pdbl, _i32, _i32, _i32, _i32, _pi32, _i32, _dbl, _i32, _pi32, _pdbl, _pdbl, _pi32, _pdbl,
+                                 _pi32, _pi32, _pdbl, _pi32, _pi32]),
     "nmfk_getk": (_i32, [_pi32, _pdbl, _i32, _dbl, _i32]),
     "nmfk_signalorder": (_i32, [_P, _P, _i64, _i32, _i64, _i32, _pi32]),
     "nmfk_launch_count": (_i64, [_P]),
@@ -85,6 +87,7 @@ SIGNATURES = {
     "nmfk_profile_enable": (_i32, [_P, _i32]),
     "nmfk_profile_get": (_i32, [_P, _pdbl, _pi64]),
     "nmfk_measure_peak": (_i32, [_P, _i32, _pdbl]),
+    "nmfk_gemm_nt": (_i32, [_P, _i32, _P, _P, _i32, _i32, _i32, _P, _i32, _pdbl]),
     "nmfk_umma_timing": (_i32, [_P, _P, _P, _i32, _P, _P]),
     "nmfk_umma_selftest": (_i32, [_P, _P, _P, _i32, _P, _P, _P, _P, _pi32]),
     "nmfk_philox_host": (_i32, [_u64, _i64, _pdbl]),

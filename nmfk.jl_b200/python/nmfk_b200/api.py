@@ -165,6 +165,20 @@ class Context:
         check(self._lib.nmfk_profile_get(self._h, C.byref(ms), C.byref(cnt)), self._h)
         return ms.value, cnt.value
 
+    def gemm_nt(self, A: np.ndarray, B: np.ndarray, reps: int = 1):
+        """C = A @ B.T with the stacked-restart GEMM of Variant FRO (nmfk_gemm_nt): A (M, K), B (N, K) C-contiguous, Float32
+        (tcgen05 3xTF32) or Float64 (DMMA).  -> (C (M, N), average device ms per launch)."""
+        dt = np.float32 if A.dtype == np.float32 else np.float64
+        A = np.ascontiguousarray(A, dtype=dt)
+        B = np.ascontiguousarray(B, dtype=dt)
+        M, K = A.shape
+        N = B.shape[0]
+        assert B.shape[1] == K
+        Cm = np.empty((M, N), dtype=dt)
+        ms = C.c_double()
+        check(self._lib.nmfk_gemm_nt(self._h, _DT[np.dtype(dt)], _ptr(A), _ptr(B), M, N, K, _ptr(Cm), int(reps), C.byref(ms)), self._h)
+        return Cm, ms.value
+
     def fit(self, W: np.ndarray, H: np.ndarray) -> float:
         """normnan(X - W*H) with NaN residuals zeroed (NMFkExecute.jl:664-668, :212-222) for host factors W (n,k), H (k,m)."""
         Wf, Hf = _f(W, self.np_dtype), _f(H, self.np_dtype)
@@ -311,6 +325,14 @@ def _params_from_kw(kw: dict, ctx: Optional[Context] = None, **defaults) -> Para
     NMFkMultiplicative.jl:24.  `weight`: a scalar travels in the parameters, an array (vector of length n, 1 x m, n x m;
     NMFkExecute.jl:484) is installed on the context."""
     vals = dict(defaults)
+    method = str(kw.pop("method", "simple")).lstrip(":")
+    algorithm = str(kw.pop("algorithm", "multdiv")).lstrip(":")
+    if method == "nmf":  # NMFkExecute.jl:763-775: NMF.jl solvers; :multdiv is MultUpdate(obj=:mse) = Variant FRO
+        if algorithm != "multdiv":
+            raise NMFkError(-6, "method=:nmf: only algorithm=:multdiv (NMF.MultUpdate(obj=:mse)) is on the B200 path")
+        vals["variant"] = 1
+    elif method != "simple":
+        raise NMFkError(-6, "method=:%s is not on the B200 path (method=:simple and method=:nmf, algorithm=:multdiv are)" % method)
     for k in list(kw):
         if k in _PARAM_NAMES:
             vals[k] = kw.pop(k)
@@ -488,11 +510,17 @@ def execute_run(X, nk: int, nNMF: int, *, clusterWmatrix: bool = False, seed: Op
             ctx.close()
 
 
-def execute_k(X, nk: int, nNMF: int = 10, *, ordersignals: bool = True, **kw):
-    """`NMFk.execute(X, nk::Integer, nNMF; ...)` NMFkExecute.jl:236-329 without the file cache (see nmfk_b200.cache for it):
-    -> (W[:, so], H[so, :], fitquality, robustness, aic)."""
+def execute_k(X, nk: int, nNMF: int = 10, *, ordersignals: bool = True, load: bool = False, save: bool = False, loadonly: bool = False,
+              resultdir: str = ".", casefilename: str = "nmfk", **kw):
+    """`NMFk.execute(X, nk::Integer, nNMF; ...)` NMFkExecute.jl:236-329 -> (W[:, so], H[so, :], fitquality, robustness, aic).
+    load / save / loadonly / resultdir / casefilename drive the result cache exactly like the reference (nmfk_b200.cache; the
+    reference defaults load = save = true, this mirror defaults them to false so that nothing is written unasked)."""
     if np.size(X) == 0:
         raise NMFkError(-7, "Input array has a zero dimension!")  # :242-244
+    if load or save or loadonly:
+        from . import cache
+        return cache.execute_k_cached(X, nk, nNMF, runner=execute_run, signalorder=signalorder, resultdir=resultdir,
+                                      casefilename=casefilename, loadonly=loadonly, load=load, save=save, ordersignals=ordersignals, **kw)
     if "Wfixed" in kw or "Hfixed" in kw:  # :305-307
         ordersignals = False
     W, H, fit, rob, aic = execute_run(X, nk, nNMF, **kw)
@@ -558,6 +586,88 @@ def execute(X, nkrange, nNMF: int = 10, *, cutoff: float = 0.5, seed: Optional[i
             details.update(total_iters=tot.value, solve_ms=ctx.last_solve_ms, launches=ctx.launches)
         ko = kopt.value
         return W, H, fitquality, robustness, aicv, (None if ko < 0 else ko)
+    finally:
+        if own:
+            ctx.close()
+
+
+class KmeansResult:
+    """The fields of Clustering.KmeansResult that robustkmeans returns (after sortclustering)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def kmeanspp_seeds(X: np.ndarray, k: int, rng: np.random.Generator) -> np.ndarray:
+    """k-means++ seeding as Clustering.kmeans does it by default (`initseeds(:kmpp, X, k)`: squared Euclidean costs whatever the
+    clustering distance): first seed uniform, the next ones sampled with probability proportional to the cost to the closest
+    seed so far.  The reference draws from Julia's RNG; here from `rng` (0-based point indices)."""
+    d, n = X.shape
+    seeds = np.empty(k, dtype=np.int32)
+    seeds[0] = rng.integers(n)
+    cost = np.sum((X - X[:, [seeds[0]]]) ** 2, axis=0)
+    for q in range(1, k):
+        tot = cost.sum()
+        seeds[q] = rng.choice(n, p=cost / tot) if tot > 0 else rng.integers(n)
+        cost = np.minimum(cost, np.sum((X - X[:, [seeds[q]]]) ** 2, axis=0))
+    return seeds
+
+
+def robustkmeans(X, k, repeats: int = 1000, *, maxiter: int = 1000, tol: float = 1e-32, compute_silhouettes_flag: bool = False,
+                 best_method: str = "worst_cliff", seed: Optional[int] = None, seeds=None, ctx: Context = None, details: Optional[dict] = None):
+    """`NMFk.robustkmeans(X, k, repeats; maxiter, tol, distance=CosineDist(), compute_silhouettes_flag)` NMFkCluster.jl:172-246 and,
+    with a range of k, :138-170 (best_method :worst_cliff / :worst_cluster_cliff).  X is d x N with the points in the COLUMNS.
+    All repeats run concurrently on the device (nmfk_robustkmeans); the k-means++ seeds come from NumPy's Philox(seed) here
+    (Julia's RNG in the reference) or explicitly as `seeds` (repeats, k).  -> KmeansResult, or (KmeansResult, silhouettes)
+    with compute_silhouettes_flag; None when the smallest k is not below the number of points (:139-142)."""
+    own = ctx is None
+    ctx = ctx or Context()
+    try:
+        X = np.asfortranarray(X, dtype=np.float64)
+        d, N = X.shape
+        if not isinstance(k, (int, np.integer)):
+            krange = [int(v) for v in k]
+            if krange[0] >= N:
+                return None  # :139-142
+            res, sil, worst, csil = {}, {}, [], []
+            for q, kk in enumerate(krange):
+                if kk >= N:
+                    continue
+                r, sl = robustkmeans(X, kk, repeats, maxiter=maxiter, tol=tol, compute_silhouettes_flag=True, seed=None if seed is None else seed + q,
+                                     ctx=ctx)
+                res[q], sil[q] = r, sl
+                worst.append(float(np.min(sl)))
+                csil.append(min(float(np.mean(sl[r.assignments == j])) for j in np.unique(r.assignments)))
+            seq = worst if best_method == "worst_cliff" else csil
+            if best_method not in ("worst_cliff", "worst_cluster_cliff"):
+                raise NMFkError(-1, "Unknown method: best_method must be :worst_cliff or :worst_cluster_cliff")
+            drops = [seq[i] - seq[i + 1] for i in range(len(seq) - 1)]
+            ki = int(np.argmax(drops)) + 1  # last(findmax(...)) + 1 (:160-163)
+            return res[ki]
+        k = int(k)
+        if seeds is None:
+            rng = np.random.Generator(np.random.Philox(key=0 if seed is None else int(seed))) if seed is not None else np.random.default_rng()
+            seeds = np.stack([kmeanspp_seeds(X, k, rng) for _ in range(repeats)])
+        seeds = np.ascontiguousarray(seeds, dtype=np.int32)
+        assert seeds.shape == (repeats, k)
+        assign = np.empty(N, dtype=np.int32)
+        centers = np.empty((k, d))
+        costs = np.empty(N)
+        counts = np.empty(k, dtype=np.int32)
+        sil = np.zeros(N)
+        tc = C.c_double()
+        it, conv, best, nempty = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        check(ctx._lib.nmfk_robustkmeans(ctx._h, X.ctypes.data_as(_lib._pdbl), d, N, k, repeats, seeds.ctypes.data_as(_lib._pi32), maxiter,
+                                         float(tol), int(compute_silhouettes_flag), assign.ctypes.data_as(_lib._pi32),
+                                         centers.ctypes.data_as(_lib._pdbl), costs.ctypes.data_as(_lib._pdbl),
+                                         counts.ctypes.data_as(_lib._pi32), C.byref(tc), C.byref(it), C.byref(conv),
+                                         sil.ctypes.data_as(_lib._pdbl), C.byref(best), C.byref(nempty)), ctx._h)
+        nc = len(np.unique(assign))
+        out = KmeansResult(centers=centers.T[:, :nc], assignments=assign, costs=costs, counts=counts[:nc], totalcost=tc.value,
+                           iterations=it.value, converged=bool(conv.value))
+        if details is not None:
+            details.update(best_repeat=best.value, empty_cluster_repeats=nempty.value)
+        return (out, sil) if compute_silhouettes_flag else out
     finally:
         if own:
             ctx.close()

@@ -506,6 +506,108 @@ def clustersolutions(factors: Sequence[np.ndarray], clusterWmatrix: bool = False
 
 
 # --------------------------------------------------------------------------------------
+# robustkmeans: src/NMFkCluster.jl:138-289 (+ Clustering.jl `kmeans`, restated)
+# --------------------------------------------------------------------------------------
+def pairwise_cosine_cols(A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """Distances.pairwise(CosineDist(), A, B; dims=2): r[i,j] = max(1 - <A[:,i],B[:,j]> / (|A[:,i]| |B[:,j]|), 0)."""
+    G = A.T @ B
+    ra = np.sqrt(np.sum(A * A, axis=0))
+    rb = np.sqrt(np.sum(B * B, axis=0))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        D = 1.0 - G / (ra[:, None] * rb[None, :])
+    return np.where(np.isnan(D), D, np.maximum(D, 0.0))
+
+
+def kmeans_lloyd(X: np.ndarray, k: int, seeds: Sequence[int], maxiter: int = 1000, tol: float = 1e-32):
+    """Clustering.kmeans(X, k; maxiter, tol, distance=CosineDist()) from given seeds (Clustering.jl 0.14/0.15 `kmeans.jl`
+    `_kmeans!`, `update_assignments!`, `update_centers!`, restated; the package is not vendored under /root/reference).  The points
+    are the COLUMNS of X (d x N).  The package draws the seeds with k-means++ from Julia's RNG (not reproducible here: an input)
+    and re-draws a centre that lost all its points at random (`repick_unused_centers`; here such a centre keeps its position,
+    and `empty` reports that it happened).  Returns a dict with the fields of KmeansResult."""
+    d, n = X.shape
+    centers = np.array(X[:, list(seeds)], dtype=np.float64, copy=True)
+    assignments = np.zeros(n, dtype=np.int64)
+    costs = np.zeros(n)
+    counts = np.zeros(k, dtype=np.int64)
+    to_update = np.ones(k, dtype=bool)
+
+    def update_assignments(dmat, is_init):
+        nonlocal to_update
+        to_update[:] = is_init
+        counts[:] = 0
+        for j in range(n):
+            c, a = 0, dmat[0, j]
+            for i in range(1, k):
+                if dmat[i, j] < a:
+                    a, c = dmat[i, j], i
+            if is_init:
+                assignments[j] = c
+            elif c != assignments[j]:
+                to_update[c] = True
+                to_update[assignments[j]] = True
+                assignments[j] = c
+            costs[j] = a
+            counts[c] += 1
+        unused = [i for i in range(k) if counts[i] == 0]
+        for i in unused:
+            to_update[i] = False
+        return unused
+
+    unused = update_assignments(pairwise_cosine_cols(centers, X), True)
+    objv = float(np.sum(costs))
+    t, converged, empty = 0, False, False
+    while not converged and t < maxiter:
+        t += 1
+        for c in range(k):  # update_centers!: mean of the assigned points for the clusters whose membership changed
+            if to_update[c] and counts[c] > 0:
+                centers[:, c] = X[:, assignments == c].sum(axis=1) / counts[c]
+        empty = empty or bool(unused)
+        unused = update_assignments(pairwise_cosine_cols(centers, X), False)
+        prev, objv = objv, float(np.sum(costs))
+        change = objv - prev
+        if change > tol:
+            pass  # "The clustering cost increased at iteration"
+        elif k == 1 or abs(change) < tol:
+            converged = True
+    return dict(centers=centers, assignments=assignments + 1, costs=costs.copy(), counts=counts.copy(), totalcost=objv, iterations=t,
+                converged=converged, empty=empty)
+
+
+def sortclustering(res: dict) -> dict:
+    """`sortclustering(c::Clustering.KmeansResult)` src/NMFkCluster.jl:264-289: relabel the clusters in order of first appearance,
+    then rank them by size (descending, stable)."""
+    a = res["assignments"]
+    j = list(dict.fromkeys(a.tolist()))  # unique, order of first appearance
+    relabel = {lab: q + 1 for q, lab in enumerate(j)}
+    ca = np.array([relabel[v] for v in a])
+    cnt = np.array([res["counts"][lab - 1] for lab in j])
+    i = np.argsort(-cnt, kind="stable")
+    ca2 = np.zeros_like(ca)
+    for q, idx in enumerate(i):
+        ca2[ca == idx + 1] = q + 1
+    r = [j[idx] - 1 for idx in i]
+    out = dict(res)
+    out.update(assignments=ca2, centers=res["centers"][:, r], counts=res["counts"][r])
+    return out
+
+
+def robustkmeans(X: np.ndarray, k: int, seeds_per_repeat: Sequence[Sequence[int]], maxiter: int = 1000, tol: float = 1e-32,
+                 compute_silhouettes_flag: bool = False):
+    """`robustkmeans(X, k, repeats; ...)` src/NMFkCluster.jl:172-246 with the seeds of every repeat injected: the first repeat
+    with the smallest total cost wins (:219-225), silhouettes on pairwise(CosineDist(), zerostoepsilon(X); dims=2) (:195-214),
+    then sortclustering (:227).  Returns (result dict, best_silhouettes or None)."""
+    best, best_cost, best_sil = None, np.inf, np.zeros(X.shape[1])
+    Xd = pairwise_cosine_rows(zerostoepsilon(X).T) if compute_silhouettes_flag else None
+    for i, seeds in enumerate(seeds_per_repeat):
+        c = kmeans_lloyd(X, k, seeds, maxiter, tol)
+        if i == 0 or c["totalcost"] < best_cost:
+            best, best_cost = c, c["totalcost"]
+            if compute_silhouettes_flag:
+                best_sil = silhouettes(c["assignments"], Xd) if c["assignments"].max() > 1 else np.zeros(X.shape[1])
+    return sortclustering(best), (best_sil if compute_silhouettes_flag else None)
+
+
+# --------------------------------------------------------------------------------------
 # finalize: src/NMFkFinalize.jl:36-79
 # --------------------------------------------------------------------------------------
 def finalize(Wa: Sequence[np.ndarray], Ha: Sequence[np.ndarray], idx: np.ndarray, clusterWmatrix: bool = False):
