@@ -9,6 +9,7 @@
 #include <climits>
 #include <cmath>
 
+#include "fro.h"
 #include "nmfk_internal.h"
 
 namespace nmfk {
@@ -252,6 +253,32 @@ __global__ void __launch_bounds__(256) cosine_gram_kernel(const double* __restri
         }
 }
 
+// Dm holds the Gram matrix G = V V^T (DMMA GEMM, fro_gemm_f64.cu): G -> cosine distances in place, same formula as above
+__global__ void cosine_from_gram_kernel(double* __restrict__ Dm, int N, const double* __restrict__ vnorm) {
+    const long long total = (long long)N * N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e % N), j = (int)(e / N);
+        double d = 1.0 - Dm[e] / (vnorm[i] * vnorm[j]);
+        d = (d != d) ? 0.0 : (d < 0.0 ? 0.0 : d);
+        if (i == j) d = 0.0;
+        Dm[e] = d;
+    }
+}
+
+// pairwise cosine distances of the N rows of V: on the FP64 tensor pipe (DMMA GEMM V V^T, then the distance formula) once the
+// matrix is big enough to fill the GPU, the 64 x 64 DFMA tiles otherwise
+cudaError_t pairwise_cosine(const double* V, int len, int ld, int N, const double* vnorm, double* Dm, cudaStream_t s) {
+    if (N >= 512) {
+        cudaError_t e = launch_fro_gemm_f64(V, ld, V, ld, Dm, N, N, N, len, s);
+        if (e != cudaSuccess) return e;
+        cosine_from_gram_kernel<<<148 * 8, 256, 0, s>>>(Dm, N, vnorm);
+        return cudaGetLastError();
+    }
+    dim3 grid((N + 63) / 64, (N + 63) / 64);
+    cosine_gram_kernel<<<grid, 256, 0, s>>>(V, len, ld, N, vnorm, Dm);
+    return cudaGetLastError();
+}
+
 // Clustering.silhouettes(assignments, dists): thread per point j, sequential over i (the order the
 // package uses), k per-cluster sums kept in shared memory.
 __global__ void silhouette_kernel(const double* __restrict__ Dm, int N, int k, const int* __restrict__ labels,
@@ -376,9 +403,7 @@ cudaError_t launch_point_silhouettes(double* V, int len, int ld, int N, int k, c
     cudaError_t e;
     floor_norm_kernel<<<(N + 7) / 8, 256, 0, s>>>(V, len, ld, N, floorv, vnorm);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    dim3 grid((N + 63) / 64, (N + 63) / 64);
-    cosine_gram_kernel<<<grid, 256, 0, s>>>(V, len, ld, N, vnorm, Dm);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = pairwise_cosine(V, len, ld, N, vnorm, Dm, s)) != cudaSuccess) return e;
     const int NT = 128;
     const size_t smem = (size_t)k * NT * sizeof(double) + (size_t)k * sizeof(int);
     silhouette_kernel<<<(N + NT - 1) / NT, NT, smem, s>>>(Dm, N, k, labels, sil);
@@ -419,9 +444,7 @@ cudaError_t launch_cluster(const ClusterArgs& a, int dtype, cudaStream_t s) {
         const double floorv = dtype == 1 ? eps * eps : (double)((float)eps * (float)eps);
         floor_norm_kernel<<<(N + 7) / 8, 256, 0, s>>>(a.V, a.len, ld, N, floorv, a.vnorm);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        dim3 grid((N + 63) / 64, (N + 63) / 64);
-        cosine_gram_kernel<<<grid, 256, 0, s>>>(a.V, a.len, ld, N, a.vnorm, a.Dm);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = pairwise_cosine(a.V, a.len, ld, N, a.vnorm, a.Dm, s)) != cudaSuccess) return e;
         const int NT = 128;
         const size_t smem = (size_t)a.k * NT * sizeof(double) + (size_t)a.k * sizeof(int);
         silhouette_kernel<<<(N + NT - 1) / NT, NT, smem, s>>>(a.Dm, N, a.k, a.labels, a.sil);

@@ -606,6 +606,51 @@ cudaError_t dispatch_tiled_apply(const TiledPassArgs& a, void* red, cudaStream_t
     NMFK_DISPATCH_K(launch_tiled_apply_k, TX, TC, kt, a, red, s)
 }
 
+// NMFK_TILED_TIMING=1: device time of every phase of the tiled engine's iteration (CUDA events between the launches, read at
+// the host synchronisation points), printed per solve - the timeline that says what bounds an iteration (row-sharded runs).
+struct PhaseTimer {
+    static constexpr int NPH = 12;
+    bool on = false;
+    std::vector<cudaEvent_t> idle;
+    std::vector<std::pair<cudaEvent_t, int>> marks;
+    double ms[NPH] = {0};
+    long long cnt[NPH] = {0};
+    void mark(cudaStream_t s, int phase) {  // `phase` = what ran since the previous mark (-1: start of a timed stretch)
+        if (!on) return;
+        cudaEvent_t e = nullptr;
+        if (!idle.empty()) {
+            e = idle.back();
+            idle.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
+        cudaEventRecord(e, s);
+        marks.emplace_back(e, phase);
+    }
+    void harvest() {
+        for (size_t i = 1; i < marks.size(); ++i) {
+            float t = 0.f;
+            if (marks[i].second >= 0 && cudaEventElapsedTime(&t, marks[i - 1].first, marks[i].first) == cudaSuccess) {
+                ms[marks[i].second] += t;
+                ++cnt[marks[i].second];
+            }
+        }
+        for (auto& m : marks) idle.push_back(m.first);
+        marks.clear();
+    }
+    void report(int iters, int rank) {
+        if (!on) return;
+        static const char* names[NPH] = {"sums_W", "pass_H", "allreduce_H", "apply_H", "sums_H", "pass_W", "impute", "objective",
+                                         "objsum_allreduce", "clamp_check", "guard_sync", "finish"};
+        fprintf(stderr, "[nmfk timing rank %d] %d iterations:", rank, iters);
+        for (int i = 0; i < NPH; ++i)
+            if (cnt[i]) fprintf(stderr, " %s=%.3fms/%lld", names[i], ms[i], cnt[i]);
+        fprintf(stderr, "\n");
+        for (auto e : idle) cudaEventDestroy(e);
+        idle.clear();
+    }
+};
+
 #define NMFK_TRY(call)                      \
     do {                                    \
         cudaError_t e__ = (call);           \
@@ -662,6 +707,10 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     // row-sharded X: den and the H-update numerators are contiguous so that one all-reduce moves both
     const ShardComm* sh = a.shard;
     const bool sharded = sh != nullptr;
+    PhaseTimer pt;
+    pt.on = getenv("NMFK_TILED_TIMING") != nullptr;
+    const int it_begin_report = 0;
+    (void)it_begin_report;
     TC* den = nullptr;  // R x 32, followed by red (R x m x kt) when sharded
     TC* red = nullptr;
     double* obj2 = nullptr;
@@ -794,17 +843,22 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
                 NMFK_TRY(cudaGetLastError());
                 ++*launches;
                 NMFK_TRY(cudaMemcpyAsync(h_active, d_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+                pt.mark(s, 10);
                 NMFK_TRY(cudaStreamSynchronize(s));
                 if (a.prof) a.prof->harvest();
+                pt.harvest();
                 if (*h_active == 0) break;
                 need_guard = false;
+                pt.mark(s, -1);
             }
             ++it;
             ph.first_iter = pw.first_iter = (it == 1);
             if (!a.Hfixed) {
                 tiled_sums_kernel<TC><<<dim3(k, R), 256, 0, s>>>(a.W, (long long)n * k, 1, n, n, a.st, den);
                 NMFK_TRY(cudaGetLastError());
+                pt.mark(s, 0);
                 NMFK_TRY((timed_tiled_pass<TX, TC>(ph, red, s, use_tc, h_active + 1, use_td, a.prof)));
+                pt.mark(s, 1);
                 *launches += 2 + (SH > 1 || sharded);
                 if (d_trace != nullptr) {
                     std::vector<long long> ht(3 * 64 * 8);
@@ -821,14 +875,18 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
                 if (sharded) {
                     // colsum(W) and W' * (X ./ (W*H)) over this rank's rows -> sums over all rows, then the update
                     NMFK_TRY(sh->allreduce(sh->comm, den, (size_t)R * 32 + redsz, sizeof(TC) == 8 ? 1 : 0, s));
+                    pt.mark(s, 2);
                     NMFK_TRY((dispatch_tiled_apply<TX, TC>(ph, red, s)));
+                    pt.mark(s, 3);
                     ++*launches;
                 }
             }
             if (!a.Wfixed) {
                 tiled_sums_kernel<TC><<<dim3(k, R), 256, 0, s>>>(a.H, (long long)k * m, k, 1, m, a.st, den);
                 NMFK_TRY(cudaGetLastError());
+                pt.mark(s, 4);
                 NMFK_TRY((timed_tiled_pass<TX, TC>(pw, nullptr, s, use_tc, h_active + 1, use_td, a.prof)));
+                pt.mark(s, 5);
                 *launches += 2 + (SW > 1);
             }
             if (a.has_nan) {
@@ -849,11 +907,13 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
                         (const TX*)a.X, n, m, k, (const TC*)a.W, (const TC*)a.H, a.st, (TC)a.lambda, 0, 1, a.weight, a.wref, objp);
                 }
                 NMFK_TRY(cudaGetLastError());
+                pt.mark(s, 7);
                 // per-restart objective sums in block order (and, row-sharded, over all ranks)
                 tiled_objsum_kernel<<<(R + 127) / 128, 128, 0, s>>>(objp, nblkObj, R, obj2);
                 NMFK_TRY(cudaGetLastError());
                 ++*launches;
                 if (sharded) NMFK_TRY(sh->allreduce(sh->comm, obj2, (size_t)R * 2, 1, s));
+                pt.mark(s, 8);
                 const bool wide_clamp = (long long)n * k >= (1ll << 18) && !a.Wfixed;
                 if (wide_clamp) {
                     const long long nk = (long long)n * k;
@@ -887,6 +947,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
                     tiled_check_kernel<TC><<<R, 256, csm, s>>>(c);
                 }
                 NMFK_TRY(cudaGetLastError());
+                pt.mark(s, 9);
                 *launches += 2;
                 need_guard = true;
             }
@@ -895,6 +956,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     }
     {
         // post-run objective on the restored X + normalisation for restarts that stopped in this call
+        pt.mark(s, -1);
         if (use_tc && !wobj) {
             NMFK_TRY(launch_tc_objective(obj_args(1, 1), h_active + 1, s));
         } else if (use_td && !wobj) {
@@ -915,8 +977,11 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
                                                   a.normalize);
         NMFK_TRY(cudaGetLastError());
         *launches += 2;
+        pt.mark(s, 11);
         NMFK_TRY(cudaStreamSynchronize(s));
         if (a.prof) a.prof->harvest();
+        pt.harvest();
+        pt.report(it, sharded ? sh->rank : 0);
     }
 done:
     if (h_active && h_active[1] != 0)
