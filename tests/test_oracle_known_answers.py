@@ -161,3 +161,68 @@ def test_finalize_means_and_variances_hand_case():
     assert np.allclose(Hv, [[4.0, 4.0], [400.0, 400.0]])  # var([1,3,5]) = 4, var([10,30,50]) = 400 (corrected)
     assert np.allclose(Wv, [[4.0, 40000.0]])
     assert csil.shape == (2, 1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2: the restated third-party pieces next to the path (NMF.jl MultUpdate, Clustering.kmeans, sortclustering) and the
+# reference-behaviour details the oracle mirrors (clusterWmatrix aliasing, DArray stop rule, Julia weight broadcasting)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_fro_oracle_is_the_lee_seung_frobenius_update():
+    """NMF.jl MultUpdate(obj=:mse): the Frobenius objective never increases (Lee & Seung 2001, theorem 1; delta only damps
+    the step) and a rank-3 mixture is recovered."""
+    rng = np.random.default_rng(0)
+    X = rng.random((40, 3)) @ rng.random((3, 25))
+    W0, H0 = rng.random((40, 3)), rng.random((3, 25))
+    objs = []
+    o.nmf_multupdate_mse(X, 3, Winit=W0, Hinit=H0, maxiter=300, tol=0.0, trace=lambda it, W, H: objs.append(float(np.sum((X - W @ H) ** 2))))
+    assert all(b <= a * (1 + 1e-12) for a, b in zip(objs, objs[1:]))
+    assert objs[-1] < 1e-3 * objs[0]
+    inf = {}
+    o.nmf_multupdate_mse(X, 3, Winit=W0, Hinit=H0, maxiter=100000, tol=1e-3, info=inf)
+    assert inf["converged"] and inf["iters"] < 100000  # stop_condition: relative change of every column / row below tol
+
+
+def test_darray_rule_equals_dense_rule_until_the_dense_one_gives_up():
+    X = np.asfortranarray(np.random.default_rng(1).random((12, 3)) @ np.random.default_rng(2).random((3, 6)))
+    W0, H0 = np.random.default_rng(3).random((12, 3)), np.random.default_rng(4).random((3, 6))
+    i1 = {}
+    Wd, Hd, _ = o.nmf_multiplicative(X.copy(), 3, Winit=W0.copy(), Hinit=H0.copy(), maxiter=40, info=i1)
+    Wa, Ha, _ = o.nmf_multiplicative_darray(X.copy(), 3, Winit=W0.copy(), Hinit=H0.copy(), maxiter=40)
+    assert i1["iters"] == 40 and np.allclose(Wd, Wa, rtol=1e-13) and np.allclose(Hd, Ha, rtol=1e-13)
+
+
+def test_julia_weight_broadcasting():
+    w = o._julia_weight(np.arange(4.0), 4, 3)
+    assert w.shape == (4, 1)  # a Vector weights the ROWS
+    assert o._julia_weight(np.ones((1, 3)), 4, 3).shape == (1, 3) and o._julia_weight(2.0, 4, 3) == 2.0
+
+
+def test_cluster_wmatrix_aliases_the_best_solution():
+    """clustersolutions(W stack, true) accumulates the centroids IN factors[1] (NMFkCluster.jl:453-455, :484, :512)."""
+    rng = np.random.default_rng(5)
+    Ws = [rng.random((7, 2)) + 0.1 for _ in range(4)]
+    first = Ws[0].copy()
+    labels, cent = o.clustersolutions(Ws, True)
+    assert not np.array_equal(Ws[0], first) and np.allclose(Ws[0], cent.T)  # the caller's matrix now holds the centroids
+    Hs = [rng.random((2, 7)) + 0.1 for _ in range(4)]
+    keep = [h.copy() for h in Hs]
+    o.clustersolutions(Hs, False)
+    assert all(np.array_equal(a, b) for a, b in zip(Hs, keep))  # permutedims copies: nothing is aliased on the H branch
+
+
+def test_kmeans_lloyd_and_sortclustering():
+    rng = np.random.default_rng(6)
+    X = np.hstack([np.array([[1.0], [0.1]]) + 0.01 * rng.random((2, 3)), np.array([[0.1], [1.0]]) + 0.01 * rng.random((2, 7))])
+    r = o.kmeans_lloyd(X, 2, [0, 9])
+    assert r["converged"] and sorted(r["counts"].tolist()) == [3, 7] and r["totalcost"] < 1e-3
+    s = o.sortclustering(r)
+    assert list(s["counts"]) == [7, 3] and list(s["assignments"][:3]) == [2, 2, 2] and list(s["assignments"][3:]) == [1] * 7
+    res, sil = o.robustkmeans(X, 2, [[0, 1], [0, 9], [3, 4]], compute_silhouettes_flag=True)
+    assert list(res["counts"]) == [7, 3] and sil.min() > 0.9
+
+
+def test_execute_run_filters_follow_the_reference_index_mix():
+    X = np.asfortranarray(np.random.default_rng(7).random((10, 2)) @ np.random.default_rng(8).random((2, 6)))
+    det = {}
+    o.execute_run(X.copy(), 2, 5, seed=3, maxiter=50, acceptratio=0.6, details=det)
+    assert det["idxsol"].tolist() == [True, True, True, False, False] and det["labels"].shape == (2, 3)
