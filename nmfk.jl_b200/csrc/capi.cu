@@ -251,6 +251,13 @@ int32_t nmfk_ctx_comm_init(nmfk_ctx* c, int32_t nranks, int32_t rank, const void
         if (r != ncclSuccess)
             return fail(c, NMFK_E_UNSUPPORTED, std::string("ncclCommInitRank: ") + g_nccl.getErrorString(r));
         c->shard = ShardComm{comm, nranks, rank, nccl_allreduce};
+        // NCCL connects its channels lazily at the first collective (hundreds of ms with 8 ranks): do it here, not inside
+        // the first timed iteration of a solve
+        DevBuf warm;
+        CU(c, warm.alloc(256 * sizeof(float)));
+        CU(c, cudaMemsetAsync(warm.p, 0, 256 * sizeof(float), c->stream));
+        CU(c, nccl_allreduce(comm, warm.p, 256, 0, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
     }
     c->sharded = true;
     c->row0 = row0;
@@ -283,6 +290,11 @@ int32_t nmfk_ctx_sweep_comm_init(nmfk_ctx* c, int32_t nranks, int32_t rank, cons
         const ncclResult_t r = g_nccl.commInitRank(&comm, nranks, id, rank);
         if (r != ncclSuccess) return fail(c, NMFK_E_UNSUPPORTED, std::string("ncclCommInitRank: ") + g_nccl.getErrorString(r));
         c->sweep_comm = comm;
+        DevBuf warm;  // first collective = NCCL's lazy channel set-up: pay it here
+        CU(c, warm.alloc(256 * sizeof(float)));
+        CU(c, cudaMemsetAsync(warm.p, 0, 256 * sizeof(float), c->stream));
+        CU(c, nccl_allreduce(comm, warm.p, 256, 0, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
     }
     c->sweep_nranks = nranks;
     c->sweep_rank = rank;

@@ -237,8 +237,18 @@ __global__ void __launch_bounds__(256) tiled_sums_kernel(const void* Vv, long lo
     const int c = blockIdx.x, r = blockIdx.y;
     if (st[r].stop != 0) return;
     const TC* V = static_cast<const TC*>(Vv) + (long long)r * v_rstride + (long long)c * sv_a;
-    double s = 0.0;
-    for (int t = threadIdx.x; t < nred; t += blockDim.x) s += (double)V[(long long)t * sv_t];
+    // four independent chains keep four loads in flight per thread (fixed order: deterministic)
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const int NT = blockDim.x;
+    int t = threadIdx.x;
+    for (; t + 3 * NT < nred; t += 4 * NT) {
+        s0 += (double)V[(long long)t * sv_t];
+        s1 += (double)V[(long long)(t + NT) * sv_t];
+        s2 += (double)V[(long long)(t + 2 * NT) * sv_t];
+        s3 += (double)V[(long long)(t + 3 * NT) * sv_t];
+    }
+    for (; t < nred; t += NT) s0 += (double)V[(long long)t * sv_t];
+    double s = (s0 + s1) + (s2 + s3);
     s = block_sum(s, red);
     if (threadIdx.x == 0) static_cast<TC*>(denv)[(long long)r * 32 + c] = (TC)s;
 }
@@ -454,9 +464,24 @@ __global__ void __launch_bounds__(256) tiled_check_kernel(const TiledCheckArgs a
 }
 
 // post-run: objective sums -> state, then normalisation (NMFkExecute.jl:791-804); one CTA per restart
+// wide W .*= total' of the finish step for tall matrices (one CTA per restart took 18 ms at n = 250 000): the finish kernel
+// leaves the k totals and a flag per restart, this one scales W with the whole GPU
+template <typename TC>
+__global__ void __launch_bounds__(256) tiled_scaleW_kernel(TC* __restrict__ Wst, long long n, int k, const double* __restrict__ tot,
+                                                            const int* __restrict__ wflag) {
+    const int r = blockIdx.y;
+    if (!wflag[r]) return;
+    TC* W = Wst + (long long)r * n * k;
+    const double* t = tot + (long long)r * 32;
+    const long long nk = n * k;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nk; e += (long long)gridDim.x * blockDim.x)
+        W[e] = W[e] * (TC)t[e / n];
+}
+
 template <typename TC>
 __global__ void __launch_bounds__(256) tiled_finish_kernel(void* Wv, void* Hv, UnitState* stv, const double* partials,
-                                                           int n, int m, int k, int nblk, int normalize) {
+                                                           int n, int m, int k, int nblk, int normalize, double* tot_out = nullptr,
+                                                           int* wflag = nullptr) {
     __shared__ double red[40];
     __shared__ double tot[32];
     const int r = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
@@ -481,7 +506,12 @@ __global__ void __launch_bounds__(256) tiled_finish_kernel(void* Wv, void* Hv, U
             if (tid == 0) tot[c] = (double)(TC)s;
         }
         __syncthreads();
-        for (long long e = tid; e < (long long)n * k; e += NT) W[e] = W[e] * (TC)tot[e / n];
+        if (wflag != nullptr) {  // W is scaled by tiled_scaleW_kernel over the whole GPU
+            for (int c = tid; c < k; c += NT) tot_out[(long long)r * 32 + c] = tot[c];
+            if (tid == 0) wflag[r] = 1;
+        } else {
+            for (long long e = tid; e < (long long)n * k; e += NT) W[e] = W[e] * (TC)tot[e / n];
+        }
         for (long long e = tid; e < (long long)k * m; e += NT) H[e] = div_cold<TC>(H[e], (TC)tot[e % k]);
     } else if (normalize == 2) {  // total = sum(W; dims=1); W ./= total; H .*= total'
         for (int c = 0; c < k; ++c) {
@@ -717,6 +747,8 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     TC* partial = nullptr;
     double* objp = nullptr;
     int* d_active = nullptr;
+    double* fin_tot = nullptr;  // wide finish: the k totals of every restart
+    int* fin_flag = nullptr;    //              ... and which restarts tiled_scaleW_kernel has to scale
     int* h_active = nullptr;  // [0] running restarts, [1] barrier time-out site reported by the tcgen05 kernel
     std::vector<UnitState> hst((size_t)R);
     int it = 0;
@@ -765,6 +797,8 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     if (psz) NMFK_TRY(cudaMalloc(&partial, psz * sizeof(TC)));
     NMFK_TRY(cudaMalloc(&objp, (size_t)R * nblkObj * 2 * sizeof(double)));
     NMFK_TRY(cudaMalloc(&d_active, sizeof(int)));
+    NMFK_TRY(cudaMalloc(&fin_tot, (size_t)R * 32 * sizeof(double)));
+    NMFK_TRY(cudaMalloc(&fin_flag, (size_t)R * sizeof(int)));
     NMFK_TRY(cudaMallocHost(&h_active, 2 * sizeof(int)));
     h_active[1] = 0;
     NMFK_TRY(cudaMemcpyAsync(hst.data(), a.st, (size_t)R * sizeof(UnitState), cudaMemcpyDeviceToHost, s));
@@ -973,9 +1007,18 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
             NMFK_TRY(sh->allreduce(sh->comm, obj2, (size_t)R * 2, 1, s));
             ++*launches;
         }
+        const bool wide_finish = a.normalize == 1 && (long long)n * k >= (1ll << 18);
+        if (wide_finish) NMFK_TRY(cudaMemsetAsync(fin_flag, 0, (size_t)R * sizeof(int), s));
         tiled_finish_kernel<TC><<<R, 256, 0, s>>>(a.W, a.H, a.st, sharded ? obj2 : objp, n, m, k, sharded ? 1 : nblkObj,
-                                                  a.normalize);
+                                                  a.normalize, wide_finish ? fin_tot : nullptr, wide_finish ? fin_flag : nullptr);
         NMFK_TRY(cudaGetLastError());
+        if (wide_finish) {
+            const long long nk = (long long)n * k;
+            dim3 g((unsigned)std::min<long long>((nk + 2047) / 2048, 1024), R);
+            tiled_scaleW_kernel<TC><<<g, 256, 0, s>>>((TC*)a.W, n, k, fin_tot, fin_flag);
+            NMFK_TRY(cudaGetLastError());
+            ++*launches;
+        }
         *launches += 2;
         pt.mark(s, 11);
         NMFK_TRY(cudaStreamSynchronize(s));
@@ -991,6 +1034,8 @@ done:
     if (objp) cudaFree(objp);
     if (obj2) cudaFree(obj2);
     if (d_active) cudaFree(d_active);
+    if (fin_tot) cudaFree(fin_tot);
+    if (fin_flag) cudaFree(fin_flag);
     if (h_active) cudaFreeHost(h_active);
     return err;
 }
