@@ -276,14 +276,20 @@ def fixed_budget_single(ctx, nb, synth, torch, cfg, args, iters, flush, k=None, 
         b.close()
         return ms, tot, nl, pm, pl
 
-    for _ in range(args.warmup):
-        device_step(False)
+    # the clock sampler starts BEFORE the warm-up steps: nvidia-smi's start-up (NVML initialisation takes driver locks) stalled
+    # the launches of the first timed step in one of two runs (301 ms instead of 224 ms, profiles/r02_bench_n1_second_outlier.json);
+    # the warm-up steps also create the profile events
     sampler = ClockSampler(torch.cuda.current_device())
     sampler.start()
+    for _ in range(args.warmup):
+        device_step(True)
+    sampler.rows.clear()  # keep the samples of the timed region only
     tot_ms = tot_it = launches = pass_l = 0
     pass_ms = 0.0
+    step_ms = []
     for _ in range(args.steps):
         ms, tot, nl, pm, pl = device_step(True)
+        step_ms.append(ms)
         tot_ms += ms
         tot_it += tot
         launches += nl
@@ -317,7 +323,7 @@ def fixed_budget_single(ctx, nb, synth, torch, cfg, args, iters, flush, k=None, 
         dts, t, rob = e2e_step()
         e2e_t += dts
         e2e_it += t
-    return dict(value=tot_it / (tot_ms * 1e-3), ms_per_step=tot_ms / args.steps, iters_per_step=tot_it / args.steps,
+    return dict(value=tot_it / (tot_ms * 1e-3), ms_per_step=tot_ms / args.steps, step_ms=step_ms, iters_per_step=tot_it / args.steps,
                 launches=launches, pass_ms=pass_ms, pass_launches=pass_l, flops_per_pass=4.0 * n * m * k * R, clocks=clocks,
                 e2e_value=e2e_it / e2e_t, e2e_ms_per_step=e2e_t / args.steps * 1e3, h2d=h2d, d2h=d2h, robustness=rob,
                 n=n, m=m, k=k, R=R)
@@ -445,6 +451,7 @@ def main():
             "config": {"workload": WORKLOADS["C3"] % iters, "engine": "tiled; tcgen05.mma kind::tf32 3-term split (kl_tiled_tc.cu)",
                        "l2": "inputs larger than L2: X is 400 MB (and its transpose another 400 MB) against 126 MB of L2; 256 MiB "
                              "are also written between steps", "restart_iterations_per_step": r["iters_per_step"],
+                       "step_ms": r["step_ms"],
                        "same_config": True},
             "clocks": r["clocks"],
             "e2e": {"value": r["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
@@ -537,11 +544,12 @@ def main():
         del X
         params = nb.default_params(maxiter=iters, engine=2)
         dmma = max(ctx.measure_peak(1) for _ in range(2))
+        sampler = ClockSampler(local_rank)
+        sampler.start()  # before the warm-up: see fixed_budget_single
         for _ in range(args.warmup):
             sweep_step(ctx, nbdist, torch, Xpin.numpy().T, ks, R_local, params, rank, world, barrier)
-        sampler = ClockSampler(local_rank)
         barrier()
-        sampler.start()
+        sampler.rows.clear()
         l0 = ctx.launches
         ctx.profile(True)
         wall = solve = 0.0
@@ -619,11 +627,12 @@ def main():
             b.close()
             return dts, ctx.last_solve_ms, int(st["iters"].sum()), pm, pl
 
-        for _ in range(args.warmup):
-            step(False)
         sampler = ClockSampler(local_rank)
-        barrier()
         sampler.start()
+        for _ in range(args.warmup):
+            step(True)
+        barrier()
+        sampler.rows.clear()
         l0 = ctx.launches
         wall = solve = pm = 0.0
         its = pl = 0
