@@ -236,6 +236,10 @@ cudaError_t solve_fro_t(const SolveArgs& a, const void* Xlo, const void* Xtlo, c
     std::vector<UnitState> hst((size_t)R);
     bool any_running = false;
     int it = 0;
+    // NMFK_TILED_TIMING=1: per-phase device time (the phase names of the KL engine are reused: sums_* = Gram kernels, pass_* =
+    // the stacked GEMMs, apply_H / impute = the two apply kernels, clamp_check = the convergence kernel)
+    PhaseTimer pt;
+    pt.on = getenv("NMFK_TILED_TIMING") != nullptr;
     FRO_TRY(cudaMalloc(&Ht, (size_t)Rk * m * sizeof(T)));
     FRO_TRY(cudaMalloc(&Nbuf, std::max((size_t)NSH * Rk * m, (size_t)NSW * Rk * n) * sizeof(T)));
     if (F32) {
@@ -279,15 +283,19 @@ cudaError_t solve_fro_t(const SolveArgs& a, const void* Xlo, const void* Xtlo, c
                 FRO_TRY(cudaGetLastError());
                 ++*launches;
                 FRO_TRY(cudaMemcpyAsync(h_active, d_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+                pt.mark(s, 10);
                 FRO_TRY(cudaStreamSynchronize(s));
                 if (a.prof) a.prof->harvest();
+                pt.harvest();
                 if (h_active[0] == 0 || h_active[1] != 0) break;
                 need_guard = false;
+                pt.mark(s, -1);
             }
             ++it;
             if (!a.Hfixed) {  // H <- H .* (W'X) ./ (W'W H + d)
                 fro_gram_kernel<T><<<dim3(R, SW), 256, gsmem, s>>>(W, k, n, SW, a.st, Gpart);
                 FRO_TRY(cudaGetLastError());
+                pt.mark(s, 0);
                 if (a.prof) a.prof->begin(s);
                 if (F32)
                     FRO_TRY(launch_fro_gemm(reinterpret_cast<const float*>(W), Wlo, n, static_cast<const float*>(a.X),
@@ -296,12 +304,15 @@ cudaError_t solve_fro_t(const SolveArgs& a, const void* Xlo, const void* Xtlo, c
                     FRO_TRY(launch_fro_gemm_f64(reinterpret_cast<const double*>(W), n, static_cast<const double*>(a.X), n,
                                                 reinterpret_cast<double*>(Nbuf), m, (int)Rk, m, n, s));
                 if (a.prof) a.prof->end(s);
+                pt.mark(s, 1);
                 FRO_TRY(apply_dispatch<T>(Ht, Htlo, Nbuf, NSH, Rk * m, k, m, R, Gpart, SW, delta, a.st, convH, s));
+                pt.mark(s, 3);
                 *launches += 3;
             }
             if (!a.Wfixed) {  // W <- W .* (X H') ./ (W H H' + d)
                 fro_gram_kernel<T><<<dim3(R, SH), 256, gsmem, s>>>(Ht, k, m, SH, a.st, Gpart);
                 FRO_TRY(cudaGetLastError());
+                pt.mark(s, 4);
                 if (a.prof) a.prof->begin(s);
                 if (F32)
                     FRO_TRY(launch_fro_gemm(reinterpret_cast<const float*>(Ht), Htlo, m, static_cast<const float*>(a.Xt),
@@ -310,11 +321,14 @@ cudaError_t solve_fro_t(const SolveArgs& a, const void* Xlo, const void* Xtlo, c
                     FRO_TRY(launch_fro_gemm_f64(reinterpret_cast<const double*>(Ht), m, static_cast<const double*>(a.Xt), m,
                                                 reinterpret_cast<double*>(Nbuf), n, (int)Rk, n, m, s));
                 if (a.prof) a.prof->end(s);
+                pt.mark(s, 5);
                 FRO_TRY(apply_dispatch<T>(W, Wlo, Nbuf, NSW, Rk * n, k, n, R, Gpart, SH, delta, a.st, convW, s));
+                pt.mark(s, 6);
                 *launches += 3;
             }
             fro_converge_kernel<<<(R + 127) / 128, 128, 0, s>>>(a.st, R, k, convW, tilesW, convH, tilesH, !a.Wfixed, !a.Hfixed, a.tol, it);
             FRO_TRY(cudaGetLastError());
+            pt.mark(s, 9);
             ++*launches;
             if (it % a.check_every == 0 || it >= a.maxiter || (a.iter_limit > 0 && it >= a.iter_limit)) need_guard = true;
         }
@@ -324,6 +338,7 @@ cudaError_t solve_fro_t(const SolveArgs& a, const void* Xlo, const void* Xtlo, c
     }
     {
         // post-run objective on the caller's X (normnan(X - W*H), NMFkExecute.jl:791-792) + normalisation (:800-804)
+        pt.mark(s, -1);
         dim3 g(nblkObj, R);
         tiled_objective_kernel<T, T><<<g, 128, (size_t)k * 128 * sizeof(T), s>>>(static_cast<const T*>(a.X), n, m, k, W, static_cast<const T*>(a.H),
                                                                                  a.st, (T)a.lambda, 1, 0, 1.0, WeightRef{nullptr, nullptr, nullptr},
@@ -332,8 +347,11 @@ cudaError_t solve_fro_t(const SolveArgs& a, const void* Xlo, const void* Xtlo, c
         tiled_finish_kernel<T><<<R, 256, 0, s>>>(a.W, a.H, a.st, objp, n, m, k, nblkObj, a.normalize);
         FRO_TRY(cudaGetLastError());
         *launches += 2;
+        pt.mark(s, 11);
         FRO_TRY(cudaStreamSynchronize(s));
         if (a.prof) a.prof->harvest();
+        pt.harvest();
+        pt.report(it, 0);
     }
 done:
     if (h_active && h_active[1] != 0) fprintf(stderr, "[nmfk] fro_gemm_kernel: barrier time-out at site %d (protocol error)\n", h_active[1]);

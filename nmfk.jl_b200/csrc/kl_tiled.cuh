@@ -762,6 +762,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     // nanosleep between barrier polls of the roles that run ahead of the critical path: low 16 bits = X producer,
     // high 16 bits = V stagers (NMFK_TC_WAIT_HINT_NS overrides; 64 / 32 ns measured best or equal on C3, C3 k=32, C5)
     const int wait_hint = getenv("NMFK_TC_WAIT_HINT_NS") ? atoi(getenv("NMFK_TC_WAIT_HINT_NS")) : ((32 << 16) | 64);
+    const int qwait = getenv("NMFK_TC_QWAIT_NS") ? atoi(getenv("NMFK_TC_QWAIT_NS")) : 0;
     auto obj_args = [&](int restore, int sel) {
         TiledPassArgs po{};
         po.D = use_td ? a.Xt : a.X;  // the DMMA kernel reads the step-contiguous copy
@@ -787,6 +788,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
         po.obj_restore = restore;
         po.obj_sel = sel;
         po.wait_hint_ns = wait_hint;
+        po.qwait_ns = qwait;
         return po;
     };
   // column sums of W would need another exchange
@@ -836,6 +838,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
         ph.lambda = a.lambda;
         ph.ktmpl = kt;
         ph.wait_hint_ns = wait_hint;
+        ph.qwait_ns = qwait;
         pw = ph;
         pw.D = use_td ? a.Xt : a.X;
         pw.U = a.W;

@@ -25,6 +25,7 @@ struct TiledPassArgs {
     int obj_restore;       // 1: substituted zeros (x == lambda) count as 0 (final objective on the restored X)
     int obj_sel;           // 0: running restarts (stop == 0); 1: restarts that stopped and are not finished (done == 0)
     int wait_hint_ns;      // nanosleep between barrier polls: low 16 bits X producer, high 16 bits V stagers
+    int qwait_ns;          // nanosleep between the quotient warps' polls of p_full (0 = spin)
     long long* trace;   // debug: clock64 stamps of CTA 0 ([role][unit < 64][8]); nullptr in production
     int ktmpl;          // column stride of `partial` (the template K of the combine kernel)
 };

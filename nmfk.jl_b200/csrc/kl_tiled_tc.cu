@@ -604,7 +604,10 @@ __global__ void __launch_bounds__((TcCfg<K8, N2>::THREADS), 1) tc_pass_kernel(co
                 const int pq = u % C::NPQ;
                 const uint32_t col = lane_base + (uint32_t)pq * C::PQ + jh;
                 if (warp == TC_QW0) TC_STAMP(0, u, 0);
-                tc::mbar_wait_h(0u, &p_full[pq], (uint32_t)((u / C::NPQ) & 1), errflag, 41);
+                if (a.qwait_ns > 0)  // a waiting group sleeps between polls: its spinning takes issue slots from the dividing group
+                    tc::mbar_wait_relaxed(&p_full[pq], (uint32_t)((u / C::NPQ) & 1), (unsigned)a.qwait_ns, errflag, 41);
+                else
+                    tc::mbar_wait_h(0u, &p_full[pq], (uint32_t)((u / C::NPQ) & 1), errflag, 41);
                 // the numerators of this group's previous unit u-2: wait for the commit behind MMA#2(u-2) (with three P/Q
                 // buffers the commit behind p_full(u) only covers MMA#2(u-3)); it has normally completed long ago
                 if (prev_slot >= 0) tc::mbar_wait_h(0u, &a_full[grp], (uint32_t)((((u - 2) >> 1)) & 1), errflag, 44);
