@@ -103,8 +103,10 @@ typedef struct nmfk_params {
  *   NMF.MultUpdate(obj=:mse), third-party NMF.jl, restated in oracle/nmfk_oracle.py).  All R restarts of a batch are
  *   STACKED: W'X is one (R*k x n)(n x m) GEMM and X*H' one (n x m)(m x R*k) GEMM on the tensor cores (tcgen05 kind::tf32
  *   with the 3-term split for Float32, DMMA for Float64).  Stops when every column of W and row of H moved by less than
- *   `tol` relative (NMF.jl stop_condition) or at maxiter. */
-enum nmfk_variant { NMFK_VARIANT_KL = 0, NMFK_VARIANT_FRO = 1 };
+ *   `tol` relative (NMF.jl stop_condition) or at maxiter.
+ * NMFK_VARIANT_SPARSITY : NMFsparsity (NMFkSparsity.jl:1-113; method=:sparsity, NMFkExecute.jl:757-758): beta-divergence updates
+ *   with an L1 penalty on H and unit-norm columns of W; its own options come from nmfk_set_sparsity_options. */
+enum nmfk_variant { NMFK_VARIANT_KL = 0, NMFK_VARIANT_FRO = 1, NMFK_VARIANT_SPARSITY = 2 };
 
 /* Solution filtering of execute_run (NMFkExecute.jl:551-596): which of the R sorted restarts reach clustersolutions /
  * finalize.  Defaults acceptratio=1, acceptfactor=Inf, nanaction=:zeroed keep all of them. */
@@ -143,6 +145,10 @@ int32_t nmfk_ctx_sync(nmfk_ctx* ctx); /* cudaStreamSynchronize on every stream o
 int32_t nmfk_set_X(nmfk_ctx* ctx, const void* X, int64_t n, int64_t m, int32_t dtype, double lambda,
                    const void* normalizevector, int32_t on_device);
 int32_t nmfk_get_xinfo(const nmfk_ctx* ctx, nmfk_xinfo* out);
+/* Options of NMFsparsity (NMFkSparsity.jl:1): beta_divergence (2 = cost_function :ed, the default; 1 = :kl; 0 = :is; any other
+ * value = fractional beta), sparsity (L1 weight on H, default 1) and its lambda (floor of X_est and of the denominators, default
+ * 1e-9).  Used by nmfk_solve / nmfk_execute_run / nmfk_execute when params.variant == NMFK_VARIANT_SPARSITY. */
+int32_t nmfk_set_sparsity_options(nmfk_ctx* ctx, double beta_divergence, double sparsity, double lambda);
 /* The `weight` keyword when it is not a scalar (execute_run's assertion NMFkExecute.jl:484; used in the objective
  * sum((((X - W*H) .* weight)[.!inan]).^2) of NMFkMultiplicative.jl:74,125).  rows x cols must be (n,1): one weight per
  * row (a Julia Vector of length n), (1,m): one per column, or (n,m): one per entry; column-major, dtype of X, host

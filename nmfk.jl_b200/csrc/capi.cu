@@ -61,6 +61,8 @@ struct nmfk_ctx {
     // Variant FRO, Float32: lo images (x - tf32(x)) of Xp / Xpt for the 3-term split, built at the first FRO solve
     void* Xlo = nullptr;
     void* Xtlo = nullptr;
+    // NMFsparsity options (nmfk_set_sparsity_options): beta_divergence, sparsity, lambda
+    double sp_beta = 2.0, sp_sparsity = 1.0, sp_lambda = 1e-9;
     // persistent device scratch of the clustering phase (grown on demand, never shrunk)
     void* scratch = nullptr;
     size_t scratch_cap = 0;
@@ -646,7 +648,7 @@ static int32_t check_params(nmfk_ctx* c, const nmfk_params* p) {
         return fail(c, NMFK_E_INVALID, "params: check_every, maxbaditers, maxreattempts must be >= 1, maxiter >= 0");
     if (p->normalize < 0 || p->normalize > 2) return fail(c, NMFK_E_INVALID, "params: normalize must be 0, 1 or 2");
     if (p->stop_rule < 0 || p->stop_rule > 1) return fail(c, NMFK_E_INVALID, "params: stop_rule must be 0 or 1");
-    if (p->variant != NMFK_VARIANT_KL && p->variant != NMFK_VARIANT_FRO) return fail(c, NMFK_E_INVALID, "params: unknown variant");
+    if (p->variant < NMFK_VARIANT_KL || p->variant > NMFK_VARIANT_SPARSITY) return fail(c, NMFK_E_INVALID, "params: unknown variant");
     if (p->stop_rule == 1 && c && c->info.nnan > 0)
         return fail(c, NMFK_E_UNSUPPORTED, "stop_rule 1 (the DArray method) with NaN entries in X is not supported: the reference "
                                            "itself returns objvalue = NaN there (NMFkMultiplicative.jl:193-195)");
@@ -768,6 +770,35 @@ static int32_t solve_fro_batches(nmfk_ctx* c, nmfk_batch* const* batches, int32_
     return NMFK_OK;
 }
 
+// NMFsparsity (method=:sparsity; NMFkExecute.jl:757-758, NMFkSparsity.jl:1-113), one batch after the other
+static int32_t solve_sparsity_batches(nmfk_ctx* c, nmfk_batch* const* batches, int32_t nb, const nmfk_params* p) {
+    if (c->info.nnan > 0) return fail(c, NMFK_E_UNSUPPORTED, "NMFsparsity: X holds NaN (the reference's preprocessing call is commented out)");
+    if (c->sharded || c->Xn || c->wrow || c->wcol || c->wmat)
+        return fail(c, NMFK_E_UNSUPPORTED, "NMFsparsity: row-sharded X, normalizevector and array weights are not available");
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < nb; ++i) {
+        if (batches[i]->k > 32) return fail(c, NMFK_E_UNSUPPORTED, "NMFsparsity: k > 32 is not supported");
+        SolveArgs a;
+        fill_args(batches[i], p, a);
+        CU(c, solve_sparsity(a, c->dtype, c->sp_beta, c->sp_sparsity, c->sp_lambda, c->stream, &c->launches));
+    }
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    CU(c, cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_solve_ms = ms;
+    return NMFK_OK;
+}
+
+int32_t nmfk_set_sparsity_options(nmfk_ctx* c, double beta_divergence, double sparsity, double lambda) {
+    if (!c) return fail(nullptr, NMFK_E_INVALID, "ctx is NULL");
+    if (!(lambda > 0)) return fail(c, NMFK_E_INVALID, "nmfk_set_sparsity_options: lambda must be positive");
+    c->sp_beta = beta_divergence;
+    c->sp_sparsity = sparsity;
+    c->sp_lambda = lambda;
+    return NMFK_OK;
+}
+
 int32_t nmfk_solve(nmfk_ctx* c, nmfk_batch* const* batches, int32_t nb, const nmfk_params* p) {
     if (!c || !batches || nb < 1) return fail(c, NMFK_E_INVALID, "nmfk_solve: bad arguments");
     int32_t rc = check_params(c, p);
@@ -779,6 +810,7 @@ int32_t nmfk_solve(nmfk_ctx* c, nmfk_batch* const* batches, int32_t nb, const nm
         if (!batches[i]->W || !batches[i]->canon) return fail(c, NMFK_E_INVALID, "nmfk_solve: H-only batch");
     }
     if (p->variant == NMFK_VARIANT_FRO) return solve_fro_batches(c, batches, nb, p);
+    if (p->variant == NMFK_VARIANT_SPARSITY) return solve_sparsity_batches(c, batches, nb, p);
     while ((int)c->pool.size() < nb) {
         cudaStream_t s;
         cudaEvent_t ev;

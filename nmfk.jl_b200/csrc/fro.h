@@ -21,4 +21,7 @@ cudaError_t launch_split_lo(const float* x, float* lo, long long len, cudaStream
 // the whole solve (fro_solve.cu); Xlo / Xtlo: lo images of a.X / a.Xt (Float32 only, else nullptr)
 cudaError_t solve_fro(const SolveArgs& a, int dtype, const void* Xlo, const void* Xtlo, cudaStream_t s, int64_t* launches);
 
+// NMFsparsity (sparsity.cu): beta-divergence multiplicative updates with an L1 penalty on H and unit-norm columns of W
+cudaError_t solve_sparsity(const SolveArgs& a, int dtype, double beta, double sparsity, double lam, cudaStream_t s, int64_t* launches);
+
 }  // namespace nmfk

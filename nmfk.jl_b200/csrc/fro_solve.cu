@@ -339,10 +339,49 @@ cudaError_t solve_fro_t(const SolveArgs& a, const void* Xlo, const void* Xtlo, c
     {
         // post-run objective on the caller's X (normnan(X - W*H), NMFkExecute.jl:791-792) + normalisation (:800-804)
         pt.mark(s, -1);
-        dim3 g(nblkObj, R);
-        tiled_objective_kernel<T, T><<<g, 128, (size_t)k * 128 * sizeof(T), s>>>(static_cast<const T*>(a.X), n, m, k, W, static_cast<const T*>(a.H),
-                                                                                 a.st, (T)a.lambda, 1, 0, 1.0, WeightRef{nullptr, nullptr, nullptr},
-                                                                                 objp);
+        // the tensor-core objective kernels of the tiled KL engine when they apply (the scalar kernel takes 39 ms on C3, the
+        // tcgen05 one 4 ms), the scalar kernel otherwise
+        TiledPassArgs po{};
+        po.U = a.W;
+        po.V = a.H;
+        po.st = a.st;
+        po.u_rstride = (long long)n * k;
+        po.v_rstride = (long long)k * m;
+        po.su_o = 1;
+        po.su_a = n;
+        po.sv_t = k;
+        po.sv_a = 1;
+        po.nown = n;
+        po.nred = m;
+        po.k = k;
+        po.R = R;
+        po.S = 1;
+        po.nblocks = nblkObj;
+        po.lambda = a.lambda;
+        po.ktmpl = resident_template_k(k);
+        po.obj_partials = objp;
+        po.obj_weight = 1.0;
+        po.obj_restore = 1;
+        po.obj_sel = 1;
+        po.wait_hint_ns = (32 << 16) | 64;
+        bool done_obj = false;
+        if (F32) {
+            po.D = a.X;
+            if (tc_pass_supported(po)) {
+                FRO_TRY(launch_tc_objective(po, d_err, s));
+                done_obj = true;
+            }
+        } else if (k >= 4) {
+            po.D = a.Xt;  // the DMMA kernel reads the step-contiguous copy
+            FRO_TRY(launch_tiled_dmma_objective(po, s));
+            done_obj = true;
+        }
+        if (!done_obj) {
+            dim3 g(nblkObj, R);
+            tiled_objective_kernel<T, T><<<g, 128, (size_t)k * 128 * sizeof(T), s>>>(static_cast<const T*>(a.X), n, m, k, W,
+                                                                                     static_cast<const T*>(a.H), a.st, (T)a.lambda, 1, 0, 1.0,
+                                                                                     WeightRef{nullptr, nullptr, nullptr}, objp);
+        }
         FRO_TRY(cudaGetLastError());
         tiled_finish_kernel<T><<<R, 256, 0, s>>>(a.W, a.H, a.st, objp, n, m, k, nblkObj, a.normalize);
         FRO_TRY(cudaGetLastError());

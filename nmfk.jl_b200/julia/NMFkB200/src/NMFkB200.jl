@@ -54,8 +54,10 @@ function makeparams(; tol=1e-19, tolOF=1e-3, weight=1, maxiter=10000, maxbaditer
 	if method == :nmf
 		algorithm == :multdiv || error("NMFkB200: method=:nmf covers algorithm=:multdiv (NMF.MultUpdate(obj=:mse)) only")
 		variant = 1
+	elseif method == :sparsity
+		variant = 2 # NMFsparsity (NMFkSparsity.jl); its own options travel through setsparsity! (called by the entry points)
 	elseif method != :simple
-		error("NMFkB200 covers method=:simple and method=:nmf, algorithm=:multdiv; use NMFk for $(method)")
+		error("NMFkB200 covers method=:simple, :sparsity and :nmf with algorithm=:multdiv; use NMFk for $(method)")
 	end
 	w = typeof(weight) <: Number ? weight : 1 # array weights are installed on the context (setweight!)
 	return Params(tol, tolOF, eps(Float64), w, maxiter, maxbaditers, maxreattempts, stopconv, 10, Wfixed, Hfixed, normalize, 0, engine, clusterWmatrix, stop_rule, variant, 0)
@@ -110,6 +112,26 @@ function setweight!(c::Context, ::Type{T}, weight) where {T}
 		check(ccall((:nmfk_set_weight, libnmfk), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64), c.h, w, size(w, 1), size(w, 2)), c.h)
 	end
 	return nothing
+end
+
+"Options of NMFsparsity (NMFkSparsity.jl:1): cost_function / beta_divergence, sparsity, lambda"
+function setsparsity!(c::Context; cost_function::Symbol=:ed, beta_divergence::Number=-1, sparsity::Number=1, lambda::Number=1e-9, kw...)
+	beta = beta_divergence == -1 ? (cost_function == :kl ? 1 : (cost_function == :is ? 0 : 2)) : beta_divergence # :5-22
+	check(ccall((:nmfk_set_sparsity_options, libnmfk), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Cdouble), c.h, beta, sparsity, lambda), c.h)
+end
+
+"NMFk.NMFsparsity(X, k; ...) -> (W, H, objvalue)  (NMFkSparsity.jl:1-113)"
+function NMFsparsity(X::AbstractMatrix{T}, k::Int; maxiter::Int=100000, tol::Number=1e-19, seed::Number=-1, Winit::AbstractMatrix{T}=Matrix{T}(undef, 0, 0), Hinit::AbstractMatrix{T}=Matrix{T}(undef, 0, 0), ctx::Context=Context(), kw...) where {T <: Union{Float32,Float64}}
+	n, m = size(X)
+	setX!(ctx, X)
+	setsparsity!(ctx; kw...)
+	seed != -1 && Random.seed!(seed)
+	Wi, Hi = drawinits(T, n, m, k, 1; Winit=Winit, Hinit=Hinit)
+	p = makeparams(; maxiter=maxiter, tol=tol, normalize=0, method=:sparsity)
+	W = Matrix{T}(undef, n, k); H = Matrix{T}(undef, k, m)
+	ssq = Ref{Cdouble}(0); nrm = Ref{Cdouble}(0); it = Ref{Cint}(0); sr = Ref{Cint}(0)
+	check(ccall((:nmfk_run_batch, libnmfk), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Params}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Cdouble}, Ref{Cdouble}, Ref{Cint}, Ref{Cint}), ctx.h, k, 1, Wi, Hi, p, W, H, ssq, nrm, it, sr), ctx.h)
+	return W, H, ssq[]
 end
 
 "Initial factors for nNMF restarts drawn like the reference: W = rand(n,k) only if Winit is empty, then H = rand(k,m) only if Hinit is empty (NMFkMultiplicative.jl:37-55), restart i seeded seed+i (NMFkExecute.jl:536)"
@@ -203,6 +225,7 @@ function execute_run(X::AbstractMatrix{T}, nk::Int, nNMF::Int; clusterWmatrix::B
 	n, m = size(X)
 	setX!(ctx, X; normalizevector=normalizevector)
 	setweight!(ctx, T, weight)
+	get(kw, :method, :simple) == :sparsity && setsparsity!(ctx; kw...)
 	modifymatrices = !(haskey(kw, :Wfixed) || haskey(kw, :Hfixed)) # NMFkExecute.jl:486-489
 	Wi, Hi = drawinits(T, n, m, nk, nNMF; seed=seed, kw...)
 	# clusterWmatrix is consumed here and NOT forwarded to the restarts (:516-540): they keep the H-row normalisation

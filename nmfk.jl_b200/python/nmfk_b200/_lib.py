@@ -52,6 +52,7 @@ SIGNATURES = {
     "nmfk_set_X": (_i32, [_P, _P, _i64, _i64, _i32, _dbl, _P, _i32]),
     "nmfk_get_xinfo": (_i32, [_P, C.POINTER(XInfo)]),
     "nmfk_set_weight": (_i32, [_P, _P, _i64, _i64]),
+    "nmfk_set_sparsity_options": (_i32, [_P, _dbl, _dbl, _dbl]),
     "nmfk_batch_create": (_i32, [_P, _i32, _i32, C.POINTER(_P)]),
     "nmfk_batch_destroy": (_i32, [_P]),
     "nmfk_batch_set_init": (_i32, [_P, _P, _P]),

@@ -331,8 +331,18 @@ def _params_from_kw(kw: dict, ctx: Optional[Context] = None, **defaults) -> Para
         if algorithm != "multdiv":
             raise NMFkError(-6, "method=:nmf: only algorithm=:multdiv (NMF.MultUpdate(obj=:mse)) is on the B200 path")
         vals["variant"] = 1
+    elif method == "sparsity":  # NMFkExecute.jl:757-758: NMFsparsity(Xn, nk; maxiter, tol, kw...)
+        if ctx is None:
+            raise NMFkError(-1, "method=:sparsity needs a context")
+        beta = kw.pop("beta_divergence", -1)
+        cf = str(kw.pop("cost_function", "ed")).lstrip(":")
+        if beta == -1:  # NMFkSparsity.jl:5-22
+            beta = {"kl": 1, "ed": 2, "is": 0}.get(cf, 2)
+        check(ctx._lib.nmfk_set_sparsity_options(ctx._h, float(beta), float(kw.pop("sparsity", 1)), float(kw.pop("lam_sparsity", 1e-9))),
+              ctx._h)
+        vals["variant"] = 2
     elif method != "simple":
-        raise NMFkError(-6, "method=:%s is not on the B200 path (method=:simple and method=:nmf, algorithm=:multdiv are)" % method)
+        raise NMFkError(-6, "method=:%s is not on the B200 path (:simple, :sparsity and :nmf with algorithm=:multdiv are)" % method)
     for k in list(kw):
         if k in _PARAM_NAMES:
             vals[k] = kw.pop(k)
@@ -381,6 +391,29 @@ def NMFmultiplicative(X, k: int, *, Winit=None, Hinit=None, seed: int = -1, lam:
     try:
         ctx.set_X(X, lam, normalizevector)
         p = _params_from_kw(kw, ctx, maxiter=kw.pop("maxiter", 1000000), normalize=0)
+        b = ctx.batch(k, 1)
+        try:
+            b.set_init(_stack(Winit, 1, (ctx.n, k), ctx.np_dtype, "Winit"), _stack(Hinit, 1, (k, ctx.m), ctx.np_dtype, "Hinit"),
+                       _seed0(seed) - 1)
+            ctx.solve([b], p)
+            r = b.get()
+        finally:
+            b.close()
+        return np.asfortranarray(r["W"][0]), np.asfortranarray(r["H"][0]), float(r["obj_ssq"][0])
+    finally:
+        if own:
+            ctx.close()
+
+
+def NMFsparsity(X, k: int, *, Winit=None, Hinit=None, seed: int = -1, maxiter: int = 100000, tol: float = 1e-19, lam: float = 1e-9,
+                ctx: Context = None, **kw):
+    """`NMFk.NMFsparsity(X, k; cost_function=:ed, beta_divergence=-1, sparsity=1, maxiter=100000, tol=1e-19, lambda=1e-9, Winit, Hinit)`
+    NMFkSparsity.jl:1-113 -> (W, H, objvalue = sum((X - W*H).^2)); `lam` is the reference's `lambda` keyword."""
+    own = ctx is None
+    ctx = ctx or Context()
+    try:
+        ctx.set_X(X)
+        p = _params_from_kw(dict(kw, method="sparsity", lam_sparsity=lam), ctx, maxiter=maxiter, tol=tol, normalize=0)
         b = ctx.batch(k, 1)
         try:
             b.set_init(_stack(Winit, 1, (ctx.n, k), ctx.np_dtype, "Winit"), _stack(Hinit, 1, (k, ctx.m), ctx.np_dtype, "Hinit"),

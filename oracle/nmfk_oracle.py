@@ -355,6 +355,79 @@ def execute_singlerun_nmf(X: np.ndarray, nk: int, *, Winit, Hinit, maxiter: int 
 
 
 # --------------------------------------------------------------------------------------
+# NMFsparsity: src/NMFkSparsity.jl:1-113 (method=:sparsity, src/NMFkExecute.jl:757-758)
+# --------------------------------------------------------------------------------------
+def nmf_sparsity(X: np.ndarray, k: int, *, cost_function: str = "ed", beta_divergence: float = -1, sparsity: float = 1,
+                 maxiter: int = 100000, tol: float = 1e-19, lam: float = 1e-9, Winit: Optional[np.ndarray] = None,
+                 Hinit: Optional[np.ndarray] = None, rng: Optional[np.random.Generator] = None, info: Optional[dict] = None,
+                 trace: Optional[Callable[[int, np.ndarray, np.ndarray, float], None]] = None):
+    """`NMFsparsity(X, k; cost_function=:ed, beta_divergence=-1, sparsity=1, maxiter, tol, lambda=1e-9, Winit, Hinit)`
+    src/NMFkSparsity.jl:1-113 with w_ind = h_ind = trues(k): beta-divergence multiplicative updates with an L1 penalty on H
+    and unit-norm columns of W.  X_est = max.(W*H, lambda) is re-formed after every half-update (:71, :88); the run stops when
+    the relative change of (divergence + sparsity * sum(H)) drops below tol (:101-106).  Returns (W, H, sum((X - W*H)^2))."""
+    if beta_divergence == -1:  # :5-22
+        beta_divergence = {"kl": 1, "ed": 2, "is": 0}.get(cost_function, 2)
+    b = beta_divergence
+    n, m = X.shape
+    if rng is None:
+        rng = np.random.default_rng()
+    W = rng.random(n * k).reshape((n, k), order="F") if Winit is None or Winit.size == 0 else np.array(Winit, copy=True)  # :31-36
+    H = rng.random(k * m).reshape((k, m), order="F") if Hinit is None or Hinit.size == 0 else np.array(Hinit, copy=True)  # :37-42
+    Wn = np.sqrt(np.sum(W ** 2, axis=0, keepdims=True))  # :44-46
+    W = W / Wn
+    H = H * Wn.T
+    X_est = np.maximum(W @ H, lam)  # :48
+    it, last_of, of, stop = 0, None, None, "maxiter"
+    while it < maxiter:  # :56
+        it += 1
+        if b == 1:  # :59-61
+            dph = np.sum(W, axis=0).reshape(k, 1) + sparsity
+            dmh = W.T @ (X / X_est)
+        elif b == 2:  # :62-64
+            dph = W.T @ X_est + sparsity
+            dmh = W.T @ X
+        else:  # :65-67
+            dph = W.T @ X_est ** (b - 1) + sparsity
+            dmh = W.T @ (X * X_est ** (b - 2))
+        dph = np.maximum(dph, lam)  # :69
+        H = H * (dmh / dph)  # :70
+        X_est = np.maximum(W @ H, lam)  # :71
+        if b == 1:  # :74-76
+            A = (X / X_est) @ H.T
+            dpw = np.sum(H, axis=1).reshape(1, k) + np.sum(A * W, axis=0, keepdims=True) * W
+            dmw = A + np.sum(np.sum(H, axis=1).reshape(1, k) * W, axis=0, keepdims=True) * W
+        elif b == 2:  # :77-79
+            dpw = X_est @ H.T + np.sum((X @ H.T) * W, axis=0, keepdims=True) * W
+            dmw = X @ H.T + np.sum((X_est @ H.T) * W, axis=0, keepdims=True) * W
+        else:  # :80-82
+            A1, A2 = X_est ** (b - 1) @ H.T, (X * X_est ** (b - 2)) @ H.T
+            dpw = A1 + np.sum(A2 * W, axis=0, keepdims=True) * W
+            dmw = A2 + np.sum(A1 * W, axis=0, keepdims=True) * W
+        dpw = np.maximum(dpw, lam)  # :84
+        W = W * (dmw / dpw)  # :85
+        W = W / np.sqrt(np.sum(W ** 2, axis=0, keepdims=True))  # :86
+        X_est = np.maximum(W @ H, lam)  # :87
+        if b == 1:  # :89-98
+            div = float(np.sum(X * np.log(X / X_est) - X + X_est))
+        elif b == 2:
+            div = float(np.sum((X - X_est) ** 2))
+        elif b == 0:
+            div = float(np.sum(X / X_est - np.log(X / X_est) - 1))
+        else:
+            div = float(np.sum(X ** b + (b - 1) * X_est ** b - b * X * X_est ** (b - 1)) / (b * (b - 1)))
+        of = div + float(np.sum(H * sparsity))  # :99
+        if trace is not None:
+            trace(it, W, H, of)
+        if it > 1 and tol > 0 and (abs(of - last_of) / last_of) < tol:  # :101-106
+            stop = "tol"
+            break
+        last_of = of
+    if info is not None:
+        info.update(iters=it, stop_reason=stop, objective=of)
+    return W, H, float(np.sum((X - W @ H) ** 2))  # :109-110
+
+
+# --------------------------------------------------------------------------------------
 # One restart as reached from execute: src/NMFkExecute.jl:729-807
 # --------------------------------------------------------------------------------------
 def execute_singlerun_compute(

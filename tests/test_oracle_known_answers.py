@@ -226,3 +226,19 @@ def test_execute_run_filters_follow_the_reference_index_mix():
     det = {}
     o.execute_run(X.copy(), 2, 5, seed=3, maxiter=50, acceptratio=0.6, details=det)
     assert det["idxsol"].tolist() == [True, True, True, False, False] and det["labels"].shape == (2, 3)
+
+
+def test_nmfsparsity_oracle_properties():
+    """NMFsparsity (NMFkSparsity.jl): W keeps unit-norm columns (:86); with sparsity = 0 and beta = 2 the Euclidean divergence of
+    the clamped model never increases; the L1 penalty shrinks sum(H)."""
+    rng = np.random.default_rng(11)
+    X = rng.random((30, 3)) @ rng.random((3, 20)) + 0.01
+    W0, H0 = rng.random((30, 3)), rng.random((3, 20))
+    objs = []
+    W, H, _ = o.nmf_sparsity(X, 3, Winit=W0, Hinit=H0, sparsity=0, maxiter=200, trace=lambda it, W, H, of: objs.append(of))
+    assert np.allclose(np.linalg.norm(W, axis=0), 1.0) and all(b <= a * (1 + 1e-10) for a, b in zip(objs, objs[1:]))
+    _, Hs, _ = o.nmf_sparsity(X, 3, Winit=W0, Hinit=H0, sparsity=5.0, maxiter=200)
+    assert Hs.sum() < H.sum()
+    inf = {}
+    o.nmf_sparsity(X, 3, Winit=W0, Hinit=H0, sparsity=0.1, maxiter=100000, tol=1e-6, info=inf)
+    assert inf["stop_reason"] == "tol" and 1 < inf["iters"] < 100000
