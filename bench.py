@@ -308,6 +308,8 @@ def fixed_budget_single(ctx, nb, synth, torch, cfg, args, iters, flush, k=None, 
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ctx.set_X(Xpin.numpy().T)  # H2D of X + preprocessing
+        if os.environ.get("NMFK_TILED_TIMING"):
+            print("[bench] e2e set_X %.1f ms" % ((time.perf_counter() - t0) * 1e3), file=sys.stderr)
         phi, rob, aic, tot = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
         nb._lib.check(ctx._lib.nmfk_execute_run(ctx._h, k, R, C.c_void_p(Wpin.data_ptr()), C.c_void_p(Hpin.data_ptr()), SEED0,
                                                 C.byref(params), Wb.ctypes.data_as(C.c_void_p), Hb.ctypes.data_as(C.c_void_p),

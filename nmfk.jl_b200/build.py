@@ -22,7 +22,7 @@ LIB = os.path.join(LIBDIR, "libnmfk_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 UNITS = ["capi.cu", "kl_resident_f64.cu", "kl_resident_f32.cu", "kl_dmma.cu", "kl_tiled.cu", "kl_tiled_f64.cu", "kl_tiled_f32.cu", "preprocess.cu", "cluster.cu",
-         "objective.cu", "microbench.cu", "tc_selftest.cu", "kl_tiled_tc.cu", "kl_tiled_dmma.cu", "fro_gemm.cu", "fro_gemm_f64.cu",
+         "objective.cu", "microbench.cu", "tc_selftest.cu", "kl_tiled_tc.cu", "kl_tiled_tc2.cu", "kl_tiled_dmma.cu", "fro_gemm.cu", "fro_gemm_f64.cu",
          "fro_solve.cu", "kmeans.cu", "sparsity.cu"]
 
 

@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -16,6 +17,7 @@
 
 #include "../../include/nmfk_b200.h"
 #include "fro.h"
+#include "kl_tiled_args.h"
 #include "nmfk_internal.h"
 #include "philox.h"
 
@@ -49,6 +51,10 @@ struct nmfk_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     void* Xp = nullptr;
     void* Xpt = nullptr;
+    // nmfk_set_X keeps the two images and the H2D staging buffer when the next X has the same size (a sweep over data sets, the
+    // end-to-end bench): three 0.4 GB allocations per call otherwise
+    void* Xstage = nullptr;
+    size_t Xbytes = 0;
     // normalizevector (NMFkMultiplicative.jl:27-31): the solver streams Xn = Xp ./ nv (and its transpose); Xp stays the
     // caller's matrix for the final objective (:119-125)
     void* Xn = nullptr;
@@ -127,9 +133,9 @@ struct DevBuf {
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() {
-        if (p) cudaFree(p);
+        if (p) dev_free(p);
     }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    cudaError_t alloc(size_t bytes) { return dev_malloc(&p, bytes ? bytes : 1); }
     void* release() {
         void* q = p;
         p = nullptr;
@@ -143,7 +149,7 @@ struct DevBuf {
 
 void free_X(nmfk_ctx* c) {
     for (void** q : {&c->Xp, &c->Xpt, &c->Xn, &c->Xnt, &c->nv, &c->wrow, &c->wcol, &c->wmat, &c->Xlo, &c->Xtlo}) {
-        if (*q) cudaFree(*q);
+        if (*q) dev_free(*q);
         *q = nullptr;
     }
     c->has_X = false;
@@ -152,10 +158,10 @@ void free_X(nmfk_ctx* c) {
 // persistent scratch of the ctx (clustering phase): at least `bytes`, contents undefined
 cudaError_t ctx_scratch(nmfk_ctx* c, size_t bytes, void** out) {
     if (c->scratch_cap < bytes) {
-        if (c->scratch) cudaFree(c->scratch);
+        if (c->scratch) dev_free(c->scratch);
         c->scratch = nullptr;
         c->scratch_cap = 0;
-        cudaError_t e = cudaMalloc(&c->scratch, bytes);
+        cudaError_t e = dev_malloc(&c->scratch, bytes);
         if (e != cudaSuccess) return e;
         c->scratch_cap = bytes;
     }
@@ -350,6 +356,15 @@ int32_t nmfk_ctx_create(int32_t device, nmfk_ctx** out) {
         delete c;
         return fail(nullptr, (int32_t)e, msg);
     }
+    {  // scratch of the solves comes from the stream-ordered pool: keep freed blocks instead of returning them to the driver
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    (void)pinned_flags();
+    tc2_pass_prepare();
     *out = c;
     return NMFK_OK;
 }
@@ -361,8 +376,9 @@ int32_t nmfk_ctx_destroy(nmfk_ctx* c) {
     nmfk_ctx_comm_destroy(c);
     free_X(c);
     c->prof.destroy();
-    if (c->scratch) cudaFree(c->scratch);
-    if (c->d_partials) cudaFree(c->d_partials);
+    if (c->scratch) dev_free(c->scratch);
+    if (c->Xstage) dev_free(c->Xstage);
+    if (c->d_partials) dev_free(c->d_partials);
     for (auto s : c->pool) cudaStreamDestroy(s);
     for (auto e : c->pool_ev) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -388,15 +404,27 @@ int32_t nmfk_set_X(nmfk_ctx* c, const void* X, int64_t n, int64_t m, int32_t dty
     if (n <= 0 || m <= 0) return fail(c, NMFK_E_EMPTY, "Input array has a zero dimension!");
     if (n > INT32_MAX || m > INT32_MAX) return fail(c, NMFK_E_UNSUPPORTED, "nmfk_set_X: dimension exceeds int32");
     CU(c, cudaSetDevice(c->device));
-    free_X(c);
     const size_t es = esize(dtype);
     const size_t bytes = (size_t)n * m * es;
     DevBuf Xp, Xpt, raw, stats, rf, cf, bm, Xn, Xnt, nv;
-    CU(c, Xp.alloc(bytes));
-    CU(c, Xpt.alloc(bytes));
+    if (c->Xp && c->Xpt && c->Xbytes == bytes) {  // same size as the previous X: reuse its images
+        Xp.p = c->Xp;
+        Xpt.p = c->Xpt;
+        c->Xp = c->Xpt = nullptr;
+    }
+    raw.p = c->Xstage;
+    c->Xstage = nullptr;
+    if (c->Xbytes != bytes && raw.p) {
+        dev_free(raw.p);
+        raw.p = nullptr;
+    }
+    free_X(c);
+    c->Xbytes = bytes;
+    if (!Xp.p) CU(c, Xp.alloc(bytes));
+    if (!Xpt.p) CU(c, Xpt.alloc(bytes));
     const void* src = X;
     if (!on_device) {
-        CU(c, raw.alloc(bytes));
+        if (!raw.p) CU(c, raw.alloc(bytes));
         CU(c, cudaMemcpyAsync(raw.p, X, bytes, cudaMemcpyHostToDevice, c->stream));
         src = raw.p;
     }
@@ -441,6 +469,7 @@ int32_t nmfk_set_X(nmfk_ctx* c, const void* X, int64_t n, int64_t m, int32_t dty
     if (hs.nneg > 0 && hs.nnan == 0) return fail(c, NMFK_E_NEGATIVE, "All matrix entries must be nonnegative!");
     c->Xp = Xp.release();
     c->Xpt = Xpt.release();
+    if (bytes <= ((size_t)2 << 30)) c->Xstage = raw.release();  // larger staging copies are not worth keeping
     c->Xn = Xn.release();
     c->Xnt = Xnt.release();
     c->nv = nv.release();
@@ -453,7 +482,7 @@ int32_t nmfk_set_weight(nmfk_ctx* c, const void* w, int64_t rows, int64_t cols) 
     if (!c->has_X) return fail(c, NMFK_E_NO_X, "nmfk_set_X has not been called");
     CU(c, cudaSetDevice(c->device));
     for (void** q : {&c->wrow, &c->wcol, &c->wmat}) {
-        if (*q) cudaFree(*q);
+        if (*q) dev_free(*q);
         *q = nullptr;
     }
     if (!w) return NMFK_OK;
@@ -468,7 +497,7 @@ int32_t nmfk_set_weight(nmfk_ctx* c, const void* w, int64_t rows, int64_t cols) 
     else
         return fail(c, NMFK_E_SHAPE, "nmfk_set_weight: weight must be n x 1, 1 x m or n x m");
     const size_t bytes = (size_t)rows * cols * esize(c->dtype);
-    CU(c, cudaMalloc(dst, bytes));
+    CU(c, dev_malloc(dst, bytes));
     CU(c, cudaMemcpyAsync(*dst, w, bytes, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return NMFK_OK;
@@ -492,11 +521,11 @@ int32_t nmfk_batch_create(nmfk_ctx* c, int32_t k, int32_t R, nmfk_batch** out) {
     b->k = k;
     b->R = R;
     const size_t es = esize(c->dtype);
-    cudaError_t e = cudaMalloc(&b->W, (size_t)c->n * k * R * es);
-    if (e == cudaSuccess) e = cudaMalloc(&b->H, (size_t)k * c->m * R * es);
-    if (e == cudaSuccess) e = cudaMalloc(&b->st, (size_t)R * sizeof(UnitState));
-    if (e == cudaSuccess) e = cudaMalloc(&b->canon, (size_t)R * c->m * sizeof(int32_t));
-    if (e == cudaSuccess && c->info.nnan > 0) e = cudaMalloc(&b->ximp, (size_t)R * c->n * c->m * es);
+    cudaError_t e = dev_malloc(&b->W, (size_t)c->n * k * R * es);
+    if (e == cudaSuccess) e = dev_malloc(&b->H, (size_t)k * c->m * R * es);
+    if (e == cudaSuccess) e = dev_malloc(&b->st, (size_t)R * sizeof(UnitState));
+    if (e == cudaSuccess) e = dev_malloc(&b->canon, (size_t)R * c->m * sizeof(int32_t));
+    if (e == cudaSuccess && c->info.nnan > 0) e = dev_malloc(&b->ximp, (size_t)R * c->n * c->m * es);
     if (e != cudaSuccess) {
         nmfk_batch_destroy(b);
         CU(c, e);
@@ -515,8 +544,8 @@ int32_t nmfk_batch_create_hstack(nmfk_ctx* c, int32_t k, int32_t R, nmfk_batch**
     b->ctx = c;
     b->k = k;
     b->R = R;
-    cudaError_t e = cudaMalloc(&b->H, (size_t)k * c->m * R * esize(c->dtype));
-    if (e == cudaSuccess) e = cudaMalloc(&b->st, (size_t)R * sizeof(UnitState));
+    cudaError_t e = dev_malloc(&b->H, (size_t)k * c->m * R * esize(c->dtype));
+    if (e == cudaSuccess) e = dev_malloc(&b->st, (size_t)R * sizeof(UnitState));
     if (e != cudaSuccess) {
         nmfk_batch_destroy(b);
         CU(c, e);
@@ -562,11 +591,11 @@ int32_t nmfk_batch_import(nmfk_batch* b, const void* W, const void* H, const dou
 int32_t nmfk_batch_destroy(nmfk_batch* b) {
     if (!b) return NMFK_OK;
     if (b->ctx) cudaSetDevice(b->ctx->device);
-    if (b->W) cudaFree(b->W);
-    if (b->H) cudaFree(b->H);
-    if (b->st) cudaFree(b->st);
-    if (b->canon) cudaFree(b->canon);
-    if (b->ximp) cudaFree(b->ximp);
+    if (b->W) dev_free(b->W);
+    if (b->H) dev_free(b->H);
+    if (b->st) dev_free(b->st);
+    if (b->canon) dev_free(b->canon);
+    if (b->ximp) dev_free(b->ximp);
     delete b;
     return NMFK_OK;
 }
@@ -588,13 +617,6 @@ static int32_t reset_state(nmfk_batch* b) {
     return NMFK_OK;
 }
 
-template <typename T>
-static bool has_nan_host(const T* p, size_t len) {
-    for (size_t i = 0; i < len; ++i)
-        if (p[i] != p[i]) return true;
-    return false;
-}
-
 static void reset_selection(nmfk_batch* b) {
     b->has_sel = false;
     b->sel.clear();
@@ -607,20 +629,33 @@ int32_t nmfk_batch_set_init_partial(nmfk_batch* b, const void* Winit, const void
     CU(c, cudaSetDevice(c->device));
     if (!b->W) return fail(c, NMFK_E_INVALID, "nmfk_batch_set_init: H-only batch");
     const size_t wl = (size_t)c->n * b->k * b->R, hl = (size_t)b->k * c->m * b->R;
-    bool wn = false, hn = false;
-    if (c->dtype == NMFK_F64) {
-        wn = Winit && has_nan_host((const double*)Winit, wl);
-        hn = Hinit && has_nan_host((const double*)Hinit, hl);
-    } else {
-        wn = Winit && has_nan_host((const float*)Winit, wl);
-        hn = Hinit && has_nan_host((const float*)Hinit, hl);
-    }
-    if (wn) return fail(c, NMFK_E_NAN_INIT, "Initial values for the W matrix entries include NaNs!");
-    if (hn) return fail(c, NMFK_E_NAN_INIT, "Initial values for the H matrix entries include NaNs!");
     if (c->sharded && (c->row0 + c->n > c->n_global))
         return fail(c, NMFK_E_SHAPE, "row-sharded ctx: row0 + local rows exceeds n_global");
     if (Winit) CU(c, cudaMemcpyAsync(b->W, Winit, wl * esize(c->dtype), cudaMemcpyHostToDevice, c->stream));
     if (Hinit) CU(c, cudaMemcpyAsync(b->H, Hinit, hl * esize(c->dtype), cudaMemcpyHostToDevice, c->stream));
+    if (Winit || Hinit) {
+        // "Initial values for the W / H matrix entries include NaNs!" (NMFkMultiplicative.jl:41, 52): checked on the device
+        // copies (a single host thread scanning 82 MB of C3 initial factors cost 10 ms per call)
+        DevBuf flags;
+        const int R = b->R;
+        CU(c, flags.alloc((size_t)2 * R * sizeof(int32_t)));
+        int32_t* f = flags.as<int32_t>();
+        if (Winit) CU(c, launch_count_nan(nullptr, b->W, 0, (int64_t)c->n * b->k, R, c->dtype, f, c->stream));
+        if (Hinit) CU(c, launch_count_nan(nullptr, b->H, 0, (int64_t)b->k * c->m, R, c->dtype, f + R, c->stream));
+        c->launches += (Winit ? 1 : 0) + (Hinit ? 1 : 0);
+        std::vector<int32_t> hf((size_t)2 * R, 0);
+        if (Winit) CU(c, cudaMemcpyAsync(hf.data(), f, (size_t)R * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        if (Hinit) CU(c, cudaMemcpyAsync(hf.data() + R, f + R, (size_t)R * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        bool wn = false, hn = false;
+        for (int r = 0; r < R; ++r) {
+            wn = wn || hf[r] != 0;
+            hn = hn || hf[(size_t)R + r] != 0;
+        }
+        if (wn || hn) b->inited = false;
+        if (wn) return fail(c, NMFK_E_NAN_INIT, "Initial values for the W matrix entries include NaNs!");
+        if (hn) return fail(c, NMFK_E_NAN_INIT, "Initial values for the H matrix entries include NaNs!");
+    }
     if (!Winit || !Hinit) {
         // the missing factor(s) from restart r's Philox stream: W = rand(n,k) only if Winit is empty, THEN H = rand(k,m) only
         // if Hinit is empty (NMFkMultiplicative.jl:37-55), so a lone missing factor takes the first numbers of the stream
@@ -748,8 +783,8 @@ static int32_t solve_fro_batches(nmfk_ctx* c, nmfk_batch* const* batches, int32_
                                                "the driver must provide cuTensorMapEncodeTiled");
         if (!c->Xlo) {
             const size_t bytes = (size_t)c->n * c->m * sizeof(float);
-            CU(c, cudaMalloc(&c->Xlo, bytes));
-            CU(c, cudaMalloc(&c->Xtlo, bytes));
+            CU(c, dev_malloc(&c->Xlo, bytes));
+            CU(c, dev_malloc(&c->Xtlo, bytes));
             CU(c, launch_split_lo((const float*)c->Xp, (float*)c->Xlo, (long long)c->n * c->m, c->stream));
             CU(c, launch_split_lo((const float*)c->Xpt, (float*)c->Xtlo, (long long)c->n * c->m, c->stream));
             c->launches += 2;
@@ -926,9 +961,9 @@ int32_t nmfk_batch_get(nmfk_batch* b, void* W_out, void* H_out, double* obj_ssq,
 static int32_t residual(nmfk_ctx* c, int k, const void* W, const void* H, int restore, double weight, double out[2]) {
     const int nb = residual_blocks((int)c->n);
     if (c->partials_cap < (size_t)nb * 2) {
-        if (c->d_partials) cudaFree(c->d_partials);
+        if (c->d_partials) dev_free(c->d_partials);
         c->d_partials = nullptr;
-        CU(c, cudaMalloc(&c->d_partials, (size_t)nb * 2 * sizeof(double)));
+        CU(c, dev_malloc(&c->d_partials, (size_t)nb * 2 * sizeof(double)));
         c->partials_cap = (size_t)nb * 2;
     }
     CU(c, launch_residual(c->Xp, c->dtype, (int)c->n, (int)c->m, k, W, H, c->lambda, restore, weight,
@@ -1090,7 +1125,7 @@ int32_t nmfk_batch_cluster(nmfk_batch* b, int32_t clusterWmatrix, int32_t* order
     // fired: vcat (:449) made fresh matrices.
     a.alias_best = clusterWmatrix ? ((char*)b->W + (size_t)order[0] * c->n * k * esize(c->dtype)) : nullptr;
     CU(c, launch_cluster(a, c->dtype, c->stream));
-    c->launches += 6 + (clusterWmatrix ? 1 : 0);
+    c->launches += 5 + cluster_walk_launches(k, len, R) + (clusterWmatrix ? 1 : 0);
     CU(c, cudaMemcpyAsync(labels.data(), a.labels, labels.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaMemcpyAsync(sil.data(), a.sil, sil.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaMemcpyAsync(csil.data(), a.clustersil, csil.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1359,18 +1394,28 @@ int32_t nmfk_execute_run(nmfk_ctx* c, int32_t k, int32_t R, const void* Winit, c
                          const nmfk_params* p, void* W_best, void* H_best, double* phi, double* robustness, double* aic,
                          int64_t* total_iters) {
     if (!c || !p) return fail(c, NMFK_E_INVALID, "nmfk_execute_run: NULL argument");
+    const bool timing = getenv("NMFK_TILED_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
     nmfk_batch* b = nullptr;
     int32_t rc = nmfk_batch_create(c, k, R, &b);
     if (rc) return rc;
+    const double t_create = ms();
     rc = nmfk_batch_set_init_partial(b, Winit, Hinit, seed0);  // either may be NULL (NMFkMultiplicative.jl:37-55)
+    const double t_init = ms();
     if (!rc) rc = nmfk_solve(c, &b, 1, p);
+    const double t_solve = ms();
     std::vector<char> Wb, Hb;
     if (!rc) rc = finish_run(b, p->clusterWmatrix != 0, Wb, Hb, phi, robustness, aic, total_iters);
+    const double t_finish = ms();
     if (!rc) {
         if (W_best) std::memcpy(W_best, Wb.data(), Wb.size());
         if (H_best) std::memcpy(H_best, Hb.data(), Hb.size());
     }
     nmfk_batch_destroy(b);
+    if (timing)
+        fprintf(stderr, "[nmfk timing] execute_run host wall clock: create %.1f, init %.1f, solve %.1f, cluster + select + scores %.1f, destroy %.1f ms\n",
+                t_create, t_init - t_create, t_solve - t_init, t_finish - t_solve, ms() - t_finish);
     return rc;
 }
 
@@ -1550,7 +1595,7 @@ int32_t nmfk_sweep(nmfk_ctx* c, const int32_t* ks, int32_t nks, int32_t R_local,
             const int gbest = order[0], br = gbest / R_local, bl = gbest % R_local;
             const size_t wb = (size_t)c->n * k * es, hb = (size_t)k * c->m * es;
             if (wtmp.p) {
-                cudaFree(wtmp.p);
+                dev_free(wtmp.p);
                 wtmp.p = nullptr;
             }
             CU(c, wtmp.alloc(wb));

@@ -168,6 +168,112 @@ __global__ void __launch_bounds__(1024) cluster_kernel(double* __restrict__ V, i
     for (int e = tid; e < k * ld; e += NT) cent[e] = cent[e] / (double)R;
 }
 
+// The same walk as cluster_kernel spread over the whole GPU: the trials stay sequential, but the k x k distances of a trial are
+// independent (one warp each, the SAME fixed-order reduction as in cluster_kernel, so results are bit-identical) and so are
+// the elements of the centroid update.  Three small launches per trial; used when a trial has enough work to pay for them
+// (C3: 256 dot products of length 10000 per trial took one SM 0.3 ms, 20 ms per call).
+__global__ void cluster_prep_kernel(double* __restrict__ V, int len, int ld, int k, int R, const int* __restrict__ bias,
+                                    int* __restrict__ labels) {
+    const double b = (*bias) ? 1.0 : 0.0;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x, gn = gridDim.x * blockDim.x;
+    for (int row = gid; row < R * k; row += gn) V[(long long)row * ld + len] = b;
+    for (int e = gid; e < k * R; e += gn) labels[e] = e < k ? e + 1 : 0;  // labels[:,1] = 1:k (:461)
+}
+__global__ void cluster_seed_kernel(const double* __restrict__ V, int ld, int k, double* __restrict__ cent) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x, gn = gridDim.x * blockDim.x;
+    for (int e = gid; e < k * ld; e += gn) cent[e] = V[e];  // centSeeds = newClusterCenters = factors[1] (:453-455)
+}
+__global__ void __launch_bounds__(256) cluster_dist_kernel(const double* __restrict__ Vt, const double* __restrict__ cent, int len,
+                                                           int ld, int k, const int* __restrict__ bias, double* __restrict__ D) {
+    const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (pair >= k * k) return;
+    const int L = (*bias) ? len + 1 : len;
+    const int f = pair % k, c = pair / k;
+    const double* x = Vt + (long long)f * ld;
+    const double* y = cent + (long long)c * ld;
+    double ab = 0.0, a2 = 0.0, b2 = 0.0;
+    for (int j = lane; j < L; j += 32) {
+        const double xv = x[j], yv = y[j];
+        ab = fma(xv, yv, ab);
+        a2 = fma(xv, xv, a2);
+        b2 = fma(yv, yv, b2);
+    }
+    ab = wsum(ab);
+    a2 = wsum(a2);
+    b2 = wsum(b2);
+    if (lane == 0) {
+        double d = 1.0 - ab / (sqrt(a2) * sqrt(b2));
+        d = (d != d) ? 0.0 : (d < 0.0 ? 0.0 : d);
+        D[pair] = d;
+    }
+}
+// greedy matching of one trial (:474-485): one warp, first (column-major) global minimum each round
+__global__ void cluster_assign_kernel(double* __restrict__ D, int k, int t, int* __restrict__ labels, int* __restrict__ assign) {
+    const int lane = threadIdx.x;
+    for (int c = lane; c < k; c += 32) assign[c] = -1;
+    __syncwarp();
+    for (int round = 0; round < k; ++round) {
+        double bv = INFINITY;
+        int bi = INT_MAX;
+        for (int e = lane; e < k * k; e += 32) {
+            const double v = D[e];
+            if (v < bv) {
+                bv = v;
+                bi = e;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov < bv || (ov == bv && oi < bi)) {
+                bv = ov;
+                bi = oi;
+            }
+        }
+        if (!(bv < INFINITY)) break;
+        const int f = bi % k, c = bi / k;
+        if (lane == 0) {
+            labels[f + (long long)t * k] = c + 1;
+            assign[c] = f;
+        }
+        for (int e = lane; e < k; e += 32) {
+            D[f + e * k] = INFINITY;
+            D[e + c * k] = INFINITY;
+        }
+        __syncwarp();
+    }
+}
+__global__ void cluster_update_kernel(const double* __restrict__ Vt, double* __restrict__ cent, int len, int ld, int k,
+                                      const int* __restrict__ bias, const int* __restrict__ assign) {
+    const int L = (*bias) ? len + 1 : len;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)k * L; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e / L), j = (int)(e - (long long)c * L);
+        const int f = assign[c];
+        if (f >= 0) cent[(long long)c * ld + j] += Vt[(long long)f * ld + j];  // newClusterCenters[:, c] .+= W[:, f]
+    }
+}
+__global__ void cluster_finish_kernel(double* __restrict__ cent, int ld, int k, int R, int* __restrict__ labels) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x, gn = gridDim.x * blockDim.x;
+    for (int t = gid; t < R; t += gn) {  // repair of unassigned labels (:487-496)
+        int* col = labels + (long long)t * k;
+        int s = 0;
+        bool anyzero = false;
+        for (int a = 0; a < k; ++a) {
+            s += col[a];
+            anyzero |= (col[a] == 0);
+        }
+        if (anyzero) {
+            if (s == 0)
+                for (int a = 0; a < k; ++a) col[a] = a + 1;
+            else
+                for (int a = 0; a < k; ++a)
+                    if (col[a] == 0) col[a] = a + 1;
+        }
+    }
+    for (int e = gid; e < k * ld; e += gn) cent[e] = cent[e] / (double)R;  // newClusterCenters ./= numTrials (:512)
+}
+
 // clusterWmatrix = true without the zero-column fix: `centSeeds` / `newClusterCenters` of the reference ARE the best solution's
 // W (NMFkCluster.jl:426-428, 453-455: no copy on this branch), so after clustersolutions that matrix holds the centroids
 // (:484, :512) and finalize / Wbest (NMFkExecute.jl:631-637) read them.  Mirror it: centroids -> the best W (factor type) and
@@ -410,6 +516,9 @@ cudaError_t launch_point_silhouettes(double* V, int len, int ld, int N, int k, c
     return cudaGetLastError();
 }
 
+// kernels the clustersolutions walk launches (the wide walk is three launches per trial)
+int cluster_walk_launches(int k, int len, int R) { return ((long long)k * k * len >= 200000 && R >= 2) ? 3 * (R - 1) + 3 : 1; }
+
 cudaError_t launch_cluster(const ClusterArgs& a, int dtype, cudaStream_t s) {
     const int N = a.R * a.k, ld = a.len + 1;
     cudaError_t e;
@@ -426,8 +535,25 @@ cudaError_t launch_cluster(const ClusterArgs& a, int dtype, cudaStream_t s) {
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     {
-        const size_t smem = (size_t)a.k * a.k * sizeof(double) + (size_t)a.k * sizeof(int);
-        cluster_kernel<<<1, 1024, smem, s>>>(a.V, a.len, ld, a.k, a.R, a.bias, a.cent, a.labels);
+        if (cluster_walk_launches(a.k, a.len, a.R) > 1) {
+            // wide walk: the k x k distances and the assignment flags of a trial live at the start of the (still unused) N x N matrix
+            double* D = a.Dm;
+            int* assign = reinterpret_cast<int*>(a.Dm + (size_t)a.k * a.k);
+            const int pb = (a.k * a.k + 7) / 8;
+            const int ub = (int)std::min<long long>(((long long)a.k * ld + 255) / 256, 148 * 8);
+            cluster_prep_kernel<<<std::min((N + 255) / 256, 148), 256, 0, s>>>(a.V, a.len, ld, a.k, a.R, a.bias, a.labels);
+            cluster_seed_kernel<<<ub, 256, 0, s>>>(a.V, ld, a.k, a.cent);
+            for (int t = 1; t < a.R; ++t) {
+                const double* Vt = a.V + (long long)t * a.k * ld;
+                cluster_dist_kernel<<<pb, 256, 0, s>>>(Vt, a.cent, a.len, ld, a.k, a.bias, D);
+                cluster_assign_kernel<<<1, 32, 0, s>>>(D, a.k, t, a.labels, assign);
+                cluster_update_kernel<<<ub, 256, 0, s>>>(Vt, a.cent, a.len, ld, a.k, a.bias, assign);
+            }
+            cluster_finish_kernel<<<ub, 256, 0, s>>>(a.cent, ld, a.k, a.R, a.labels);
+        } else {
+            const size_t smem = (size_t)a.k * a.k * sizeof(double) + (size_t)a.k * sizeof(int);
+            cluster_kernel<<<1, 1024, smem, s>>>(a.V, a.len, ld, a.k, a.R, a.bias, a.cent, a.labels);
+        }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (a.alias_best != nullptr) {

@@ -34,6 +34,7 @@
 
 #include "fro.h"
 #include "tc_ptx.cuh"
+#include "tma.cuh"
 
 namespace nmfk {
 namespace {
@@ -46,32 +47,10 @@ constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // A hi | A lo | B hi | 
 constexpr int EPI_WARPS = 8, THREADS = (2 + EPI_WARPS) * 32;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
 // [rows x kdim] row-major FP32 matrix (leading dimension ld floats) -> boxes of box_rows x 32 floats, 128-byte swizzle;
 // out-of-range elements read as zero (edge tiles contribute nothing)
 bool make_map(CUtensorMap* map, const void* base, long long rows, long long kdim, long long ld, int box_rows) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return false;
-    cuuint64_t dims[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return tma_make_map_f32(map, base, kdim, rows, ld, BK, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // K-major operand tile in SWIZZLE_128B layout: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO); the leading byte
@@ -86,12 +65,6 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
     return d;
 }
 
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                     tc::smem_u32(dst)),
-                 "l"(map), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1)
-                 : "memory");
-}
 __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
@@ -294,7 +267,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 
 }  // namespace
 
-bool fro_gemm_supported(long long N, long long K) { return encode_fn() != nullptr && (K % 4) == 0 && (N % 4) == 0 && K >= 4; }
+bool fro_gemm_supported(long long N, long long K) { return tma_encode_fn() != nullptr && (K % 4) == 0 && (N % 4) == 0 && K >= 4; }
 
 static int fro_cluster(int M) {
     static int cluster_env = -1;

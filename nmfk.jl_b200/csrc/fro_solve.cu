@@ -240,20 +240,21 @@ cudaError_t solve_fro_t(const SolveArgs& a, const void* Xlo, const void* Xtlo, c
     // the stacked GEMMs, apply_H / impute = the two apply kernels, clamp_check = the convergence kernel)
     PhaseTimer pt;
     pt.on = getenv("NMFK_TILED_TIMING") != nullptr;
-    FRO_TRY(cudaMalloc(&Ht, (size_t)Rk * m * sizeof(T)));
-    FRO_TRY(cudaMalloc(&Nbuf, std::max((size_t)NSH * Rk * m, (size_t)NSW * Rk * n) * sizeof(T)));
+    FRO_TRY(scratch_alloc(&Ht, (size_t)Rk * m * sizeof(T), s));
+    FRO_TRY(scratch_alloc(&Nbuf, std::max((size_t)NSH * Rk * m, (size_t)NSW * Rk * n) * sizeof(T), s));
     if (F32) {
-        FRO_TRY(cudaMalloc(&Wlo, (size_t)Rk * n * sizeof(float)));
-        FRO_TRY(cudaMalloc(&Htlo, (size_t)Rk * m * sizeof(float)));
+        FRO_TRY(scratch_alloc(&Wlo, (size_t)Rk * n * sizeof(float), s));
+        FRO_TRY(scratch_alloc(&Htlo, (size_t)Rk * m * sizeof(float), s));
     }
-    FRO_TRY(cudaMalloc(&Gpart, (size_t)R * std::max(SW, SH) * k * k * sizeof(double)));
-    FRO_TRY(cudaMalloc(&convW, (size_t)R * tilesW * k * 2 * sizeof(double)));
-    FRO_TRY(cudaMalloc(&convH, (size_t)R * tilesH * k * 2 * sizeof(double)));
-    FRO_TRY(cudaMalloc(&objp, (size_t)R * nblkObj * 2 * sizeof(double)));
-    FRO_TRY(cudaMalloc(&d_active, 2 * sizeof(int)));
+    FRO_TRY(scratch_alloc(&Gpart, (size_t)R * std::max(SW, SH) * k * k * sizeof(double), s));
+    FRO_TRY(scratch_alloc(&convW, (size_t)R * tilesW * k * 2 * sizeof(double), s));
+    FRO_TRY(scratch_alloc(&convH, (size_t)R * tilesH * k * 2 * sizeof(double), s));
+    FRO_TRY(scratch_alloc(&objp, (size_t)R * nblkObj * 2 * sizeof(double), s));
+    FRO_TRY(scratch_alloc(&d_active, 2 * sizeof(int), s));
     d_err = d_active + 1;
     FRO_TRY(cudaMemsetAsync(d_active, 0, 2 * sizeof(int), s));
-    FRO_TRY(cudaMallocHost(&h_active, 2 * sizeof(int)));
+    h_active = pinned_flags();
+    if (h_active == nullptr) FRO_TRY(cudaErrorMemoryAllocation);
     FRO_TRY(cudaMemcpyAsync(hst.data(), a.st, (size_t)R * sizeof(UnitState), cudaMemcpyDeviceToHost, s));
     FRO_TRY(cudaStreamSynchronize(s));
     for (auto& u : hst)
@@ -394,16 +395,15 @@ cudaError_t solve_fro_t(const SolveArgs& a, const void* Xlo, const void* Xtlo, c
     }
 done:
     if (h_active && h_active[1] != 0) fprintf(stderr, "[nmfk] fro_gemm_kernel: barrier time-out at site %d (protocol error)\n", h_active[1]);
-    if (Ht) cudaFree(Ht);
-    if (Nbuf) cudaFree(Nbuf);
-    if (Wlo) cudaFree(Wlo);
-    if (Htlo) cudaFree(Htlo);
-    if (Gpart) cudaFree(Gpart);
-    if (convW) cudaFree(convW);
-    if (convH) cudaFree(convH);
-    if (objp) cudaFree(objp);
-    if (d_active) cudaFree(d_active);
-    if (h_active) cudaFreeHost(h_active);
+    scratch_free(Ht, s);
+    scratch_free(Nbuf, s);
+    scratch_free(Wlo, s);
+    scratch_free(Htlo, s);
+    scratch_free(Gpart, s);
+    scratch_free(convW, s);
+    scratch_free(convH, s);
+    scratch_free(objp, s);
+    scratch_free(d_active, s);
     return err;
 }
 

@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
+#include <chrono>
 #include <vector>
 
 #include "kl_resident.cuh"  // load_row, warp_sum, block_sum, div_cold, VecOf
@@ -739,6 +740,9 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     const bool sharded = sh != nullptr;
     PhaseTimer pt;
     pt.on = getenv("NMFK_TILED_TIMING") != nullptr;
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
+    double host_setup_ms = 0.0;
     const int it_begin_report = 0;
     (void)it_begin_report;
     TC* den = nullptr;  // R x 32, followed by red (R x m x kt) when sharded
@@ -793,15 +797,17 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     };
   // column sums of W would need another exchange
 
-    NMFK_TRY(cudaMalloc(&den, ((size_t)R * 32 + redsz) * sizeof(TC)));
+    NMFK_TRY(scratch_alloc(&den, ((size_t)R * 32 + redsz) * sizeof(TC), s));
     if (sharded) red = den + (size_t)R * 32;
-    NMFK_TRY(cudaMalloc(&obj2, (size_t)R * 2 * sizeof(double)));
-    if (psz) NMFK_TRY(cudaMalloc(&partial, psz * sizeof(TC)));
-    NMFK_TRY(cudaMalloc(&objp, (size_t)R * nblkObj * 2 * sizeof(double)));
-    NMFK_TRY(cudaMalloc(&d_active, sizeof(int)));
-    NMFK_TRY(cudaMalloc(&fin_tot, (size_t)R * 32 * sizeof(double)));
-    NMFK_TRY(cudaMalloc(&fin_flag, (size_t)R * sizeof(int)));
-    NMFK_TRY(cudaMallocHost(&h_active, 2 * sizeof(int)));
+    NMFK_TRY(scratch_alloc(&obj2, (size_t)R * 2 * sizeof(double), s));
+    if (psz) NMFK_TRY(scratch_alloc(&partial, psz * sizeof(TC), s));
+    NMFK_TRY(scratch_alloc(&objp, (size_t)R * nblkObj * 2 * sizeof(double), s));
+    NMFK_TRY(scratch_alloc(&d_active, sizeof(int), s));
+    NMFK_TRY(scratch_alloc(&fin_tot, (size_t)R * 32 * sizeof(double), s));
+    NMFK_TRY(scratch_alloc(&fin_flag, (size_t)R * sizeof(int), s));
+    h_active = pinned_flags();
+    if (h_active == nullptr) NMFK_TRY(cudaErrorMemoryAllocation);
+    h_active[0] = h_active[1] = 0;
     h_active[1] = 0;
     NMFK_TRY(cudaMemcpyAsync(hst.data(), a.st, (size_t)R * sizeof(UnitState), cudaMemcpyDeviceToHost, s));
     NMFK_TRY(cudaStreamSynchronize(s));
@@ -872,6 +878,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
             ph.trace = d_trace;
         }
         bool need_guard = true;
+        host_setup_ms = host_ms();
         while (true) {
             if (need_guard) {
                 NMFK_TRY(cudaMemsetAsync(d_active, 0, sizeof(int), s));
@@ -1027,19 +1034,19 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
         NMFK_TRY(cudaStreamSynchronize(s));
         if (a.prof) a.prof->harvest();
         pt.harvest();
+        if (pt.on) fprintf(stderr, "[nmfk timing] host wall clock: set-up %.1f ms, whole solve %.1f ms\n", host_setup_ms, host_ms());
         pt.report(it, sharded ? sh->rank : 0);
     }
 done:
     if (h_active && h_active[1] != 0)
         fprintf(stderr, "[nmfk] tc_pass_kernel: barrier time-out at site %d (protocol error)\n", h_active[1]);
-    if (den) cudaFree(den);
-    if (partial) cudaFree(partial);
-    if (objp) cudaFree(objp);
-    if (obj2) cudaFree(obj2);
-    if (d_active) cudaFree(d_active);
-    if (fin_tot) cudaFree(fin_tot);
-    if (fin_flag) cudaFree(fin_flag);
-    if (h_active) cudaFreeHost(h_active);
+    scratch_free(den, s);
+    scratch_free(partial, s);
+    scratch_free(objp, s);
+    scratch_free(obj2, s);
+    scratch_free(d_active, s);
+    scratch_free(fin_tot, s);
+    scratch_free(fin_flag, s);
     return err;
 }
 

@@ -38,6 +38,12 @@ int tc_pass_group(int k);  // restarts that share one X tile inside a CTA
 int tc_pass_ctas_per_sm(int k);
 int tc_pass_chunk(int k);  // steps per chunk (slices hold whole chunks)
 cudaError_t launch_tc_pass(const TiledPassArgs& a, int* d_errflag, cudaStream_t s);
+// second generation for k <= 16 (kl_tiled_tc2.cu): U in shared memory, separate P and Q tiles; same grid and arguments
+bool tc2_pass_enabled(int k);
+cudaError_t launch_tc2_pass(const TiledPassArgs& a, int* d_errflag, cudaStream_t s);
+// one-time host-side set-up (driver entry point of the tensor-map encoder, kernel attributes): called when a context is
+// created so that it never falls inside a timed solve
+void tc2_pass_prepare();
 // Float32 objective sums on the same machinery (MMA#1 only): a = the W-update arguments (D = X, U = W, V = H), S = 1
 cudaError_t launch_tc_objective(const TiledPassArgs& a, int* d_errflag, cudaStream_t s);
 

@@ -185,6 +185,7 @@ struct ClusterArgs {
                           // the reference's aliased newClusterCenters (NMFkCluster.jl:453-455); nullptr otherwise
 };
 cudaError_t launch_cluster(const ClusterArgs& a, int dtype, cudaStream_t s);
+int cluster_walk_launches(int k, int len, int R);
 cudaError_t launch_zero_nan(void* p, long long len, int dtype, cudaStream_t s);
 // per-cluster means / corrected variances over the trials (NMFkFinalize.jl:68-74); outputs are device buffers of the factor type
 cudaError_t launch_cluster_means(const void* F, int len, int k, int R, int use_W, const int32_t* d_order, const int32_t* d_amap,
@@ -205,5 +206,42 @@ cudaError_t umma_peak(double* tflops, cudaStream_t s);
 cudaError_t umma_timing(const float* U, const float* V, int reps, long long* out8, float* bias, cudaStream_t s);
 cudaError_t umma_selftest(const float* U, const float* V, int mode, float* Pss, float* Pts, float* ACCa, float* ACCb, int* err,
                           cudaStream_t s);
+
+// Pinned host words for the device -> host flags of a solve, allocated once per host thread: cudaMallocHost / cudaFreeHost
+// synchronise the device and take up to hundreds of milliseconds, which showed up as sporadic 0.3 - 0.6 s stalls inside timed
+// solves.  Solves are synchronous (they return after their last stream synchronisation), so one buffer per thread is enough.
+inline int* pinned_flags() {
+    static thread_local int* p = nullptr;
+    if (!p && cudaMallocHost(&p, 64) != cudaSuccess) p = nullptr;
+    return p;
+}
+// Device buffers of the entry points (X images, factor stacks, temporaries): pooled like the scratch of the solves, but with
+// the semantics of cudaMalloc / cudaFree - usable from any stream once dev_malloc returns (host-synchronised allocation), and
+// freed only after everything on the device has finished.  cudaMalloc / cudaFree of the 0.4 GB X images and of the factor stacks
+// cost 50 - 300 ms per nmfk_execute_run call (map / unmap in the driver); the pool keeps the blocks.
+inline cudaError_t dev_malloc(void** p, size_t bytes) {
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 16, cudaStreamPerThread);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
+    return e;
+}
+template <typename T>
+inline cudaError_t dev_malloc(T** p, size_t bytes) {
+    return dev_malloc(reinterpret_cast<void**>(p), bytes);
+}
+inline void dev_free(void* p) {
+    if (!p) return;
+    cudaDeviceSynchronize();
+    cudaFreeAsync(p, cudaStreamPerThread);
+}
+// Device scratch of a solve comes from the stream-ordered pool (release threshold raised when the context is created): no
+// device-wide synchronisation and, in the steady state, no driver call at all.
+inline cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t s) { return cudaMallocAsync(p, bytes ? bytes : 16, s); }
+template <typename T>
+inline cudaError_t scratch_alloc(T** p, size_t bytes, cudaStream_t s) {
+    return scratch_alloc(reinterpret_cast<void**>(p), bytes, s);
+}
+inline void scratch_free(void* p, cudaStream_t s) {
+    if (p) cudaFreeAsync(p, s);
+}
 
 }  // namespace nmfk

@@ -321,13 +321,14 @@ cudaError_t solve_sparsity_t(const SolveArgs& a, double beta, double sparsity, d
             goto done;                      \
         }                                   \
     } while (0)
-    SP_TRY(cudaMalloc(&Aest, (size_t)R * std::max(n, m) * KM * sizeof(T)));
-    SP_TRY(cudaMalloc(&Ax, (size_t)R * std::max(n, m) * KM * sizeof(T)));
-    SP_TRY(cudaMalloc(&cst, (size_t)R * 64 * sizeof(double)));
-    SP_TRY(cudaMalloc(&part, (size_t)R * nblk * sizeof(double)));
-    SP_TRY(cudaMalloc(&objp, (size_t)R * nblkObj * 2 * sizeof(double)));
-    SP_TRY(cudaMalloc(&d_active, sizeof(int)));
-    SP_TRY(cudaMallocHost(&h_active, sizeof(int)));
+    SP_TRY(scratch_alloc(&Aest, (size_t)R * std::max(n, m) * KM * sizeof(T), s));
+    SP_TRY(scratch_alloc(&Ax, (size_t)R * std::max(n, m) * KM * sizeof(T), s));
+    SP_TRY(scratch_alloc(&cst, (size_t)R * 64 * sizeof(double), s));
+    SP_TRY(scratch_alloc(&part, (size_t)R * nblk * sizeof(double), s));
+    SP_TRY(scratch_alloc(&objp, (size_t)R * nblkObj * 2 * sizeof(double), s));
+    SP_TRY(scratch_alloc(&d_active, sizeof(int), s));
+    h_active = pinned_flags();
+    if (h_active == nullptr) SP_TRY(cudaErrorMemoryAllocation);
     SP_TRY(cudaMemcpyAsync(hst.data(), a.st, (size_t)R * sizeof(UnitState), cudaMemcpyDeviceToHost, s));
     SP_TRY(cudaStreamSynchronize(s));
     for (auto& u : hst)
@@ -376,13 +377,12 @@ cudaError_t solve_sparsity_t(const SolveArgs& a, double beta, double sparsity, d
     }
 done:
 #undef SP_TRY
-    if (Aest) cudaFree(Aest);
-    if (Ax) cudaFree(Ax);
-    if (cst) cudaFree(cst);
-    if (part) cudaFree(part);
-    if (objp) cudaFree(objp);
-    if (d_active) cudaFree(d_active);
-    if (h_active) cudaFreeHost(h_active);
+    scratch_free(Aest, s);
+    scratch_free(Ax, s);
+    scratch_free(cst, s);
+    scratch_free(part, s);
+    scratch_free(objp, s);
+    scratch_free(d_active, s);
     return err;
 }
 

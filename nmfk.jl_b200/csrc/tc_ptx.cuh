@@ -51,10 +51,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking test of a phase (no suspension): for roles that poll several barriers
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // bounded wait; `where` identifies the call site in *errflag on time-out
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* errflag, int where) {
     for (uint32_t spin = 0; spin < (1u << 28); ++spin)
         if (mbar_try_wait(bar, parity)) return;
+    if (errflag) atomicExch(errflag, where);
+    __threadfence_system();
+    __trap();
+}
+
+// spin on the non-suspending test (the suspending try_wait wakes up late when the phase completes just after the thread was parked)
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity, int* errflag, int where) {
+    for (uint32_t spin = 0; spin < (1u << 28); ++spin)
+        if (mbar_test(bar, parity)) return;
     if (errflag) atomicExch(errflag, where);
     __threadfence_system();
     __trap();
@@ -141,6 +160,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16p(uint32_t taddr, const uint32_t* r) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
         "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),

@@ -7,6 +7,8 @@
 // with Q = 0.5 * (U V^T) computed by scalar FMAs and split as hi = q & 0xffffe000, lo = q - hi.
 // tests/test_gpu_parity.py compares the four outputs with NumPy.
 #include "nmfk_internal.h"
+#include <cstdio>
+
 #include "tc_ptx.cuh"
 
 namespace nmfk {
@@ -155,10 +157,13 @@ __global__ void __launch_bounds__(128) umma_timing_kernel(const float* __restric
     __shared__ __align__(128) float B1[TS * KP];
     __shared__ __align__(128) float B2[2 * KP * TS];  // 32 rows: the N = 32 timing reads rows 16..31 (zeros)
     __shared__ __align__(8) uint64_t bar[1];
+    __shared__ __align__(8) uint64_t scratch_bar[2];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
     if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
     if (tid == 0) {
+        tc::mbar_init(&scratch_bar[0], 1);
+        tc::mbar_init(&scratch_bar[1], 1);
         tc::mbar_init(&bar[0], 1);
         tc::mbar_fence_init();
     }
@@ -235,6 +240,110 @@ __global__ void __launch_bounds__(128) umma_timing_kernel(const float* __restric
     timed(3, 96, 32, false, false);
     timed(6, 96, 64, true, false);
     timed(7, 96, 16, false, true);
+    // Burst experiments (reps has bit 20 set): how long the issuing thread is held by the short MMA bursts of the KL pass -
+    // mode 0: 16 small MMAs (8 x N=32 + 8 x N=16, chained, A from tensor memory) + 2 commits; 1: + 1 commit; 2: no commit;
+    // 3: 6 x N=64 (A from tensor memory) + commit; 4: alternating 3 and 0; 5: as 4 with two of the six N=64 MMAs reading A from
+    // shared memory.  Prints the cycles per burst spent issuing and the cycles per burst until completion.
+    if (reps & (1 << 20)) {
+        for (int mode = 0; mode < 6; ++mode) {
+            long long t0 = 0, t1 = 0;
+            if (warp == 0) {
+                tc::tc_fence_after_sync();
+                const uint32_t id64 = tc::idesc_tf32(M, 64, 0), id32 = tc::idesc_tf32(M, 32, 0), id16 = tc::idesc_tf32(M, 16, 0);
+                const uint64_t da = tc::smem_desc(tc::smem_u32(As), LBO, SBO_K16), db1 = tc::smem_desc(tc::smem_u32(B1), LBO, SBO_K16);
+                const uint64_t db2 = tc::smem_desc(tc::smem_u32(B2), LBO, SBO_K64);
+                t0 = clock64();
+                if (tc::elect_one()) {
+                    for (int burst = 0; burst < 16; ++burst) {
+                        const bool big = mode == 3 || (mode >= 4 && (burst & 1) == 0);
+                        if (big) {
+                            const uint32_t d = tbase + 320 + (burst & 2) * 32;
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {
+                                if (mode == 5)
+                                    tc::mma_tf32_ss(d, da + ks * 16, db1 + ks * 16, id64, ks > 0);
+                                else
+                                    tc::mma_tf32_ts(d, tbase + C_U + ks * 8, db1 + ks * 16, id64, ks > 0);
+                                tc::mma_tf32_ts(d, tbase + C_U + ks * 8, db1 + ks * 16, id64, 1);
+                                tc::mma_tf32_ts(d, tbase + C_U + ks * 8, db1 + ks * 16, id64, 1);
+                            }
+                            tc::mma_commit(&scratch_bar[0]);
+                        } else {
+                            const uint32_t d = tbase + 448 + (burst & 2) * 16;
+#pragma unroll
+                            for (int ks = 0; ks < 8; ++ks) tc::mma_tf32_ts(d, tbase + C_QH + ks * 8, db2 + ks * 16, id32, ks > 0);
+#pragma unroll
+                            for (int ks = 0; ks < 8; ++ks) tc::mma_tf32_ts(d, tbase + C_QL + ks * 8, db2 + ks * 16, id16, 1);
+                            if (mode != 2) tc::mma_commit(&scratch_bar[0]);
+                            if (mode == 0 || mode >= 4) tc::mma_commit(&scratch_bar[1]);
+                        }
+                    }
+                    t1 = clock64();
+                    tc::mma_commit(&bar[0]);
+                }
+                __syncwarp();
+            }
+            tc::mbar_wait(&bar[0], phase, errflag, 4);
+            phase ^= 1;
+            tc::tc_fence_after_sync();
+            const long long t2 = clock64();
+            if (warp == 0) {
+                const long long ti = __shfl_sync(0xffffffffu, t1, 0) | 0;  // only the elected lane holds t1
+                long long tmax = t1;
+                for (int off = 16; off > 0; off >>= 1) tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, off));
+                (void)ti;
+                if (tid == 0) printf("burst mode %d: issue %lld clk / burst, complete %lld clk / burst\n", mode, (tmax - t0) / 16, (t2 - t0) / 16);
+            }
+            tc::tc_fence_before_sync();
+            __syncthreads();
+        }
+    }
+    // Tensor-memory load / store throughput with all four warps (one per 32-lane quarter) streaming, alone and while the
+    // tensor pipe runs a long series of N = 64 MMAs (reps bit 20): clk per 4 x 32 x 32 x 4 B = 16 KB.
+    if (reps & (1 << 20)) {
+        for (int mode = 0; mode < 4; ++mode) {  // 0: loads, 1: stores, 2: loads under MMA, 3: stores under MMA
+            __syncthreads();
+            if ((mode & 2) && warp == 0) {
+                tc::tc_fence_after_sync();
+                const uint32_t id64 = tc::idesc_tf32(M, 64, 0);
+                const uint64_t db1 = tc::smem_desc(tc::smem_u32(B1), LBO, SBO_K16);
+                if (tc::elect_one()) {
+                    for (int i = 0; i < 64; ++i) tc::mma_tf32_ts(tbase + 320, tbase + C_U, db1, id64, 1);
+                    tc::mma_commit(&bar[0]);
+                }
+                __syncwarp();
+            }
+            uint32_t r32[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r32[j] = tid + j;
+            uint32_t sink = 0;
+            const long long t0 = clock64();
+            for (int i = 0; i < 32; ++i) {
+                if (mode & 1) {
+                    tc::tmem_st32(lane_base + 384 + (i & 1) * 32, r32);
+                } else {
+                    tc::tmem_ld32(lane_base + 384 + (i & 1) * 32, r32);
+                    if ((i & 7) == 7) {
+                        tc::tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sink ^= r32[j];
+                    }
+                }
+            }
+            if (mode & 1) tc::tmem_wait_st(); else tc::tmem_wait_ld();
+            const long long t1 = clock64();
+            if (sink == 0x9e3779b9u) out[0] = 1;
+            if (mode & 2) {
+                tc::mbar_wait(&bar[0], phase, errflag, 5);
+                phase ^= 1;
+                tc::tc_fence_after_sync();
+            }
+            const long long t2 = clock64();
+            if (tid == 0) printf("tmem mode %d: %lld clk per 16 KB (4 warps x x32), mma series done after %lld clk (2048+ alone)\n", mode, (t1 - t0) / 32, t2 - t0);
+            tc::tc_fence_before_sync();
+            __syncthreads();
+        }
+    }
     {
         uint32_t r32[32];
         long long t0 = clock64();
@@ -259,7 +368,7 @@ __global__ void __launch_bounds__(128) umma_timing_kernel(const float* __restric
     if (tid == 0) {
         tc::tc_fence_after_sync();
         const uint32_t id = tc::idesc_tf32(M, KP, 0);
-        for (int i = 0; i < reps * 8; ++i)
+        for (int i = 0; i < (reps & 0xfffff) * 8; ++i)
             tc::mma_tf32_ts(tbase + C_ACCA, tbase + C_QH + (i & 7) * 8, tc::smem_desc(tc::smem_u32(B2) + (i & 7) * 2 * LBO, LBO, SBO_K64), id,
                             i > 0);
         tc::mma_commit(&bar[0]);

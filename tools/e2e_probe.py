@@ -1,0 +1,33 @@
+"""Where the end-to-end C3 step spends its host time: nmfk_set_X (H2D + preprocessing) and nmfk_execute_run, 10 steps."""
+import ctypes as C
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "nmfk.jl_b200", "python"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import nmfk_b200 as nb  # noqa: E402
+from nmfk_b200 import synth  # noqa: E402
+
+n = m = 10000
+k, R = 16, 64
+X = synth.mixture(n, m, 16, seed=2015, dtype=np.float32)
+Xpin = torch.from_numpy(np.ascontiguousarray(X.T)).pin_memory()
+W0, H0 = synth.philox_inits(7, R, n, k, m, dtype=np.float32)
+Wpin, Hpin = torch.from_numpy(W0).pin_memory(), torch.from_numpy(H0).pin_memory()
+Wb, Hb = np.empty((k, n), np.float32), np.empty((m, k), np.float32)
+with nb.Context(0) as ctx:
+    params = nb.default_params(maxiter=20, engine=2)
+    for i in range(10):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.set_X(Xpin.numpy().T)
+        t1 = time.perf_counter()
+        phi, rob, aic, tot = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        nb._lib.check(ctx._lib.nmfk_execute_run(ctx._h, k, R, C.c_void_p(Wpin.data_ptr()), C.c_void_p(Hpin.data_ptr()), 1,
+                                                C.byref(params), Wb.ctypes.data_as(C.c_void_p), Hb.ctypes.data_as(C.c_void_p),
+                                                C.byref(phi), C.byref(rob), C.byref(aic), C.byref(tot)), ctx._h)
+        t2 = time.perf_counter()
+        print("step %d: set_X %.1f ms, execute_run %.1f ms (solve %.1f ms)" % (i, (t1 - t0) * 1e3, (t2 - t1) * 1e3, ctx.last_solve_ms), flush=True)

@@ -21,6 +21,14 @@ with nb.Context(0) as ctx:
 t = np.fromfile("/tmp/tc_trace.bin", dtype=np.int64).reshape(3, 64, 8)
 t0 = t[t > 0].min()
 q, mm, st = t[0], t[1], t[2]
+if os.environ.get("NMFK_TC_GEN", "2") != "1":
+    print("gen2 quotient detail (group 0): unit | pwait ldP half0 afullwait drain+st0 half1+st1 arrive | cycle")
+    for u in range(8, 40, 2):
+        qq = q[u]
+        if qq[0] == 0 or q[u + 2, 0] == 0:
+            break
+        print("%4d | %6d %5d %6d %6d %6d %6d %6d | %6d" % (u, qq[1] - qq[0], qq[2] - qq[1], qq[5] - qq[2], qq[6] - qq[5], qq[7] - qq[6],
+                                                         qq[3] - qq[7], qq[4] - qq[3], q[u + 2, 0] - qq[0]))
 print("unit | quotient group 0 (even units): pwait  ld  compute+drain  st+arrive | cycle of 2 units || mma (this unit): qwait mma2-issue vwait mma1-issue || stager: cpwait vempty convert")
 for u in range(8, 40, 2):
     if q[u, 0] == 0 or q[u + 2, 0] == 0:
