@@ -64,7 +64,7 @@ WORKLOADS = {
 }
 ITERS = {"C3": 20, "C4": 3, "C5": 10}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full` captures
-TRAFFIC = {"C3": (893748480, "profiles/r02_tc_pass_c3.txt"), "C4": (None, None), "C5": (None, None), "C2": (17534720, "profiles/r01_resident_dmma_v3_k10.txt")}
+TRAFFIC = {"C3": (908832000, "profiles/r02_tc2_pass_c3.txt"), "C4": (None, None), "C5": (None, None), "C2": (17534720, "profiles/r01_resident_dmma_v3_k10.txt")}
 
 
 def blas_threads():
@@ -450,7 +450,7 @@ def main():
             "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOADS["C3"] % iters, "engine": "tiled; tcgen05.mma kind::tf32 3-term split (kl_tiled_tc.cu)",
+            "config": {"workload": WORKLOADS["C3"] % iters, "engine": "tiled; tcgen05.mma kind::tf32 3-term split, X tiles by tensor-map TMA (kl_tiled_tc2.cu)",
                        "l2": "inputs larger than L2: X is 400 MB (and its transpose another 400 MB) against 126 MB of L2; 256 MiB "
                              "are also written between steps", "restart_iterations_per_step": r["iters_per_step"],
                        "step_ms": r["step_ms"],
@@ -463,7 +463,7 @@ def main():
             "gpu_launches": int(r["launches"]),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "tc_pass_kernel<K8,N2,WIDE,0> (one launch = one half-update of all 64 restarts)",
+                         "kernel": "tc2_pass_kernel<16> (one launch = one half-update of all 64 restarts)",
                          "launch_ms": per_launch_ms, "launches_timed": int(r["pass_launches"]),
                          "algorithmic_flops_per_launch": r["flops_per_pass"],
                          "algorithmic_bytes_per_launch": float(r["n"]) * r["m"] * 4,
@@ -472,8 +472,9 @@ def main():
                                         "(TF32 = half of it = %.1f)" % (tf32, mp.get("bf16_tflops", float("nan")),
                                                                        mp.get("bf16_tflops", float("nan")) / 2),
                          "frac_of_fp32_ffma_peak": achieved / ffma, "fp32_ffma_peak": ffma,
-                         "what_bounds": "the CUDA-core quotient stage (MUFU.RCP + hi/lo split + tensor-memory traffic of Q), not "
-                                        "the tensor pipe: see DESIGN.md 4a",
+                         "what_bounds": "latency, not a pipe: the 16 quotient warps (4 per scheduler) spend a unit in tensor-memory round "
+                                        "trips, shared-memory loads and fixed-latency arithmetic with nothing to switch to; tensor pipe "
+                                        "23 %, issue slots 64 %, no unit above 45 % (profiles/r02_tc2_pass_c3.txt, DESIGN.md 4a)",
                          "hbm_gbs_if_streaming_only": float(r["n"]) * r["m"] * 4 / (per_launch_ms * 1e-3) / 1e9,
                          "hbm_peak_gbs": mp.get("hbm_gbs")}}
         if not args.no_cpu_baseline:
