@@ -959,7 +959,7 @@ int32_t nmfk_batch_get(nmfk_batch* b, void* W_out, void* H_out, double* obj_ssq,
 
 // residual sums of one (W,H) device pair; out[0] = weighted ssq, out[1] = plain ssq
 static int32_t residual(nmfk_ctx* c, int k, const void* W, const void* H, int restore, double weight, double out[2]) {
-    const int nb = residual_blocks((int)c->n);
+    const int nb = residual_blocks((int)c->n, (int)c->m);
     if (c->partials_cap < (size_t)nb * 2) {
         if (c->d_partials) dev_free(c->d_partials);
         c->d_partials = nullptr;

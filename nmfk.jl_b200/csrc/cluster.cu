@@ -183,7 +183,7 @@ __global__ void cluster_seed_kernel(const double* __restrict__ V, int ld, int k,
     const int gid = blockIdx.x * blockDim.x + threadIdx.x, gn = gridDim.x * blockDim.x;
     for (int e = gid; e < k * ld; e += gn) cent[e] = V[e];  // centSeeds = newClusterCenters = factors[1] (:453-455)
 }
-__global__ void __launch_bounds__(256) cluster_dist_kernel(const double* __restrict__ Vt, const double* __restrict__ cent, int len,
+__global__ void __launch_bounds__(64) cluster_dist_kernel(const double* __restrict__ Vt, const double* __restrict__ cent, int len,
                                                            int ld, int k, const int* __restrict__ bias, double* __restrict__ D) {
     const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (pair >= k * k) return;
@@ -192,7 +192,22 @@ __global__ void __launch_bounds__(256) cluster_dist_kernel(const double* __restr
     const double* x = Vt + (long long)f * ld;
     const double* y = cent + (long long)c * ld;
     double ab = 0.0, a2 = 0.0, b2 = 0.0;
-    for (int j = lane; j < L; j += 32) {
+    int j = lane;
+    for (; j + 7 * 32 < L; j += 8 * 32) {  // eight loads of each vector in flight; the sums keep the order of the plain loop
+        double xv[8], yv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            xv[u] = x[j + u * 32];
+            yv[u] = y[j + u * 32];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            ab = fma(xv[u], yv[u], ab);
+            a2 = fma(xv[u], xv[u], a2);
+            b2 = fma(yv[u], yv[u], b2);
+        }
+    }
+    for (; j < L; j += 32) {
         const double xv = x[j], yv = y[j];
         ab = fma(xv, yv, ab);
         a2 = fma(xv, xv, a2);
@@ -539,13 +554,13 @@ cudaError_t launch_cluster(const ClusterArgs& a, int dtype, cudaStream_t s) {
             // wide walk: the k x k distances and the assignment flags of a trial live at the start of the (still unused) N x N matrix
             double* D = a.Dm;
             int* assign = reinterpret_cast<int*>(a.Dm + (size_t)a.k * a.k);
-            const int pb = (a.k * a.k + 7) / 8;
+            const int pb = (a.k * a.k + 1) / 2;  // two warps (pairs) per CTA: k^2 / 2 CTAs
             const int ub = (int)std::min<long long>(((long long)a.k * ld + 255) / 256, 148 * 8);
             cluster_prep_kernel<<<std::min((N + 255) / 256, 148), 256, 0, s>>>(a.V, a.len, ld, a.k, a.R, a.bias, a.labels);
             cluster_seed_kernel<<<ub, 256, 0, s>>>(a.V, ld, a.k, a.cent);
             for (int t = 1; t < a.R; ++t) {
                 const double* Vt = a.V + (long long)t * a.k * ld;
-                cluster_dist_kernel<<<pb, 256, 0, s>>>(Vt, a.cent, a.len, ld, a.k, a.bias, D);
+                cluster_dist_kernel<<<pb, 64, 0, s>>>(Vt, a.cent, a.len, ld, a.k, a.bias, D);
                 cluster_assign_kernel<<<1, 32, 0, s>>>(D, a.k, t, a.labels, assign);
                 cluster_update_kernel<<<ub, 256, 0, s>>>(Vt, a.cent, a.len, ld, a.k, a.bias, assign);
             }

@@ -148,7 +148,7 @@ bool resident_dmma_fits(int n, int m, int k);
 bool resident_fits(int n, int m, int k, size_t sizeofTC);
 
 // generic residual sums of one (W,H): partials[2*b] = weighted ssq, partials[2*b+1] = plain ssq of CTA b
-int residual_blocks(int n);
+int residual_blocks(int n, int m);
 cudaError_t launch_residual(const void* X, int dtype, int n, int m, int k, const void* W, const void* H, double lambda,
                             int restore, double weight, const WeightRef& wref, double* d_partials, cudaStream_t s);
 
