@@ -384,6 +384,11 @@ int32_t nmfk_ctx_destroy(nmfk_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
+    {  // hand the pooled blocks of this context back to the driver
+        cudaMemPool_t pool = nullptr;
+        cudaStreamSynchronize(cudaStreamPerThread);
+        if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
     delete c;
     return NMFK_OK;
 }
