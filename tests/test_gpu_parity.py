@@ -423,6 +423,44 @@ def test_tc_tiled_trace_parity_f32(ctx, n, m, k, niter):
     assert np.allclose(ob, obr, rtol=2e-3, atol=1e-12 + 1e-5 * obr.max())
 
 
+def test_tc_generations_agree(ctx, tmp_path):
+    """k <= 16 runs the second-generation tcgen05 pass (kl_tiled_tc2.cu); NMFK_TC_GEN=1 selects the first one (kl_tiled_tc.cu), which
+    still serves 16 < k <= 32.  Same inputs through both (the first in a child process: the switch is read once per process), ragged
+    sizes (edge tiles of the tensor-map TMA load, a partial last chunk, an odd number of restarts per group); the oracle comparisons
+    of this file run the default, i.e. the second generation."""
+    import os
+    import subprocess
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n, m, k, R, niter = 1156, 840, 12, 7, 6
+    X = synth.mixture(n, m, 4, seed=31, dtype=np.float32)
+    W0, H0 = synth.philox_inits(41, R, n, k, m, dtype=np.float32)
+    np.savez(tmp_path / "in.npz", X=X, W0=W0, H0=H0)
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import nmfk_b200 as nb\n"
+        "d = np.load(%r)\n"
+        "with nb.Context(0) as ctx:\n"
+        "    ctx.set_X(d['X'])\n"
+        "    b = ctx.batch(%d, %d); b.set_init(d['W0'], d['H0'])\n"
+        "    ctx.solve([b], nb.default_params(maxiter=%d, engine=2))\n"
+        "    g = b.get(); np.savez(%r, W=g['W'], H=g['H'], iters=g['iters'])\n"
+    ) % (os.path.join(ROOT, "nmfk.jl_b200", "python"), ROOT, str(tmp_path / "in.npz"), k, R, niter, str(tmp_path / "gen1.npz"))
+    env = dict(os.environ, NMFK_TC_GEN="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    g1 = np.load(tmp_path / "gen1.npz")
+    ctx.set_X(X)
+    b = ctx.batch(k, R)
+    b.set_init(W0, H0)
+    ctx.solve([b], nb.default_params(maxiter=niter, engine=2))
+    g2 = b.get()
+    b.close()
+    assert relerr(g2["W"], g1["W"]) < 2e-5 and relerr(g2["H"], g1["H"]) < 2e-5
+    assert np.array_equal(g2["iters"], g1["iters"])
+
+
 @pytest.mark.parametrize("n,m,k,R", [(2048, 512, 16, 9), (20000, 1000, 24, 5), (1000, 5000, 8, 6)])
 def test_tc_tiled_restart_groups_match_scalar_pass(ctx, n, m, k, R):
     """Several restarts per CTA (ragged last group), sliced reductions and edge tiles: the tcgen05 pass and the
