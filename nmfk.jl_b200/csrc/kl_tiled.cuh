@@ -729,7 +729,16 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
         const long long smax = std::max(1, nred / ((use_tc ? tc_pass_chunk(k) : (use_td ? tiled_dmma_chunk() : TCH)) * 8));
         if (S > smax) S = smax;
         if (S < 1) S = 1;
-        return (int)S;
+        // wave quantisation: one CTA per SM, so a grid of 3.46 waves (C4, 32 restarts per GPU: 16 own blocks x 32) runs as 4.  A few
+        // more slices are worth their combine pass when they fill the last wave (>= 5 % of the launch).
+        auto eff = [&](long long s_) {
+            const long long ctas = (long long)nblk * units * s_;
+            return (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
+        };
+        long long best = S;
+        for (long long s2 = S + 1; s2 <= std::min(smax, S + 3); ++s2)
+            if (eff(s2) > eff(best) + 0.05) best = s2;
+        return (int)best;
     };
     const int SH = slices(nblkH, n), SW = slices(nblkW, m);
     const int nblkObj = (n + 127) / 128;
