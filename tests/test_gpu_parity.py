@@ -423,6 +423,28 @@ def test_tc_tiled_trace_parity_f32(ctx, n, m, k, niter):
     assert np.allclose(ob, obr, rtol=2e-3, atol=1e-12 + 1e-5 * obr.max())
 
 
+def test_tc2_random_shapes_match_scalar_pass(ctx):
+    """Randomised ragged shapes (tools/tc2_stress.py) through the tcgen05 pass and the scalar-FMA pass of the tiled engine:
+    own / reduction sizes that are not multiples of the 128 x 64 tile, 1..9 restarts (odd groups -> shadow units), k = 1..16."""
+    rng = np.random.default_rng(123)
+    for c in range(14):
+        n = int(rng.choice([4, 8, 64, 128, 132, 260, 1000, 3108])) if c % 3 else 4 * int(rng.integers(1, 500))
+        m = 4 * int(rng.integers(1, 400)) if c % 2 else int(rng.choice([4, 64, 68, 200, 332, 2000]))
+        k, R, iters = int(rng.integers(1, 17)), int(rng.integers(1, 10)), int(rng.integers(1, 5))
+        X = synth.mixture(n, m, min(k, 4), seed=c, dtype=np.float32)
+        W0, H0 = synth.philox_inits(100 + c, R, n, k, m, dtype=np.float32)
+        ctx.set_X(X)
+        out = []
+        for eng in (2, 4):
+            b = ctx.batch(k, R)
+            b.set_init(W0, H0)
+            ctx.solve([b], nb.default_params(maxiter=iters, engine=eng))
+            g = b.get()
+            out.append((g["W"], g["H"]))
+            b.close()
+        assert relerr(out[0][0], out[1][0]) < 2e-5 and relerr(out[0][1], out[1][1]) < 2e-5, (c, n, m, k, R, iters)
+
+
 def test_tc_generations_agree(ctx, tmp_path):
     """k <= 16 runs the second-generation tcgen05 pass (kl_tiled_tc2.cu); NMFK_TC_GEN=1 selects the first one (kl_tiled_tc.cu), which
     still serves 16 < k <= 32.  Same inputs through both (the first in a child process: the switch is read once per process), ragged
