@@ -45,7 +45,6 @@ struct TcCfg {
     static constexpr int TS = 64;                                     // steps per chunk
     static constexpr int NXS = 3;                                     // X tile stages
     static constexpr int NRAW = 4;                                    // raw V chunk buffers
-    static constexpr bool SWAPK = false;
     static constexpr int NVB = K8 <= 16 ? 4 : 3;                      // V image buffers (shared memory budget for k > 16)
     static constexpr int RPAD = K8 > 24 ? 0 : 4;                      // raw V chunk padding (shared memory budget at K8 = 32)
     static constexpr int QW = TS / 4;                                 // quotient warps: lane quarter = warp % 4, 16 columns each

@@ -12,9 +12,12 @@
 //     three MMA#1 terms) is an image in shared memory.  (All of U in shared memory was tried first: MMA#1 as an smem x smem
 //     instruction reads 6 KB per instruction and ran at half speed.  A single P tile shared by both groups was tried second:
 //     the pulls of P and MMA#1 then alternate strictly and the issuer thread becomes the critical path.)
+//   * TWO threads issue the MMAs (warp 0: MMA#1, warp 1: MMA#2): one thread issuing both spends ~740 clk per unit issuing
+//     (the commit behind the 16 small MMAs of MMA#2 alone costs 75 clk) plus ~450 clk in barrier waits and fences, and was
+//     the critical path of every single-issuer variant;
 //   * X tiles arrive by ONE tensor-map TMA load per chunk (the 64 row-wise bulk copies cost the issuing thread ~2000 clk);
-//   * tensor-memory loads / stores take 300+ clk while MMAs are in flight: the numerators of the previous unit are fetched
-//     behind the stores of Q and consumed one half-division later.
+//   * the numerators of the previous unit are fetched behind the stores of Q and consumed one half-division later.
+// What bounds it now is the quotient stage itself: ~5 quotients per clk per SM however it is scheduled.
 //
 // Tensor-memory map (512 columns): P0 | P1 (64 each), Q0 | Q1 (Qhi 64 + Qlo 64 each), two per-unit numerator buffers of 32, U hi of
 // the 4 restarts of the CTA (16 each).  Warps: 0 = MMA#1 issuer, 1 = MMA#2 issuer + TMA producer, 2-5 = V stagers
@@ -39,7 +42,6 @@ struct Tc2Cfg {
     static constexpr int TS = 64;
     static constexpr int NXS = 3;                                     // X tile stages
     static constexpr int NRAW = 3;                                    // raw V chunk buffers (converting u, u+1 in flight, u+2 issued)
-    static constexpr bool SWAPK = false;
     static constexpr int NVB = 5;                                     // V image buffers: an image lives from MMA#1(u) to MMA#2(u), ~4 units
     static constexpr int RPAD = 4;
     static constexpr int QW = TS / 4;

@@ -15,8 +15,7 @@ constexpr uint32_t TC_LBO = 128;  // leading-dimension byte offset of the canoni
         if (trc != nullptr && (unit) < 64 && lane == 0) trc[((role) * 64 + (unit)) * 8 + (ev)] = clock64(); \
     } while (0)
 
-// C: configuration (TS, NVB, NRAW, SW, K8, V_BYTES, B1_BYTES, B2_BYTES, SBO1, SBO2, RAW_BYTES, RAWP_T, RAWP_A, SWAPK); SWAPK: the
-// MMA#2 image holds step t at K position t ^ 1 (for a quotient stage that leaves pairs of columns swapped; unused); first = thread id of the
+// C: configuration (TS, NVB, NRAW, SW, K8, V_BYTES, B1_BYTES, B2_BYTES, SBO1, SBO2, RAW_BYTES, RAWP_T, RAWP_A); first = thread id of the
 // first stager thread; unit u = chunk * nact + restart slot.
 template <class C, int K8, bool OBJ>
 __device__ __forceinline__ void tc_stager_role(const TiledPassArgs& a, unsigned char* Vs, float* Raw, uint64_t* v_full, uint64_t* v_empty,
@@ -178,13 +177,8 @@ __device__ __forceinline__ void tc_stager_role(const TiledPassArgs& a, unsigned 
                     l[i] = v[q][i] - h[i];
                 }
                 const uint32_t off = offB[q];
-                if (C::SWAPK) {
-                    *reinterpret_cast<float4*>(base + off) = make_float4(h[1], h[0], h[3], h[2]);
-                    *reinterpret_cast<float4*>(base + C::B2_BYTES + off) = make_float4(l[1], l[0], l[3], l[2]);
-                } else {
-                    *reinterpret_cast<float4*>(base + off) = make_float4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<float4*>(base + C::B2_BYTES + off) = make_float4(l[0], l[1], l[2], l[3]);
-                }
+                *reinterpret_cast<float4*>(base + off) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(base + C::B2_BYTES + off) = make_float4(l[0], l[1], l[2], l[3]);
             }
         }
         tc::fence_async_smem();
