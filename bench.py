@@ -573,6 +573,20 @@ def main():
         launches = ctx.launches - l0
         wall_max, solve_max, pm_max = reduce_max([wall, solve, pm])
         launches_all, = reduce_sum([float(launches)])
+        # the strong-scaling anchor of THIS run: rank 0 alone repeats one step with all 256 restarts of every k on its GPU (a
+        # second context without the communicator) while the other ranks wait; outside the timed region
+        n1 = None
+        if rank == 0 and not args.no_also:
+            try:
+                with nb.Context(local_rank) as ctx1:
+                    dt1, ms1, out1 = sweep_step(ctx1, nbdist, torch, Xpin.numpy().T, ks, R, params, 0, 1, lambda: None)
+                    n1 = {"value": out1["total_iters"] / (ms1 * 1e-3), "unit": UNIT, "ms_per_step": ms1, "e2e_value": out1["total_iters"] / dt1,
+                          "restart_iterations_per_step": out1["total_iters"],
+                          "note": "the same step (same X, same 256 x 31 restarts, same iteration budget) on GPU 0 alone, measured in this "
+                                  "run after the timed region, one step without warm-up"}
+            except Exception as e:  # noqa: BLE001
+                n1 = {"error": repr(e)}
+        barrier()
         if rank == 0:
             flops_rank = sum(8.0 * n * m * k * R_local * iters for k in ks) * args.steps  # per GPU, both half-updates
             achieved = flops_rank / (pm_max * 1e-3) / 1e12 if pm_max > 0 else float("nan")
@@ -588,7 +602,8 @@ def main():
                            "sharding": "restarts (nmfk_sweep): 256 / N restarts of every k per GPU; k groups of <= 48 GB of factor stacks",
                            "l2": "inputs larger than L2: X is 1.6 GB (and its transpose); 256 MiB written between steps",
                            "restart_iterations_per_step": its / args.steps, "kopt": kopt, "same_config": True,
-                           "strong_scaling_n1": "bench.py --gpus 1 reports this same step on one GPU under also.C4_strong_n1"},
+                           "strong_scaling_n1": n1 if n1 is not None else
+                           "bench.py --gpus 1 reports this same step on one GPU under also.C4_strong_n1"},
                 "clocks": clocks,
                 "e2e": {"value": its / wall_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": wall_max / args.steps * 1e3,
