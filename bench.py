@@ -576,8 +576,8 @@ def main():
         # the strong-scaling anchor of THIS run: rank 0 alone repeats one step with all 256 restarts of every k on its GPU (a
         # second context without the communicator) while the other ranks wait; outside the timed region
         n1 = None
-        if rank == 0 and not args.no_also:
-            try:
+        if rank == 0 and not args.no_also and args.steps <= 5:  # a long run (the driver's K) is not made 37 s longer: the one-GPU
+            try:                                               # step is also in the N = 1 line (also.C4_strong_n1)
                 with nb.Context(local_rank) as ctx1:
                     dt1, ms1, out1 = sweep_step(ctx1, nbdist, torch, Xpin.numpy().T, ks, R, params, 0, 1, lambda: None)
                     n1 = {"value": out1["total_iters"] / (ms1 * 1e-3), "unit": UNIT, "ms_per_step": ms1, "e2e_value": out1["total_iters"] / dt1,
