@@ -79,3 +79,23 @@ def test_signalorder_matches_oracle():
     W = np.array([[1.0, 1.0, 2.0], [1.0, 1.0, 2.0]])
     H = np.array([[1.0, 1.0], [1.0, 1.0], [3.0, 3.0]])
     assert list(nmfk_b200.signalorder(W, H)) == [2, 0, 1]  # ties keep their order (stable sortperm)
+
+
+def test_julia_shim_ccalls_match_the_header():
+    """The Julia shim cannot run here (no Julia): at least every `ccall` names an exported entry point and passes as many
+    arguments as the header declares (a renamed or re-shaped entry point would otherwise only fail on a user's machine)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "nmfk_b200.h")).read()
+    protos = {}
+    for mm in re.finditer(r"\b(?:int32_t|int64_t|const char\*|void|double)\s+(nmfk_\w+)\s*\(([^;]*?)\)\s*;", hdr, re.S):
+        args = mm.group(2).strip()
+        protos[mm.group(1)] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    jl = open(os.path.join(root, "nmfk.jl_b200", "julia", "NMFkB200", "src", "NMFkB200.jl")).read()
+    calls = list(re.finditer(r"ccall\(\(:(nmfk_\w+),\s*\w+\),\s*\w+,\s*\(([^)]*)\)", jl, re.S))
+    assert len(calls) >= 20
+    for mm in calls:
+        name, types = mm.group(1), mm.group(2).strip()
+        n = 0 if types == "" else len([t for t in types.split(",") if t.strip()])
+        assert name in protos, name
+        assert protos[name] == n, (name, protos[name], n)
