@@ -723,6 +723,7 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
     const int nblkH = (m + ownper - 1) / ownper;  // H-update: own = columns
     const int nblkW = (n + ownper - 1) / ownper;  // W-update: own = rows
     constexpr int TCH = TiledCfg<TX>::TCH;
+    const double slice_gain = getenv("NMFK_TILED_SLICE_GAIN") ? atof(getenv("NMFK_TILED_SLICE_GAIN")) : 0.05;
     auto slices = [&](int nblk, int nred) {
         const long long target = (use_tc ? 3ll * tc_pass_ctas_per_sm(k) : (use_td ? 3ll : 4ll)) * sms;
         long long S = (target + (long long)nblk * units - 1) / ((long long)nblk * units);
@@ -730,14 +731,15 @@ cudaError_t solve_tiled_t(const SolveArgs& a, cudaStream_t s, int64_t* launches)
         if (S > smax) S = smax;
         if (S < 1) S = 1;
         // wave quantisation: one CTA per SM, so a grid of 3.46 waves (C4, 32 restarts per GPU: 16 own blocks x 32) runs as 4.  A few
-        // more slices are worth their combine pass when they fill the last wave (>= 5 % of the launch).
+        // more slices are worth their combine pass when they fill the last wave (>= 5 % of the launch; on C3, 8.54 waves, three
+        // slices would gain 3.6 % of the grid and measured 1.3 % SLOWER with their partial sums and combine pass).
         auto eff = [&](long long s_) {
             const long long ctas = (long long)nblk * units * s_;
             return (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
         };
         long long best = S;
         for (long long s2 = S + 1; s2 <= std::min(smax, S + 3); ++s2)
-            if (eff(s2) > eff(best) + 0.05) best = s2;
+            if (eff(s2) > eff(best) + slice_gain) best = s2;
         return (int)best;
     };
     const int SH = slices(nblkH, n), SW = slices(nblkW, m);
